@@ -1,0 +1,249 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(ctypes -> libtrl_b200.so); the CPU oracle is only the checker.  Integer work: bit-exact."""
+import os
+import types
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from tetris_reinforcement_learning_b200 import synth  # noqa: E402
+from tetris_reinforcement_learning_b200.const import MASK_WORDS, MINOS, POLICY_SHAPE  # noqa: E402
+from tetris_reinforcement_learning_b200.state import (GAME_DTYPE, STEPOUT_DTYPE, games_equal,  # noqa: E402
+                                                      rows_to_grid, unpack_mask)
+
+
+@pytest.fixture(scope="module")
+def mg():
+    from tetris_reinforcement_learning_b200 import move_generation
+    return move_generation
+
+
+@pytest.fixture(scope="module")
+def env():
+    from tetris_reinforcement_learning_b200 import env as e
+    return e
+
+
+def _popcount_rows(mask_bits):
+    return np.unpackbits(mask_bits.view(np.uint8), axis=-1).sum(axis=-1)
+
+
+def _moves_from_mask(mask_row):
+    bits = np.unpackbits(mask_row.view(np.uint8), bitorder="little")
+    return np.flatnonzero(bits)
+
+
+# ------------------------------------------------------------------------------------------
+# movegen
+# ------------------------------------------------------------------------------------------
+
+def test_movegen_reference_vectors(mg, golden_dir):
+    g = np.load(os.path.join(golden_dir, "movegen_golden.npz"))
+    res = mg.movegen_host(g["boards"], g["cur"], g["alt"], want_mask=True, want_moves=True)
+    assert (res["status"] == 0).all()
+    assert np.array_equal(res["mask_bits"], g["mask_bits"])
+    assert np.array_equal(res["n_moves"], _popcount_rows(g["mask_bits"]))
+    for j in range(0, len(g["cur"]), 37):
+        want = _moves_from_mask(g["mask_bits"][j])
+        assert np.array_equal(res["moves"][j, :len(want)], want)  # np.argwhere order (ai.py:1016-1024)
+
+
+def test_movegen_known_answers(mg):
+    """Reference tests.py:23-32 (O, held O, empty board = 9) and SURVEY A.8 empty-board counts."""
+    empty = np.zeros((7, 40), np.uint16)
+    ids = np.arange(7, dtype=np.uint8)
+    res = mg.movegen_host(empty, ids, ids)
+    assert list(res["n_moves"]) == [17, 34, 9, 17, 17, 34, 34]
+
+
+@pytest.mark.parametrize("seed,caves", [(20261018, False), (7, True)])
+def test_movegen_random_sweep_vs_oracle(mg, oracle, seed, caves):
+    boards, cur, alt = synth.movegen_workload(3000, seed=seed, caves=caves)
+    # ragged hold modes: held == current, no active piece, no alt at all
+    cur = cur.copy(); alt = alt.copy()
+    alt[3::11] = cur[3::11]
+    cur[5::13] = 255
+    alt[6::17] = 255
+    want_masks, want_n, want_st, _ = oracle.movegen_batch(boards, cur, alt, n_threads=os.cpu_count() or 1)
+    res = mg.movegen_host(boards, cur, alt, want_mask=True, want_moves=True)
+    assert np.array_equal(res["status"], want_st)
+    bad = np.flatnonzero((res["mask_bits"] != want_masks).any(axis=1))
+    assert bad.size == 0, f"{bad.size} masks differ, first call {bad[:5]}"
+    assert np.array_equal(res["n_moves"], want_n)
+    for j in range(0, boards.shape[0], 501):
+        want = _moves_from_mask(want_masks[j])
+        assert np.array_equal(res["moves"][j, :len(want)], want)
+
+
+def test_movegen_edge_cases(mg, oracle):
+    rows = np.zeros((6, 40), np.uint16)
+    rows[1, :] = 0x3FF & ~1            # everything full except column 0: topped out
+    rows[2, 20:] = 0x3FF & ~(1 << 4)   # well in column 4 reaching above the spawn row
+    rows[3, 18:] = 0x1FF               # column 9 well, spawn row partly covered
+    rows[4, 39] = 0x3FE
+    rows[5, 17:19] = 0x078             # blocks exactly on the spawn cells
+    cur = np.array([255, 4, 4, 6, 2, 0], np.uint8)
+    alt = np.array([255, 6, 0, 4, 2, 3], np.uint8)
+    res = mg.movegen_host(rows, cur, alt)
+    want_masks, want_n, want_st, _ = oracle.movegen_batch(rows, cur, alt)
+    assert np.array_equal(res["mask_bits"], want_masks)
+    assert np.array_equal(res["status"], want_st)
+    assert res["status"][0] & 0x4 and res["n_moves"][0] == 0   # TRL_ST_NO_PIECE
+    empty = mg.movegen_host(np.zeros((0, 40), np.uint16), np.zeros(0, np.uint8), np.zeros(0, np.uint8))
+    assert empty["n_moves"].shape == (0,)
+
+
+def test_movegen_moves_truncation_flag(mg):
+    rows = np.zeros((1, 40), np.uint16)
+    res = mg.movegen_host(rows, np.array([6], np.uint8), np.array([1], np.uint8), want_moves=True, moves_cap=16)
+    assert res["n_moves"][0] == 68 and res["status"][0] & 0x2  # full count reported, list truncated
+
+
+def test_get_move_matrix_dropin(mg, oracle):
+    """The reference-facing call: a duck-typed Player in, bool (27,39,11) out."""
+    boards = synth.random_boards(8, seed=5)
+    for i in range(8):
+        grid = rows_to_grid(boards[i]).astype(object)
+        cur, held, queue = MINOS[i % 7], (MINOS[(i + 3) % 7] if i % 2 else None), [MINOS[(i + 5) % 7]]
+        player = types.SimpleNamespace(
+            board=types.SimpleNamespace(grid=grid), piece=types.SimpleNamespace(type=cur),
+            held_piece=held, queue=types.SimpleNamespace(pieces=queue))
+        got = mg.get_move_matrix(player, algo="convolutional")
+        assert got.shape == POLICY_SHAPE and got.dtype == np.bool_
+        alt = MINOS.index(held) if held else MINOS.index(queue[0])
+        want = oracle.movegen_one(boards[i], MINOS.index(cur), alt)[0]
+        assert np.array_equal(got, want)
+    with pytest.raises(ValueError):
+        mg.get_move_matrix(player, algo="no-such-algo")
+    with pytest.raises(NotImplementedError):
+        mg.get_move_matrix(player, algo="brute-force")
+
+
+def test_movegen_full_size_properties(mg, oracle):
+    """BASELINE config 2 at full size (1M boards x 7 pieces) on device tensors: determinism,
+    n_moves == popcount(mask) == len(move list), and a strided sample against the oracle."""
+    import torch
+    n_boards = int(os.environ.get("TRL_FULL_BOARDS", "1000000"))
+    boards, cur, alt = synth.movegen_workload(n_boards)
+    n = boards.shape[0]
+    dev = torch.device("cuda:0")
+    d_boards = torch.from_numpy(boards.view(np.int16)).to(dev)
+    d_cur, d_alt = torch.from_numpy(cur).to(dev), torch.from_numpy(alt).to(dev)
+    d_mask = torch.empty((n, MASK_WORDS), dtype=torch.int32, device=dev)
+    d_moves = torch.empty((n, 128), dtype=torch.int16, device=dev)
+    d_n = torch.empty(n, dtype=torch.int16, device=dev)
+    d_st = torch.empty(n, dtype=torch.int32, device=dev)
+    mg.movegen_device(d_boards, d_cur, d_alt, d_mask, d_moves, d_n, d_st)
+    torch.cuda.synchronize()
+    assert int((d_st != 0).sum()) == 0
+    # popcount(mask) == n_moves, computed on device in slabs
+    total = 0
+    for lo in range(0, n, 1 << 19):
+        hi = min(n, lo + (1 << 19))
+        m = d_mask[lo:hi]
+        pc = torch.zeros(hi - lo, dtype=torch.int32, device=dev)
+        for b in range(32):
+            pc += (m >> b) & 1
+        assert torch.equal(pc.to(torch.int16), d_n[lo:hi])
+        total += int(pc.sum())
+    checksum1 = int(d_mask.to(torch.int64).sum())
+    # determinism: second run, identical bits
+    d_mask2 = torch.empty_like(d_mask)
+    mg.movegen_device(d_boards, d_cur, d_alt, d_mask2, None, None, None)
+    torch.cuda.synchronize()
+    assert int(d_mask2.to(torch.int64).sum()) == checksum1
+    assert torch.equal(d_mask[::9973], d_mask2[::9973])
+    del d_mask2
+    # strided sample vs oracle (bit-exact) incl. ascending move lists
+    idx = np.arange(0, n, max(1, n // 20000))
+    want_masks, want_n, _, _ = oracle.movegen_batch(boards[idx], cur[idx], alt[idx], n_threads=os.cpu_count() or 1)
+    t_idx = torch.from_numpy(idx).to(dev)
+    got = d_mask[t_idx].cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, want_masks)
+    got_moves = d_moves[t_idx].cpu().numpy().view(np.uint16)
+    for k in range(0, len(idx), 97):
+        want = _moves_from_mask(want_masks[k])
+        assert np.array_equal(got_moves[k, :len(want)], want)
+    assert total > 40 * n_boards  # sanity: tens of placements per call
+
+
+# ------------------------------------------------------------------------------------------
+# env step
+# ------------------------------------------------------------------------------------------
+
+def test_env_reference_transitions(env, golden_dir):
+    g = np.load(os.path.join(golden_dir, "env_golden.npz"))
+    before = g["before"].copy().view(GAME_DTYPE).reshape(-1)
+    after = g["after"].copy().view(GAME_DTYPE).reshape(-1)
+    seed = int(g["seed"])
+    for add_bag in (0, 1):
+        sel = np.flatnonzero(g["add_bag"] == add_bag)
+        games = np.ascontiguousarray(before[sel])
+        out = env.env_step_host(games, g["moves"][sel], bool(add_bag), seed)
+        assert (out["status"] == 0).all()
+        eq = games_equal(games, after[sel])
+        assert eq.all(), f"{(~eq).sum()} transitions differ, first {np.flatnonzero(~eq)[:5]}"
+
+
+def test_game_setup_vs_oracle(env, oracle):
+    got = env.game_setup_host(2048, first_game_id=77, seed=20261018)
+    want = oracle.game_setup(2048, 77, 20261018)
+    assert games_equal(got, want).all()
+
+
+def test_env_selfplay_vs_oracle(env, mg, oracle):
+    """Random legal self-play from setup, GPU movegen + GPU env step vs the oracle, every ply:
+    boards, queues, holds, garbage lists, attack, b2b, combo, top-outs, bag refills."""
+    seed, n = 4242, 512
+    rng = np.random.default_rng(seed)
+    games = env.game_setup_host(n, 0, seed)
+    shadow = oracle.game_setup(n, 0, seed)
+    attacks = clears = 0
+    for ply in range(120):
+        pl = games["players"][np.arange(n), games["turn"]]
+        boards = np.ascontiguousarray(pl["rows"])
+        cur = pl["piece"].copy()
+        alt = np.where(pl["held"] != 255, pl["held"], np.where(pl["qlen"] > 0, pl["queue"][:, 0], 255)).astype(np.uint8)
+        res = mg.movegen_host(boards, cur, alt, want_mask=False, want_moves=True, moves_cap=256)
+        dead = (games["players"]["game_over"].any(axis=1)) | (res["n_moves"] == 0)
+        pick = (rng.random(n) * np.maximum(res["n_moves"], 1)).astype(np.int64)
+        moves = res["moves"][np.arange(n), pick].astype(np.uint16)
+        moves[dead] = 0xFFFF
+        out = env.env_step_host(games, moves, True, seed)
+        want = oracle.env_step(shadow, moves, True, seed)
+        assert np.array_equal(out.view(np.uint8), want.view(np.uint8)), f"step outputs differ at ply {ply}"
+        eq = games_equal(games, shadow)
+        assert eq.all(), f"ply {ply}: {(~eq).sum()} games differ"
+        attacks += int((out["attack"] > 0).sum()); clears += int((out["rows_cleared"] > 0).sum())
+        if dead.all():
+            break
+    assert games["players"]["game_over"].any()  # random play tops out: the terminal path was hit
+
+
+def test_env_device_api_and_skip(env, oracle):
+    import torch
+    seed, n = 9, 300
+    dev = torch.device("cuda:0")
+    d_games = torch.zeros((n, 400), dtype=torch.uint8, device=dev)
+    env.game_setup_device(d_games, first_game_id=5, seed=seed)
+    host = d_games.cpu().numpy().view(GAME_DTYPE).reshape(-1)
+    want = oracle.game_setup(n, 5, seed)
+    assert games_equal(host, want).all()
+    # hard-drop O at the left wall for even games, skip odd games
+    mv = np.full(n, 0xFFFF, np.uint16)
+    from tetris_reinforcement_learning_b200.const import move_to_index
+    legal_any = []
+    for i in range(0, n, 2):
+        m = oracle.movegen_one(want[i]["players"][0]["rows"], int(want[i]["players"][0]["piece"]),
+                               int(want[i]["players"][0]["queue"][0]))[0]
+        mv[i] = np.flatnonzero(m.reshape(-1))[0]
+    d_moves = torch.from_numpy(mv.view(np.int16)).to(dev)
+    d_out = torch.zeros((n, 8), dtype=torch.uint8, device=dev)
+    env.env_step_device(d_games, d_moves, d_out, add_bag=False, seed=seed)
+    torch.cuda.synchronize()
+    got = d_games.cpu().numpy().view(GAME_DTYPE).reshape(-1)
+    exp_out = oracle.env_step(want, mv, False, seed)
+    assert games_equal(got, want).all()
+    assert np.array_equal(d_out.cpu().numpy().view(STEPOUT_DTYPE).reshape(-1).view(np.uint8), exp_out.view(np.uint8))

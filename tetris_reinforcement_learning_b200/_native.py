@@ -1,0 +1,64 @@
+"""ctypes binding of libtrl_b200.so (include/trl.h).
+
+There is NO CPU fallback: if the CUDA library is missing or fails to load, importing this
+module's `lib()` raises.  Build it with `python -m tetris_reinforcement_learning_b200.build`.
+"""
+import ctypes
+import os
+
+from .state import GAME_DTYPE, PLAYER_DTYPE
+
+_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtrl_b200.so")
+_lib = None
+
+ABI_VERSION = 1
+
+c_void_p, c_int, c_u64, c_u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32
+
+# name -> (restype, argtypes); pointers are passed as integers (device or host addresses)
+SIGNATURES = {
+    "trl_abi_version": (c_int, []),
+    "trl_last_error": (ctypes.c_char_p, []),
+    "trl_sizeof_player": (c_int, []),
+    "trl_sizeof_game": (c_int, []),
+    "trl_movegen": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                            c_void_p, c_void_p, c_void_p]),
+    "trl_movegen_games": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "trl_movegen_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                 c_void_p, c_void_p]),
+    "trl_env_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_u64, c_void_p]),
+    "trl_env_step_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_u64]),
+    "trl_game_setup": (c_int, [c_void_p, c_int, c_u32, c_u64, c_void_p]),
+    "trl_game_setup_host": (c_int, [c_void_p, c_int, c_u32, c_u64]),
+}
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libtrl_b200.so once; raise loudly if it is absent or ABI-incompatible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise NativeLibraryError(
+            f"{_SO} not found: the CUDA extension is not built. Run "
+            "`python -m tetris_reinforcement_learning_b200.build` (needs nvcc). There is no CPU fallback.")
+    L = ctypes.CDLL(_SO)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)  # AttributeError if the symbol is missing
+        fn.restype, fn.argtypes = res, args
+    if L.trl_abi_version() != ABI_VERSION:
+        raise NativeLibraryError(f"ABI mismatch: library {L.trl_abi_version()} != binding {ABI_VERSION}")
+    if L.trl_sizeof_player() != PLAYER_DTYPE.itemsize or L.trl_sizeof_game() != GAME_DTYPE.itemsize:
+        raise NativeLibraryError("struct layout mismatch between include/trl.h and state.py")
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().trl_last_error().decode() if rc == -2 else {-1: "bad argument", -3: "out of memory"}.get(rc, "?")
+        raise RuntimeError(f"{what} failed with code {rc}: {msg}")

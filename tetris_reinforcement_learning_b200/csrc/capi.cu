@@ -1,0 +1,44 @@
+// capi.cu — library plumbing of libtrl_b200.so: version, errors, workspace.
+#include <cuda_runtime.h>
+#include <mutex>
+#include <string.h>
+
+#include "trl_common.cuh"
+
+static thread_local char g_err[256] = "";
+static std::mutex g_ws_mutex;
+static void* g_ws_ptr[TRL_WS_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+static size_t g_ws_size[TRL_WS_SLOTS] = {0, 0, 0, 0};
+static cudaStream_t g_host_stream = nullptr;
+
+int trl_check(cudaError_t e) {
+    if (e == cudaSuccess) return TRL_OK;
+    strncpy(g_err, cudaGetErrorString(e), sizeof(g_err) - 1);
+    g_err[sizeof(g_err) - 1] = 0;
+    return TRL_E_CUDA;
+}
+
+void* trl_workspace(int slot, size_t bytes) {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    if (slot < 0 || slot >= TRL_WS_SLOTS) return nullptr;
+    if (g_ws_size[slot] >= bytes && g_ws_ptr[slot]) return g_ws_ptr[slot];
+    if (g_ws_ptr[slot]) { cudaFree(g_ws_ptr[slot]); g_ws_ptr[slot] = nullptr; g_ws_size[slot] = 0; }
+    void* p = nullptr;
+    if (trl_check(cudaMalloc(&p, bytes)) != TRL_OK) return nullptr;
+    g_ws_ptr[slot] = p;
+    g_ws_size[slot] = bytes;
+    return p;
+}
+
+cudaStream_t trl_host_stream() {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    if (!g_host_stream) {
+        if (trl_check(cudaStreamCreateWithFlags(&g_host_stream, cudaStreamNonBlocking)) != TRL_OK) return nullptr;
+    }
+    return g_host_stream;
+}
+
+extern "C" int trl_abi_version(void) { return 1; }
+extern "C" const char* trl_last_error(void) { return g_err; }
+extern "C" int trl_sizeof_player(void) { return (int)sizeof(TrlPlayer); }
+extern "C" int trl_sizeof_game(void) { return (int)sizeof(TrlGame); }
