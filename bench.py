@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the self-play hot path (contract: see DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--boards B]
+
+A "step" is one pass of legal-placement enumeration over BASELINE config 2: B = 1,000,000
+random s2 boards x 7 current pieces with a second (hold) piece = 7,000,000 get_move_matrix
+calls per GPU (weak scaling: every rank owns its own board shard, no collective on the data
+path).  `value` = placements/s with inputs resident in HBM; `e2e` = the same metric through the
+reference-facing C-ABI call with pinned HOST buffers (H2D + kernel + D2H inside the timed region).
+One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_CALL = 80 + 4 + 1448  # board + (cur, alt, pad) in, bit-packed (27,39,11) mask out
+METRIC = "placements/sec (movegen)"
+UNIT = "placements/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_workload(n_boards, rank):
+    from tetris_reinforcement_learning_b200 import synth
+    return synth.movegen_workload(n_boards, seed=synth.DEFAULT_SEED + 1000 * rank)
+
+
+def cpu_baseline(boards, cur, alt, target_s=12.0):
+    """The oracle port (plain C, pthreads over all host cores) on a bounded sample of the workload."""
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    probe = min(boards.shape[0], 7 * 2000)
+    t0 = time.perf_counter()
+    _, _, _, tot = oracle.movegen_batch(boards[:probe], cur[:probe], alt[:probe], n_threads=cores, want_masks=True)
+    dt = time.perf_counter() - t0
+    n = int(min(boards.shape[0], max(probe, probe * target_s / max(dt, 1e-3))))
+    n -= n % 7
+    t0 = time.perf_counter()
+    _, _, _, tot = oracle.movegen_batch(boards[:n], cur[:n], alt[:n], n_threads=cores, want_masks=True)
+    dt = time.perf_counter() - t0
+    return {"value": tot / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {n // 7} boards x 7 pieces ({n} calls, {tot} placements) of the same workload, "
+                      f"{dt:.1f} s, oracle/trl_oracle.c with {cores} pthreads",
+            "python_reference_per_core": 3.7e4,
+            "python_reference_note": "unmodified reference get_move_matrix measured in the build container (SURVEY §6); "
+                                     "it cannot travel to the GPU box"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port
+    (the reference is pure Python and cannot travel to the GPU box), all host threads."""
+    if rank != 0:
+        return
+    from oracle import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    n_boards = args.boards
+    sample_boards = max(1000, min(n_boards, args.ref_sample_boards))
+    boards, cur, alt = make_workload(sample_boards, 0)
+    times, tot = [], 0
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        _, _, _, tot = oracle.movegen_batch(boards, cur, alt, n_threads=cores, want_masks=True)
+        if it >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times))
+    value = tot / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+        "config": {"workload": f"BASELINE config 2 movegen sweep: {n_boards} random s2 boards x 7 pieces with hold "
+                               f"(each CPU step = a bounded sample of {sample_boards} boards x 7)",
+                   "boards": n_boards, "calls_per_step": int(boards.shape[0])},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample_boards} boards x 7 pieces per step, oracle/trl_oracle.c, {cores} pthreads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from tetris_reinforcement_learning_b200 import _native, move_generation
+    from tetris_reinforcement_learning_b200.const import MASK_WORDS
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L = _native.lib()
+
+    boards, cur, alt = make_workload(args.boards, rank)
+    n = boards.shape[0]
+    d_boards = torch.from_numpy(boards.view(np.int16)).to(dev)
+    d_cur, d_alt = torch.from_numpy(cur).to(dev), torch.from_numpy(alt).to(dev)
+    d_mask = torch.empty((n, MASK_WORDS), dtype=torch.int32, device=dev)
+    d_n = torch.empty(n, dtype=torch.int16, device=dev)
+    d_st = torch.empty(n, dtype=torch.int32, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        move_generation.movegen_device(d_boards, d_cur, d_alt, d_mask, None, d_n, d_st)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    placements = int(d_n.to(torch.int64).sum().item())
+    bad_status = int((d_st != 0).sum().item())
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record()
+    barrier()
+    clocks = sampler.stop()
+    kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+
+    # ---- e2e: the reference-facing host call with pinned host buffers ----
+    h_boards = torch.from_numpy(boards.view(np.int16)).pin_memory()
+    h_cur, h_alt = torch.from_numpy(cur).pin_memory(), torch.from_numpy(alt).pin_memory()
+    h_mask = torch.empty((n, MASK_WORDS), dtype=torch.int32).pin_memory()
+    h_n = torch.empty(n, dtype=torch.int16).pin_memory()
+    h_st = torch.empty(n, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        rc = L.trl_movegen_host(h_boards.data_ptr(), h_cur.data_ptr(), h_alt.data_ptr(), n, h_mask.data_ptr(),
+                                None, 0, h_n.data_ptr(), h_st.data_ptr())
+        _native.check(rc, "trl_movegen_host")
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_ok = bool(np.array_equal(h_n.numpy(), d_n.cpu().numpy()))
+    h2d = n * (80 + 2)
+    d2h = n * (MASK_WORDS * 4 + 2 + 4)
+
+    # ---- reduce over ranks: max time, summed work ----
+    stats = torch.tensor([total_ms, e2e_s, float(placements), float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        total_ms, e2e_s, kern_ms = float(mx[0]), float(mx[1]), float(mx[3])
+        placements_all = float(sm[2])
+    else:
+        kern_ms, placements_all = float(np.mean(kernel_ms)), float(placements)
+
+    if rank != 0:
+        return
+    peak, peak_src = load_peaks()
+    achieved = ALGO_BYTES_PER_CALL * n / (kern_ms * 1e-3) / 1e9
+    value = placements_all * args.steps / (total_ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u16", "data": "synthetic",
+        "config": {"workload": f"BASELINE config 2 movegen sweep: {args.boards} random s2 boards x 7 pieces with hold per GPU "
+                               "(3 board families, seed 20261018), ruleset s2, algo convolutional",
+                   "boards_per_gpu": args.boards, "calls_per_step_per_gpu": n,
+                   "placements_per_step_per_gpu": placements, "l2": "inputs+outputs (>10 GB/step) exceed the 126 MB L2",
+                   "status_nonzero": bad_status},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "movegen_thread_kernel",
+                     "algorithmic_bytes_per_call": ALGO_BYTES_PER_CALL, "kernel_ms": kern_ms,
+                     "note": "integer-issue bound, not HBM bound (SURVEY §8d): see profiles/ for issue utilisation"},
+        "e2e": {"value": placements_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "matches_device_run": e2e_ok,
+                "api": "trl_movegen_host (pinned host buffers, bit-packed masks returned to the host)"},
+        "gpu_launches": args.steps,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        line["cpu_baseline"] = cpu_baseline(boards, cur, alt)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--boards", type=int, default=1_000_000, help="boards per GPU (x7 pieces = calls per step)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ref-sample-boards", type=int, default=40_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

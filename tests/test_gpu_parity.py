@@ -137,7 +137,8 @@ def test_movegen_full_size_properties(mg, oracle):
     d_st = torch.empty(n, dtype=torch.int32, device=dev)
     mg.movegen_device(d_boards, d_cur, d_alt, d_mask, d_moves, d_n, d_st)
     torch.cuda.synchronize()
-    assert int((d_st != 0).sum()) == 0
+    assert int(((d_st & ~2) != 0).sum()) == 0          # only TRL_ST_MOVES_TRUNC (cap 128) may be set
+    assert torch.equal((d_st & 2) != 0, d_n > 128)
     # popcount(mask) == n_moves, computed on device in slabs
     total = 0
     for lo in range(0, n, 1 << 19):
@@ -145,15 +146,19 @@ def test_movegen_full_size_properties(mg, oracle):
         m = d_mask[lo:hi]
         pc = torch.zeros(hi - lo, dtype=torch.int32, device=dev)
         for b in range(32):
-            pc += (m >> b) & 1
+            pc += ((m >> b) & 1).sum(dim=1, dtype=torch.int32)
         assert torch.equal(pc.to(torch.int16), d_n[lo:hi])
         total += int(pc.sum())
-    checksum1 = int(d_mask.to(torch.int64).sum())
+
+    def checksum(t):
+        return sum(int(t[lo:lo + (1 << 19)].sum(dtype=torch.int64)) for lo in range(0, n, 1 << 19))
+
+    checksum1 = checksum(d_mask)
     # determinism: second run, identical bits
     d_mask2 = torch.empty_like(d_mask)
     mg.movegen_device(d_boards, d_cur, d_alt, d_mask2, None, None, None)
     torch.cuda.synchronize()
-    assert int(d_mask2.to(torch.int64).sum()) == checksum1
+    assert checksum(d_mask2) == checksum1
     assert torch.equal(d_mask[::9973], d_mask2[::9973])
     del d_mask2
     # strided sample vs oracle (bit-exact) incl. ascending move lists
@@ -164,7 +169,7 @@ def test_movegen_full_size_properties(mg, oracle):
     assert np.array_equal(got, want_masks)
     got_moves = d_moves[t_idx].cpu().numpy().view(np.uint16)
     for k in range(0, len(idx), 97):
-        want = _moves_from_mask(want_masks[k])
+        want = _moves_from_mask(want_masks[k])[:128]
         assert np.array_equal(got_moves[k, :len(want)], want)
     assert total > 40 * n_boards  # sanity: tens of placements per call
 

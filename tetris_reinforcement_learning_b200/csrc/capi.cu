@@ -9,7 +9,7 @@ static thread_local char g_err[256] = "";
 static std::mutex g_ws_mutex;
 static void* g_ws_ptr[TRL_WS_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
 static size_t g_ws_size[TRL_WS_SLOTS] = {0, 0, 0, 0};
-static cudaStream_t g_host_stream = nullptr;
+static cudaStream_t g_host_stream[2] = {nullptr, nullptr};
 
 int trl_check(cudaError_t e) {
     if (e == cudaSuccess) return TRL_OK;
@@ -30,12 +30,13 @@ void* trl_workspace(int slot, size_t bytes) {
     return p;
 }
 
-cudaStream_t trl_host_stream() {
+cudaStream_t trl_host_stream(int which) {
     std::lock_guard<std::mutex> lock(g_ws_mutex);
-    if (!g_host_stream) {
-        if (trl_check(cudaStreamCreateWithFlags(&g_host_stream, cudaStreamNonBlocking)) != TRL_OK) return nullptr;
+    which &= 1;
+    if (!g_host_stream[which]) {
+        if (trl_check(cudaStreamCreateWithFlags(&g_host_stream[which], cudaStreamNonBlocking)) != TRL_OK) return nullptr;
     }
-    return g_host_stream;
+    return g_host_stream[which];
 }
 
 extern "C" int trl_abi_version(void) { return 1; }

@@ -258,18 +258,27 @@ extern "C" int trl_movegen_games(const TrlGame* games, int n, uint32_t* mask_bit
 extern "C" int trl_movegen_host(const uint16_t* boards, const uint8_t* cur, const uint8_t* alt, int n,
                                 uint32_t* mask_bits, uint16_t* moves, int moves_cap, uint16_t* n_moves,
                                 uint32_t* status) {
-    if (n < 0 || !boards || !cur || !alt) return TRL_E_ARG;
+    if (n < 0 || !boards || !cur || !alt || (moves && moves_cap <= 0)) return TRL_E_ARG;
     if (n == 0) return TRL_OK;
-    cudaStream_t s = trl_host_stream();
-    if (!s) return TRL_E_CUDA;
-    // chunked so that the staging workspace stays bounded for multi-million-call sweeps
-    const int chunk = 1 << 18;
-    size_t per = TRL_ROWS * 2 + 2 + TRL_MASK_WORDS * 4 + (moves ? (size_t)moves_cap * 2 : 0) + 2 + 4;
-    char* ws = (char*)trl_workspace(TRL_WS_HOST_STAGE, per * (size_t)(n < chunk ? n : chunk) + 256);
+    // Chunked and double-buffered over two streams: with pinned host buffers the H2D / D2H
+    // copies of one chunk overlap the kernel of the other; the staging workspace stays bounded
+    // for multi-million-call sweeps.
+    const int chunk = 1 << 17;
+    const size_t per = TRL_ROWS * 2 + 2 + TRL_MASK_WORDS * 4 + (moves ? (size_t)moves_cap * 2 : 0) + 2 + 4;
+    const int cmax = n < chunk ? n : chunk;
+    const size_t half = (per * (size_t)cmax + 255) & ~(size_t)255;
+    char* ws = (char*)trl_workspace(TRL_WS_HOST_STAGE, 2 * half);
     if (!ws) return TRL_E_NOMEM;
-    for (int off = 0; off < n; off += chunk) {
-        int m = (n - off < chunk) ? n - off : chunk;
-        char* p = ws;
+    cudaStream_t st[2] = {trl_host_stream(0), trl_host_stream(1)};
+    if (!st[0] || !st[1]) return TRL_E_CUDA;
+    int rc = TRL_OK;
+    int c = 0;
+    for (int off = 0; off < n && !rc; off += chunk, ++c) {
+        const int m = (n - off < chunk) ? n - off : chunk;
+        cudaStream_t s = st[c & 1];
+        rc = trl_check(cudaStreamSynchronize(s));  // this half's previous chunk has fully drained
+        if (rc) break;
+        char* p = ws + (size_t)(c & 1) * half;
         uint32_t* d_mask = (uint32_t*)p;  p += (size_t)m * TRL_MASK_WORDS * 4;
         uint32_t* d_status = (uint32_t*)p; p += (size_t)m * 4;
         uint16_t* d_boards = (uint16_t*)p; p += (size_t)m * TRL_ROWS * 2;
@@ -278,7 +287,7 @@ extern "C" int trl_movegen_host(const uint16_t* boards, const uint8_t* cur, cons
         uint16_t* d_nm = (uint16_t*)p; p += (size_t)m * 2;
         uint8_t* d_cur = (uint8_t*)p; p += m;
         uint8_t* d_alt = (uint8_t*)p; p += m;
-        int rc = trl_check(cudaMemcpyAsync(d_boards, boards + (size_t)off * TRL_ROWS, (size_t)m * TRL_ROWS * 2, cudaMemcpyHostToDevice, s));
+        rc = trl_check(cudaMemcpyAsync(d_boards, boards + (size_t)off * TRL_ROWS, (size_t)m * TRL_ROWS * 2, cudaMemcpyHostToDevice, s));
         if (!rc) rc = trl_check(cudaMemcpyAsync(d_cur, cur + off, m, cudaMemcpyHostToDevice, s));
         if (!rc) rc = trl_check(cudaMemcpyAsync(d_alt, alt + off, m, cudaMemcpyHostToDevice, s));
         if (!rc) rc = launch_movegen(d_boards, d_cur, d_alt, nullptr, m, d_mask, d_moves, moves_cap, d_nm, d_status, s);
@@ -286,8 +295,8 @@ extern "C" int trl_movegen_host(const uint16_t* boards, const uint8_t* cur, cons
         if (!rc && moves) rc = trl_check(cudaMemcpyAsync(moves + (size_t)off * moves_cap, d_moves, (size_t)m * moves_cap * 2, cudaMemcpyDeviceToHost, s));
         if (!rc && n_moves) rc = trl_check(cudaMemcpyAsync(n_moves + off, d_nm, (size_t)m * 2, cudaMemcpyDeviceToHost, s));
         if (!rc && status) rc = trl_check(cudaMemcpyAsync(status + off, d_status, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
-        if (!rc) rc = trl_check(cudaStreamSynchronize(s));
-        if (rc) return rc;
     }
-    return TRL_OK;
+    int rc0 = trl_check(cudaStreamSynchronize(st[0]));
+    int rc1 = trl_check(cudaStreamSynchronize(st[1]));
+    return rc ? rc : (rc0 ? rc0 : rc1);
 }

@@ -12,5 +12,5 @@ int trl_check(cudaError_t e);
 enum TrlWorkspaceSlot { TRL_WS_MOVEGEN_MASK = 0, TRL_WS_HOST_STAGE = 1, TRL_WS_SLOTS = 4 };
 void* trl_workspace(int slot, size_t bytes);
 
-// Stream used by the *_host entry points (created on first use, non-blocking).
-cudaStream_t trl_host_stream();
+// Streams (0 or 1) used by the *_host entry points (created on first use, non-blocking).
+cudaStream_t trl_host_stream(int which = 0);

@@ -21,47 +21,53 @@ def _pack(occ):
     return (occ.astype(np.uint16) * w).sum(axis=-1).astype(np.uint16)
 
 
-def random_boards(n, seed=DEFAULT_SEED, caves=False):
-    """-> uint16[n, 40] bitrow boards."""
-    rng = np.random.default_rng(seed)
+CHUNK = 16384  # boards are generated in fixed chunks so that any n is a prefix of the same stream
+
+
+def _random_chunk(rng, n, caves):
     nfam = 4 if caves else 3
     fam = np.arange(n) % nfam
     occ = np.zeros((n, ROWS, COLS), dtype=bool)
     row_idx = np.arange(ROWS)[None, :, None]  # 0 = top
 
-    # F0
-    idx = np.nonzero(fam == 0)[0]
-    if idx.size:
-        h = rng.integers(0, 16, size=(idx.size, 1, COLS))
-        fill = rng.random((idx.size, ROWS, COLS)) < 0.85
-        occ[idx] = (row_idx >= ROWS - h) & fill
-    # F1
-    idx = np.nonzero(fam == 1)[0]
-    if idx.size:
-        g = rng.integers(0, 14, size=(idx.size, 1, 1))
-        hole = rng.integers(0, COLS, size=(idx.size, ROWS, 1))
-        garbage = (row_idx >= ROWS - g) & (np.arange(COLS)[None, None, :] != hole)
-        junk_rows = (row_idx >= ROWS - g - 4) & (row_idx < ROWS - g)
-        junk = junk_rows & (rng.random((idx.size, ROWS, COLS)) < 0.4)
-        occ[idx] = garbage | junk
-    # F2
-    idx = np.nonzero(fam == 2)[0]
-    if idx.size:
-        k = rng.integers(1, 18, size=(idx.size, 1, 1))
-        occ[idx] = (row_idx >= ROWS - k) & (rng.random((idx.size, ROWS, COLS)) < 0.5)
-    # F3
-    if caves:
+    idx = np.nonzero(fam == 0)[0]  # F0
+    h = rng.integers(0, 16, size=(idx.size, 1, COLS))
+    fill = rng.random((idx.size, ROWS, COLS), dtype=np.float32) < 0.85
+    occ[idx] = (row_idx >= ROWS - h) & fill
+
+    idx = np.nonzero(fam == 1)[0]  # F1
+    g = rng.integers(0, 14, size=(idx.size, 1, 1))
+    hole = rng.integers(0, COLS, size=(idx.size, ROWS, 1))
+    garbage = (row_idx >= ROWS - g) & (np.arange(COLS)[None, None, :] != hole)
+    junk_rows = (row_idx >= ROWS - g - 4) & (row_idx < ROWS - g)
+    junk = junk_rows & (rng.random((idx.size, ROWS, COLS), dtype=np.float32) < 0.4)
+    occ[idx] = garbage | junk
+
+    idx = np.nonzero(fam == 2)[0]  # F2
+    k = rng.integers(1, 18, size=(idx.size, 1, 1))
+    occ[idx] = (row_idx >= ROWS - k) & (rng.random((idx.size, ROWS, COLS), dtype=np.float32) < 0.5)
+
+    if caves:  # F3
         idx = np.nonzero(fam == 3)[0]
-        if idx.size:
-            k = rng.integers(6, 22, size=(idx.size, 1, 1))
-            p = rng.uniform(0.15, 0.45, size=(idx.size, 1, 1))
-            occ[idx] = (row_idx >= ROWS - k) & (rng.random((idx.size, ROWS, COLS)) < p)
+        k = rng.integers(6, 22, size=(idx.size, 1, 1))
+        p = rng.uniform(0.15, 0.45, size=(idx.size, 1, 1))
+        occ[idx] = (row_idx >= ROWS - k) & (rng.random((idx.size, ROWS, COLS), dtype=np.float32) < p)
 
     full = occ.all(axis=2)
     if full.any():
         bi, ri = np.nonzero(full)
         occ[bi, ri, rng.integers(0, COLS, size=bi.size)] = False
     return _pack(occ)
+
+
+def random_boards(n, seed=DEFAULT_SEED, caves=False):
+    """-> uint16[n, 40] bitrow boards; board i depends only on (seed, caves, i)."""
+    out = np.empty((n, ROWS), dtype=np.uint16)
+    for c, lo in enumerate(range(0, n, CHUNK)):
+        rng = np.random.default_rng([int(seed), c, int(caves)])
+        hi = min(n, lo + CHUNK)
+        out[lo:hi] = _random_chunk(rng, CHUNK, caves)[: hi - lo]
+    return out
 
 
 def movegen_workload(n_boards, seed=DEFAULT_SEED, caves=False, hold_shift=None):
