@@ -179,6 +179,139 @@ int trl_env_step_host(TrlGame* games, const uint16_t* moves, int n, TrlStepOut* 
 int trl_game_setup(TrlGame* games, int n, uint32_t first_game_id, uint64_t seed, void* stream);
 int trl_game_setup_host(TrlGame* games, int n, uint32_t first_game_id, uint64_t seed);
 
+/* ------------------------------------------------------------------------------------ */
+/* network input encoding                                                                */
+/* replaces ai.game_to_X + get_grids/get_pieces/get_stat/get_garbage/simplify_grid        */
+/*   (ai.py:1364-1413) and the tensor stacking of BatchedEvaluator._dispatch (ai.py:724-731) */
+/* ------------------------------------------------------------------------------------ */
+
+/*
+ * games  [*] TrlGame; item i encodes games[index ? index[i] : i]
+ * grids  [2n][400]  OUT rows 0..n-1: grid of the side to move, rows n..2n-1: opponent (0/1)
+ * extras [n][105]   OUT a_pieces(49) a_b2b a_combo a_garbage o_pieces(49) o_b2b o_combo
+ *                       o_garbage color  — the non-grid inputs in torch.cat order
+ *                       (architectures.py:128-140)
+ * dtype  0 = float32, 1 = bfloat16
+ */
+int trl_encode_features(const TrlGame* games, const int32_t* index, int n, void* grids,
+                        void* extras, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* search (MCTS / PUCT) and the self-play episode                                         */
+/* replaces ai.MCTS / amcts (ai.py:299-659, 766-996), MCTSNode/MCTSTree/NodeState         */
+/*   (ai.py:237-297), get_move_list (ai.py:1016-1024), the policy clamp + root softmax +   */
+/*   normalisation (ai.py:411-443), search_statistics' visit counts (ai.py:1330-1361) and  */
+/*   the per-move part of play_game (ai.py:1610-1668: search -> record -> make_move).      */
+/* The tree lives in HBM as struct-of-arrays; one warp per game; one leaf per game per     */
+/* step (exactly the reference's BatchedEvaluator shape, ai.py:670-742).                   */
+/* ------------------------------------------------------------------------------------ */
+
+#define TRL_SAMPLE_MOVES 512
+
+/* Config's search fields (ai.py:97-137), doubles where the reference computes in float64. */
+typedef struct TrlSearchParams {
+    uint64_t seed;
+    double cpuct, dpuct;               /* CPUCT, DPUCT                                     */
+    double fpu_value;                  /* FpuValue                                         */
+    double root_softmax_temp;          /* RootSoftmaxTemp                                  */
+    double temperature;                /* temperature (used only when training)            */
+    double playout_cap_chance;         /* playout_cap_chance                               */
+    double dirichlet_alpha, dirichlet_s, dirichlet_eps; /* DIRICHLET_ALPHA / _S / _EXPLORATION */
+    double c_forced;                   /* CForcedPlayout                                   */
+    int32_t max_iter;                  /* MAX_ITER                                         */
+    int32_t iters_long, iters_short;   /* playout-cap iteration counts (ai.py:323-330)     */
+    int32_t fpu_reduction;             /* FpuStrategy == 'reduction' (else 'absolute')     */
+    int32_t use_root_softmax;
+    int32_t training;
+    int32_t use_playout_cap;           /* use_playout_cap_randomization                    */
+    int32_t use_noise;                 /* use_dirichlet_noise                              */
+    int32_t use_dirichlet_s;
+    int32_t use_forced;                /* use_forced_playouts_and_policy_target_pruning    */
+    int32_t use_tanh;
+    int32_t save_all;
+    int32_t max_rounds;                /* MAX_MOVES = 1000 (const.py:12)                   */
+    int32_t restart_finished;          /* != 0: a finished game is replaced by a fresh one */
+    uint32_t game_id_stride;           /* new game id = previous id + stride (ranks interleave) */
+    int32_t pad_;
+} TrlSearchParams;
+
+/* Per-game search control block. */
+typedef struct TrlSearchCtl {
+    int32_t iter;                      /* iterations done in the running search (0 = not started) */
+    int32_t max_iter;                  /* iteration budget of the running search           */
+    int32_t n_nodes, n_states;
+    int32_t leaf;                      /* node selected in this step                       */
+    int32_t leaf_kind;                 /* 0 expand, 1 evaluate only (no_move), 2 terminal, 3 idle */
+    uint32_t search_no;                /* searches finished in this game (= plies played)  */
+    uint32_t garbage_ctr;              /* sequential garbage draws inside the running search */
+    uint32_t status;                   /* sticky TRL_ST_* bits                             */
+    uint32_t fast;                     /* playout-cap short search: no noise, not saved    */
+    uint32_t active;                   /* 0 = slot parked (game over and no restart)       */
+    uint32_t games_finished;
+    uint64_t sims;                     /* simulations run in this slot                     */
+    int32_t lines_sent0, lines_cleared0; /* player 0 totals of the running game (ai.py:1518-1529) */
+    double leaf_value;                 /* value of a terminal leaf                         */
+    int32_t max_depth, pad_;
+} TrlSearchCtl;
+
+/* One finished search = one training position before augmentation (ai.py:1611-1666). */
+typedef struct TrlSample {
+    uint32_t game_id;
+    uint16_t search_no;
+    uint8_t turn;                      /* side to move = owner of the sample                */
+    uint8_t saved;                     /* reference `save` flag (False for fast searches)   */
+    uint16_t n_children;
+    uint16_t chosen_move;
+    uint32_t total_visits;             /* sum of post-prune visits                          */
+    int32_t iterations;
+    TrlGame state;                     /* position searched (queues cut to 5 previews)      */
+    uint16_t moves[TRL_SAMPLE_MOVES];  /* root children in creation (argwhere) order        */
+    uint16_t visits[TRL_SAMPLE_MOVES]; /* post-prune visit counts                           */
+    uint16_t visits_pre[TRL_SAMPLE_MOVES]; /* pre-prune visit counts                        */
+} TrlSample;
+
+/* One finished game (ai.py:1675-1699). */
+typedef struct TrlGameEnd {
+    uint32_t game_id;
+    int32_t winner;                    /* 0 / 1, -1 = draw (MAX_MOVES reached)              */
+    uint32_t plies;
+    uint32_t rounds;
+    int32_t pieces0, lines_sent0, lines_cleared0, pad_;
+} TrlGameEnd;
+
+/* All device buffers of a search batch; caller-allocated (sizes in elements). */
+typedef struct TrlSearchBuffers {
+    int32_t n_games, node_cap, state_cap, moves_cap, sample_cap, end_cap, pad0_, pad1_;
+    /* tree, per node [n_games * node_cap] */
+    double* prior; double* value_sum; int32_t* visits; int32_t* parent; int32_t* slot; uint16_t* move;
+    /* per materialised state [n_games * state_cap] */
+    TrlGame* states; int32_t* first_child; int32_t* n_children; double* fpu;
+    /* per game [n_games] */
+    TrlSearchCtl* ctl; TrlGame* games; int32_t* leaf_state;
+    uint16_t* legal; uint16_t* n_legal;      /* [n_games * moves_cap], [n_games]            */
+    /* outputs */
+    TrlSample* samples; uint32_t* sample_count; TrlGameEnd* ends; uint32_t* end_count;
+    uint32_t* next_game_id;                  /* [1] id given to the next restarted game     */
+    const double* noise_override;            /* [n_games * moves_cap] or NULL (tests)       */
+} TrlSearchBuffers;
+
+int trl_sizeof_search_ctl(void);
+int trl_sizeof_sample(void);
+
+/* Step part 1: (start a search if needed,) select a leaf per game and materialise its state;
+ * writes leaf_state[g] = index into `states` of the position the net must evaluate, or -1. */
+int trl_search_select(const TrlSearchBuffers* buf, const TrlSearchParams* prm, void* stream);
+
+/* Legal placements for the selected leaves: trl_movegen_games on states[leaf_state[g]]. */
+int trl_search_movegen(const TrlSearchBuffers* buf, void* stream);
+
+/* Step part 2: expand the leaf with the network outputs (values [n_games], logits
+ * [n_games][11583]; dtype 0 = float32, 1 = bfloat16), root noise, backup, FPU refresh; when a
+ * search has used its iteration budget: choose the move, prune, emit the sample, play the move
+ * on the real game, emit the game end and restart. */
+int trl_search_expand(const TrlSearchBuffers* buf, const TrlSearchParams* prm, const void* values,
+                      const void* logits, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -132,10 +132,48 @@ def gen_env(n_games=260, plies=40):
     print("env_golden:", len(moves), "transitions", stats)
 
 
+def gen_mcts(n_searches=24, iters=48):
+    """mcts_golden.npz: reference ai.MCTS outputs under the fake evaluator and the Philox tape."""
+    from oracle import features_oracle, mcts_oracle
+    from oracle.pin_mcts_against_reference import config_families, positions, tanh_wrap
+    m = rh.full_modules()
+    fams = config_families(m.ai, iters)
+    pos = positions(40, SEED)
+    recs, fam_idx, moves, saves, n_nodes, root_q = [], [], [], [], [], []
+    child_moves = np.full((n_searches, 512), 0xFFFF, np.uint16)
+    child_visits = np.zeros((n_searches, 512), np.int32)
+    child_priors = np.zeros((n_searches, 512), np.float64)
+    n_children = np.zeros(n_searches, np.int32)
+    for k in range(n_searches):
+        rec = pos[k % len(pos)]
+        name, cfg = fams[k % len(fams)]
+        ev = tanh_wrap(features_oracle.fake_evaluate) if cfg.use_tanh else features_oracle.fake_evaluate
+        r = rh.reference_mcts(cfg, rec[0], ev, mcts_oracle.SearchTape(SEED, int(rec[0]["game_id"]), k))
+        c = len(r["moves"])
+        recs.append(rec.copy()); fam_idx.append(k % len(fams)); moves.append(r["move"]); saves.append(int(r["save"]))
+        n_nodes.append(r["n_nodes"]); root_q.append(r["root_value_avg"]); n_children[k] = c
+        child_moves[k, :c] = r["moves"]; child_visits[k, :c] = r["visits_post"]; child_priors[k, :c] = r["priors"]
+    recs = np.concatenate(recs)
+    np.savez_compressed(os.path.join(OUT, "mcts_golden.npz"),
+                        games=recs.view(np.uint8).reshape(len(recs), -1), family=np.array(fam_idx, np.int32),
+                        family_names=np.array([f[0] for f in fams]), iters=iters, seed=SEED,
+                        move=np.array(moves, np.int32), save=np.array(saves, np.uint8),
+                        n_nodes=np.array(n_nodes, np.int32), root_value_avg=np.array(root_q, np.float64),
+                        n_children=n_children, child_moves=child_moves, child_visits=child_visits,
+                        child_priors=child_priors)
+    print("mcts_golden:", n_searches, "searches x", iters, "iterations")
+
+
 if __name__ == "__main__":
     if not rh.available():
         sys.exit("reference checkout not available")
     os.makedirs(OUT, exist_ok=True)
-    gen_movegen()
-    gen_attack()
-    gen_env()
+    which = sys.argv[1:] or ["movegen", "attack", "env", "mcts"]
+    if "movegen" in which:
+        gen_movegen()
+    if "attack" in which:
+        gen_attack()
+    if "env" in which:
+        gen_env()
+    if "mcts" in which:
+        gen_mcts()

@@ -46,9 +46,16 @@ def lib():
         L.trl_oracle_game_setup_batch.restype = None
         L.trl_oracle_game_setup_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64]
         L.trl_oracle_garbage_column.restype = ctypes.c_int
-        L.trl_oracle_garbage_column.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32]
+        L.trl_oracle_garbage_column.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
+        L.trl_oracle_env_step_rng.restype = None
+        L.trl_oracle_env_step_rng.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32,
+                                              u32p, ctypes.c_void_p]
         L.trl_oracle_generate_bag.restype = None
         L.trl_oracle_generate_bag.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, u8p]
+        L.trl_oracle_uniform.restype = ctypes.c_double
+        L.trl_oracle_uniform.argtypes = [ctypes.c_uint64] + [ctypes.c_uint32] * 4
+        L.trl_oracle_gamma.restype = ctypes.c_double
+        L.trl_oracle_gamma.argtypes = [ctypes.c_uint64] + [ctypes.c_uint32] * 3 + [ctypes.c_double]
         L.trl_oracle_philox.restype = None
         L.trl_oracle_philox.argtypes = [ctypes.c_uint64] + [ctypes.c_uint32] * 4 + [u32p]
         _lib = L
@@ -112,8 +119,19 @@ def game_setup(n, first_game_id, seed):
     return games
 
 
-def garbage_column(seed, game_id, ctr):
-    return lib().trl_oracle_garbage_column(int(seed), int(game_id), int(ctr))
+def garbage_column(seed, game_id, ctr, stream=0):
+    return lib().trl_oracle_garbage_column(int(seed), int(game_id), int(stream), int(ctr))
+
+
+def env_step_rng(game, move, add_bag, seed, stream, ctr):
+    """One game (GAME_DTYPE array of length 1) stepped with an explicit garbage-RNG stream and
+    counter; returns (STEPOUT record, new counter)."""
+    assert game.dtype == GAME_DTYPE and game.shape == (1,)
+    out = np.zeros(1, dtype=STEPOUT_DTYPE)
+    c = ctypes.c_uint32(int(ctr))
+    lib().trl_oracle_env_step_rng(game.ctypes.data, int(move), int(bool(add_bag)), int(seed), int(stream),
+                                  ctypes.byref(c), out.ctypes.data)
+    return out[0], c.value
 
 
 def generate_bag(seed, game_id, bag_ctr, player):
@@ -126,3 +144,11 @@ def philox(seed, c0, c1, c2, c3):
     out = np.zeros(4, dtype=np.uint32)
     lib().trl_oracle_philox(int(seed), int(c0), int(c1), int(c2), int(c3), _p(out, ctypes.c_uint32))
     return out
+
+
+def uniform(seed, game_id, search_no, purpose, idx=0):
+    return lib().trl_oracle_uniform(int(seed), int(game_id), int(search_no), int(purpose), int(idx))
+
+
+def gamma(seed, game_id, search_no, child, alpha):
+    return lib().trl_oracle_gamma(int(seed), int(game_id), int(search_no), int(child), float(alpha))

@@ -51,6 +51,57 @@ def modules():
     return _mods
 
 
+class _Dummy:
+    """Callable, attribute-able stand-in for anything reached inside a stubbed package."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __call__(self, *a, **k):
+        return _Dummy()
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Dummy()
+
+
+class _DummyModule(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Dummy()
+
+
+_full = None
+
+
+def full_modules(workdir="/tmp/trl_ref_work"):
+    """Import ALL of the reference incl. ai.py / architectures.py (MCTS, play_game, networks).
+
+    SURVEY §8c recipe: permissive dummies for pygame / tensorflow / keras / matplotlib, ujson ->
+    stdlib json, and a cwd whose parent holds a `Storage/` directory (ai.py:57-59 mkdirs
+    `Storage/logs` at import time).  NOTE: changes the process cwd to `workdir`/run."""
+    global _full
+    if _full is not None:
+        return _full
+    m = modules()
+    import json
+    for name in ("tensorflow", "tensorflow.keras", "tensorflow.python", "tensorflow.python.ops",
+                 "tensorflow.python.ops.math_ops", "keras", "keras.backend", "matplotlib", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            sys.modules[name] = _DummyModule(name)
+    sys.modules.setdefault("ujson", json)
+    os.makedirs(os.path.join(workdir, "Storage"), exist_ok=True)
+    os.makedirs(os.path.join(workdir, "run"), exist_ok=True)
+    os.chdir(os.path.join(workdir, "run"))
+    import ai
+    import architectures
+    m.ai, m.architectures = ai, architectures
+    _full = m
+    return m
+
+
 # ---------------------------------------------------------------------------------------
 # tape RNG: the reference's `random` draws replaced by the same Philox streams the oracle
 # and the CUDA kernels use (SURVEY A.7)
@@ -67,13 +118,15 @@ class TapeRandom:
         self.rng_ctr = 0
         self.bag_ctr = 0
         self._bag_player = 0
+        self.stream = 0
 
-    def bind(self, game_id, rng_ctr, bag_ctr):
+    def bind(self, game_id, rng_ctr, bag_ctr, stream=0):
         self.game_id, self.rng_ctr, self.bag_ctr, self._bag_player = game_id, rng_ctr, bag_ctr, 0
+        self.stream = stream
 
     def randint(self, a, b):  # player.py:185
         assert (a, b) == (0, 9)
-        col = self._o.garbage_column(self.seed, self.game_id, self.rng_ctr)
+        col = self._o.garbage_column(self.seed, self.game_id, self.rng_ctr, self.stream)
         self.rng_ctr += 1
         return col
 
@@ -190,3 +243,90 @@ def fixture_boards():
                 out[name] = grid_to_rows(np.vstack([pad, arr]))
                 break
     return out
+
+
+# ---------------------------------------------------------------------------------------
+# driving the reference's MCTS with an injected evaluator and tape RNG
+# ---------------------------------------------------------------------------------------
+
+class _AiRandomShim:
+    """Stands in for the `random` module inside ai.py: random() is the playout-cap coin
+    (ai.py:324); choices() restates CPython's random.choices with the tape's single uniform."""
+
+    def __init__(self, tape):
+        self.tape = tape
+
+    def random(self):
+        return self.tape.coin()
+
+    def choices(self, population, weights=None, k=1):
+        from bisect import bisect
+        from oracle.mcts_oracle import _accumulate
+        cum = _accumulate(weights)
+        total = cum[-1] + 0.0
+        return [population[bisect(cum, self.tape.choice_uniform() * total, 0, len(population) - 1)]]
+
+
+class _NumpyProxy:
+    """numpy with random.gamma redirected to the tape (ai.py:489)."""
+
+    def __init__(self, tape):
+        import numpy
+        self._np = numpy
+        self.random = types.SimpleNamespace(gamma=lambda shape, scale, size: tape.gamma(shape, size))
+
+    def __getattr__(self, name):
+        return getattr(self._np, name)
+
+
+class _SearchGarbageShim:
+    """`random` inside player.py during a search: sequential draws from the search stream."""
+
+    def __init__(self, tape):
+        self.tape = tape
+
+    def randint(self, a, b):
+        from oracle import oracle
+        col = oracle.garbage_column(self.tape.seed, self.tape.game_id, self.tape.garbage_ctr, self.tape.garbage_stream)
+        self.tape.garbage_ctr += 1
+        return col
+
+
+def reference_mcts(config, game_rec, evaluate, tape):
+    """Run the reference's own MCTS (ai.py:299-659) from a packed game with `evaluate(rec)` as
+    the network and `tape` (oracle.mcts_oracle.SearchTape) as every RNG.  Returns the same
+    dict layout as mcts_oracle.search (without pre-prune visits)."""
+    from tetris_reinforcement_learning_b200.const import move_to_index
+    from tetris_reinforcement_learning_b200.state import GAME_DTYPE, pack_game
+    m = full_modules()
+    ai = m.ai
+    game = make_game(game_rec)
+
+    def evaluate_hook(cfg, g, net):
+        rec = np.zeros((), dtype=GAME_DTYPE)
+        pack_game(g, out=rec)
+        return evaluate(rec)
+
+    saved = (ai.evaluate, ai.random, ai.np, m.player.random)
+    ai.evaluate, ai.random, ai.np = evaluate_hook, _AiRandomShim(tape), _NumpyProxy(tape)
+    m.player.random = _SearchGarbageShim(tape)
+    try:
+        move, tree, save = ai.MCTS(config, game, None)
+    finally:
+        ai.evaluate, ai.random, ai.np, m.player.random = saved
+    root = tree.get_node("root")
+    kids = [tree.get_node(c).data for c in root.successors(tree.identifier)]
+    return {"move": move_to_index(move), "moves": [move_to_index(k.move) for k in kids],
+            "visits_post": [int(k.visit_count) for k in kids], "priors": [float(k.policy) for k in kids],
+            "save": bool(save), "n_nodes": tree._counter + 1, "root_visits": int(root.data.visit_count),
+            "root_value_avg": float(root.data.value_avg), "garbage_draws": tape.garbage_ctr}
+
+
+def reference_game_to_X(game_rec):
+    """ai.game_to_X on a packed game -> (grids [2,40,10], extras [105]) in this repo's layout."""
+    m = full_modules()
+    x = m.ai.game_to_X(make_game(game_rec))
+    grids = np.stack([np.asarray(x[0], dtype=np.float32), np.asarray(x[5], dtype=np.float32)])
+    extras = np.concatenate([np.asarray(x[1], np.float32).reshape(-1), [x[2], x[3], x[4]],
+                             np.asarray(x[6], np.float32).reshape(-1), [x[7], x[8], x[9]], [x[10]]]).astype(np.float32)
+    return grids, extras

@@ -1,0 +1,206 @@
+"""GPU tests of the feature encoder, the search kernels and the self-play engine (-m gpu).
+
+Search parity is stated against vectors produced by the reference's own ai.MCTS (golden file
+generated in the build container, oracle/gen_golden.py) under an injected deterministic
+evaluator and the shared Philox tape.  Integer outputs of the engine (states, move lists) are
+bit-exact; visit counts are compared with the tolerance written in the tests, because the device
+sums priors with warp reductions and uses CUDA's libm."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from tetris_reinforcement_learning_b200.config import Config  # noqa: E402
+from tetris_reinforcement_learning_b200.state import GAME_DTYPE, games_equal  # noqa: E402
+
+
+def config_families(iters):
+    base = dict(visual=False, ruleset="s2", model="pytorch", MAX_ITER=iters, CPUCT=0.75)
+    return [
+        Config(training=False, **base),
+        Config(training=True, **base),
+        Config(training=True, use_forced_playouts_and_policy_target_pruning=True,
+               use_playout_cap_randomization=False, **base),
+        Config(training=True, FpuStrategy="absolute", use_tanh=True, use_root_softmax=False, **base),
+    ]
+
+
+def fake_evaluator_torch(device, tanh=False):
+    """The oracle's integer-hash evaluator (oracle/features_oracle.py) in torch: bit-identical
+    float32 values / logits on both sides."""
+    import torch
+    from oracle import features_oracle as fo
+    wg = torch.from_numpy(fo.W_GRID).to(device)
+    we = torch.from_numpy(fo.W_EXTRA).to(device)
+    j = torch.arange(11583, dtype=torch.int64, device=device)
+
+    def ev(grids, extras):
+        G = extras.shape[0]
+        g = grids.reshape(2, G, 400).permute(1, 0, 2).reshape(G, 800).to(torch.int64)
+        e = extras.to(torch.int64) + 2
+        h = ((g * wg).sum(1) + (e * we).sum(1)) & 0x7FFFFFFF
+        value = ((h % 997) + 1).to(torch.float32) / 1000.0
+        if tanh:
+            value = 2 * value - 1
+        logits = ((((h >> 3)[:, None] * (2 * j + 1)[None, :]) + 7 * j * j) % 4096).to(torch.float32) / fo.LOGIT_DIV
+        return value.contiguous(), logits.contiguous()
+    return ev
+
+
+def test_feature_encode_vs_oracle(oracle):
+    import torch
+    from oracle import features_oracle as fo
+    from oracle.pin_against_reference import random_midgame
+    from tetris_reinforcement_learning_b200 import _native
+    rng = np.random.default_rng(3)
+    games = random_midgame(rng, 257, 3)
+    dev = torch.device("cuda:0")
+    d_games = torch.from_numpy(games.view(np.uint8).reshape(-1)).to(dev)
+    n = len(games)
+    for dt, tdt in ((0, torch.float32), (1, torch.bfloat16)):
+        grids = torch.zeros((2 * n, 400), dtype=tdt, device=dev)
+        extras = torch.zeros((n, 105), dtype=tdt, device=dev)
+        rc = _native.lib().trl_encode_features(d_games.data_ptr(), None, n, grids.data_ptr(), extras.data_ptr(), dt,
+                                               torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        gh, eh = grids.float().cpu().numpy(), extras.float().cpu().numpy()
+        for i in range(n):
+            wg, we = fo.encode(games[i])
+            assert np.array_equal(gh[i], wg[0].reshape(-1)) and np.array_equal(gh[n + i], wg[1].reshape(-1))
+            assert np.array_equal(eh[i], we)
+    # indexed form (what the search uses): reversed order
+    idx = torch.arange(n - 1, -1, -1, dtype=torch.int32, device=dev)
+    grids = torch.zeros((2 * n, 400), dtype=torch.float32, device=dev)
+    extras = torch.zeros((n, 105), dtype=torch.float32, device=dev)
+    assert _native.lib().trl_encode_features(d_games.data_ptr(), idx.data_ptr(), n, grids.data_ptr(), extras.data_ptr(), 0,
+                                             torch.cuda.current_stream().cuda_stream) == 0
+    wg, we = fo.encode(games[n - 1])
+    assert np.array_equal(grids[0].cpu().numpy(), wg[0].reshape(-1)) and np.array_equal(extras[0].cpu().numpy(), we)
+
+
+def _run_family(golden, fam, cfg, sel, use_graph):
+    import torch
+    from tetris_reinforcement_learning_b200.selfplay import SelfPlayEngine
+    games = golden["games"][sel].copy().view(GAME_DTYPE).reshape(-1)
+    G = len(games)
+    dev = "cuda:0"
+    eng = SelfPlayEngine(cfg, fake_evaluator_torch(torch.device(dev), tanh=cfg.use_tanh), G, device=dev,
+                         seed=int(golden["seed"]), restart_finished=False, save_all=True, use_cuda_graph=use_graph)
+    eng.set_games(games)
+    ctl = eng.get_ctl()
+    ctl["search_no"] = sel  # the golden tape is keyed by (game_id, search index)
+    eng.set_ctl(ctl)
+    long_iters, _ = cfg.playout_iterations()
+    budget = long_iters if (cfg.training and cfg.use_playout_cap_randomization) else cfg.MAX_ITER
+    eng.step(budget)
+    samples, _ = eng.drain()
+    first = {}
+    for s in samples:
+        key = int(s["game_id"])
+        if key not in first or int(s["search_no"]) < int(first[key]["search_no"]):
+            first[key] = s
+    return games, first, eng
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_search_vs_reference_vectors(golden_dir, use_graph):
+    """Device search vs the reference's ai.MCTS (24 searches, 4 config families, 48 iterations,
+    playout-cap / Gamma noise / temperature / forced playouts + pruning / tanh + absolute FPU).
+
+    Tolerance: root children and their order are bit-exact (integer work); per search the
+    total-variation distance between device and reference visit distributions must be <= 0.05
+    and at least 80 % of the searches must match the reference's visit counts exactly."""
+    golden = np.load(os.path.join(golden_dir, "mcts_golden.npz"))
+    fams = config_families(int(golden["iters"]))
+    exact = total = 0
+    worst_tv = 0.0
+    for fam, cfg in enumerate(fams):
+        sel = np.flatnonzero(golden["family"] == fam)
+        games, first, eng = _run_family(golden, fam, cfg, sel, use_graph)
+        assert len(first) == len(sel)
+        for k, gi in zip(sel, range(len(sel))):
+            s = first[int(games[gi]["game_id"])]
+            assert int(s["search_no"]) == k
+            C = int(golden["n_children"][k])
+            assert int(s["n_children"]) == C
+            assert np.array_equal(s["moves"][:C], golden["child_moves"][k][:C])      # argwhere order, bit-exact
+            assert bool(s["saved"]) == bool(golden["save"][k])                         # playout-cap coin
+            want = golden["child_visits"][k][:C].astype(np.float64)
+            got = s["visits"][:C].astype(np.float64)
+            tv = 0.5 * np.abs(want / max(want.sum(), 1) - got / max(got.sum(), 1)).sum()
+            worst_tv = max(worst_tv, tv)
+            total += 1
+            same = np.array_equal(want, got)
+            exact += int(same)
+            if same:
+                assert int(s["chosen_move"]) == int(golden["move"][k])
+        ctl = eng.get_ctl()
+        assert (ctl["status"] == 0).all()
+    assert worst_tv <= 0.05, f"worst total-variation distance {worst_tv}"
+    assert exact >= 0.8 * total, f"only {exact}/{total} searches match the reference's visit counts exactly"
+
+
+def test_search_tree_invariants_and_selfplay_with_network():
+    """AlphaSame(10,16) in bf16 under a CUDA graph: games finish, samples are consistent."""
+    import torch
+    from tetris_reinforcement_learning_b200 import architectures as arch
+    from tetris_reinforcement_learning_b200.selfplay import SelfPlayEngine, make_net_evaluator
+    torch.manual_seed(0)
+    net = arch.AlphaSame(arch.AlphaSameConfig(blocks=10, filters=16)).to("cuda:0")
+    cfg = Config(visual=False, ruleset="s2", model="pytorch", model_config=arch.AlphaSameConfig(), MAX_ITER=16,
+                 training=True, use_forced_playouts_and_policy_target_pruning=True)
+    G = 64
+    eng = SelfPlayEngine(cfg, make_net_evaluator(net, torch.bfloat16), G, seed=11, feature_dtype=torch.bfloat16,
+                         max_rounds=12, sample_cap=8192)
+    eng.step(600)
+    samples, ends = eng.drain()
+    ctl = eng.get_ctl()
+    assert int(ctl["sims"].sum()) == 600 * G
+    assert len(samples) > 0 and len(ends) > 0
+    long_iters, short_iters = cfg.playout_iterations()
+    for s in samples[:200]:
+        C = int(s["n_children"])
+        assert C > 0 and s["saved"] == 1 and int(s["iterations"]) == long_iters
+        pre = s["visits_pre"][:C].astype(int)
+        post = s["visits"][:C].astype(int)
+        assert pre.sum() == long_iters - 1           # iteration 1 expands the root only
+        assert (post <= pre).all() and post.sum() == int(s["total_visits"]) and post.sum() > 0
+        assert int(s["chosen_move"]) in set(int(m) for m in s["moves"][:C])
+        assert np.all(np.diff(s["moves"][:C].astype(int)) > 0)   # ascending = argwhere order
+    assert set(np.unique(ends["winner"])) <= {-1, 0, 1}
+    assert (ends["plies"] > 0).all()
+    assert (ctl["status"] & ~np.uint32(0)).max() == 0
+
+
+def test_engine_is_deterministic_and_matches_oracle_env():
+    """Two engines with the same seed produce identical games; every recorded position replays
+    through the CPU oracle (positions + chosen moves form a legal trajectory)."""
+    import torch
+    from oracle import oracle
+    from tetris_reinforcement_learning_b200.selfplay import SelfPlayEngine
+    cfg = Config(visual=False, ruleset="s2", model="pytorch", MAX_ITER=8, training=True)
+    outs = []
+    for _ in range(2):
+        eng = SelfPlayEngine(cfg, fake_evaluator_torch(torch.device("cuda:0")), 32, seed=5, save_all=True,
+                             restart_finished=False, max_rounds=6, use_cuda_graph=False)
+        eng.step(400)
+        outs.append((eng.drain(), eng.get_games()))
+    (s1, e1), g1 = outs[0]
+    (s2, e2), g2 = outs[1]
+    assert games_equal(g1, g2).all()
+    assert len(s1) == len(s2) and len(e1) == len(e2) == 32
+    k1 = sorted((int(s["game_id"]), int(s["search_no"]), int(s["chosen_move"])) for s in s1)
+    k2 = sorted((int(s["game_id"]), int(s["search_no"]), int(s["chosen_move"])) for s in s2)
+    assert k1 == k2
+    # replay game 0 through the oracle
+    mine = sorted([s for s in s1 if int(s["game_id"]) == 0], key=lambda s: int(s["search_no"]))
+    shadow = oracle.game_setup(1, 0, 5)
+    for s in mine:
+        root = np.array([s["state"]], dtype=GAME_DTYPE)
+        trunc = shadow.copy()
+        for pl in range(2):
+            trunc[0]["players"][pl]["qlen"] = min(int(trunc[0]["players"][pl]["qlen"]), 5)
+        assert games_equal(root, trunc).all(), f"search {int(s['search_no'])}: recorded root differs from the replay"
+        oracle.env_step(shadow, np.array([s["chosen_move"]], np.uint16), True, 5)

@@ -30,6 +30,12 @@ SIGNATURES = {
     "trl_env_step_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_u64]),
     "trl_game_setup": (c_int, [c_void_p, c_int, c_u32, c_u64, c_void_p]),
     "trl_game_setup_host": (c_int, [c_void_p, c_int, c_u32, c_u64]),
+    "trl_sizeof_search_ctl": (c_int, []),
+    "trl_sizeof_sample": (c_int, []),
+    "trl_search_select": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "trl_search_movegen": (c_int, [c_void_p, c_void_p]),
+    "trl_search_expand": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "trl_encode_features": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
 }
 
 
@@ -62,3 +68,30 @@ def check(rc, what):
     if rc != 0:
         msg = lib().trl_last_error().decode() if rc == -2 else {-1: "bad argument", -3: "out of memory"}.get(rc, "?")
         raise RuntimeError(f"{what} failed with code {rc}: {msg}")
+
+
+# ---- ctypes mirrors of the search structs (include/trl.h) ----
+
+class SearchParams(ctypes.Structure):
+    _fields_ = [("seed", ctypes.c_uint64),
+                ("cpuct", ctypes.c_double), ("dpuct", ctypes.c_double), ("fpu_value", ctypes.c_double),
+                ("root_softmax_temp", ctypes.c_double), ("temperature", ctypes.c_double),
+                ("playout_cap_chance", ctypes.c_double),
+                ("dirichlet_alpha", ctypes.c_double), ("dirichlet_s", ctypes.c_double), ("dirichlet_eps", ctypes.c_double),
+                ("c_forced", ctypes.c_double),
+                ("max_iter", ctypes.c_int32), ("iters_long", ctypes.c_int32), ("iters_short", ctypes.c_int32),
+                ("fpu_reduction", ctypes.c_int32), ("use_root_softmax", ctypes.c_int32), ("training", ctypes.c_int32),
+                ("use_playout_cap", ctypes.c_int32), ("use_noise", ctypes.c_int32), ("use_dirichlet_s", ctypes.c_int32),
+                ("use_forced", ctypes.c_int32), ("use_tanh", ctypes.c_int32), ("save_all", ctypes.c_int32),
+                ("max_rounds", ctypes.c_int32), ("restart_finished", ctypes.c_int32),
+                ("game_id_stride", ctypes.c_uint32), ("pad_", ctypes.c_int32)]
+
+
+class SearchBuffers(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("n_games", "node_cap", "state_cap", "moves_cap", "sample_cap",
+                                              "end_cap", "pad0_", "pad1_")] + \
+               [(n, ctypes.c_void_p) for n in ("prior", "value_sum", "visits", "parent", "slot", "move",
+                                               "states", "first_child", "n_children", "fpu",
+                                               "ctl", "games", "leaf_state", "legal", "n_legal",
+                                               "samples", "sample_count", "ends", "end_count",
+                                               "next_game_id", "noise_override")]

@@ -32,7 +32,7 @@ env_step_kernel(TrlGame* __restrict__ games, const uint16_t* __restrict__ moves,
     for (int w = lane; w < kGameWords; w += 32) sg[w] = gg[w];
     __syncwarp();
     if (lane == 0) {
-        TrlStepOut o = trl_env_step_scalar(&s_games[wib], (int)mv, add_bag != 0, seed);
+        TrlStepOut o = trl_env_step_scalar(&s_games[wib], (int)mv, add_bag != 0, seed, 0u, &s_games[wib].rng_ctr);
         if (out) out[i] = o;
     }
     __syncwarp();

@@ -12,10 +12,12 @@
 #pragma once
 #include "trl_tables.cuh"
 
-// random.randint(0, 9) of player.py:185 as draw #ctr of Philox stream (seed, game_id).
-__device__ __forceinline__ int trl_garbage_column(uint64_t seed, uint32_t game_id, uint32_t ctr) {
+// random.randint(0, 9) of player.py:185 as draw #ctr of Philox stream (seed, game_id, stream).
+// stream 0 = real moves (ctr = TrlGame.rng_ctr); stream 1+k = leaf simulations inside the k-th
+// search of the game (ctr = sequential draw index within that search).
+__device__ __forceinline__ int trl_garbage_column(uint64_t seed, uint32_t game_id, uint32_t stream, uint32_t ctr) {
     uint32_t o[4];
-    trl_philox(seed, ctr, game_id, 1u, 0u, o);
+    trl_philox(seed, ctr, game_id, 1u, stream, o);
     return (int)__umulhi(o[0], 10u);
 }
 
@@ -115,7 +117,8 @@ __device__ __forceinline__ int trl_get_attack_s2(int n, bool tspin, bool mini, b
 }
 
 // One full Game.make_move on a game in shared memory.  Scalar: call from ONE lane.
-__device__ __noinline__ TrlStepOut trl_env_step_scalar(TrlGame* g, int move, bool add_bag, uint64_t seed) {
+static __device__ __noinline__ TrlStepOut trl_env_step_scalar(TrlGame* g, int move, bool add_bag, uint64_t seed,
+                                                       uint32_t stream, uint32_t* ctr) {
     TrlStepOut o;
     o.rows_cleared = 0; o.attack = 0; o.flags = 0; o.garbage_col = 0; o.status = 0;
     if ((unsigned)move >= (unsigned)TRL_POLICY_SIZE) { o.status = TRL_ST_BAD_MOVE; return o; }
@@ -198,8 +201,8 @@ __device__ __noinline__ TrlStepOut trl_env_step_scalar(TrlGame* g, int move, boo
 
     int send_n = 0, send_col = 0;
     if (attack > 0) {  // one hole column per attack (player.py:184-186)
-        send_col = trl_garbage_column(seed, g->game_id, g->rng_ctr);
-        g->rng_ctr += 1;
+        send_col = trl_garbage_column(seed, g->game_id, stream, *ctr);
+        *ctr += 1;
         send_n = attack;
     }
 

@@ -1,0 +1,77 @@
+// features.cu — network input encoding straight from packed bitboard states.
+//
+// Replaces ai.game_to_X / get_grids / get_pieces / get_stat / get_garbage / simplify_grid
+// (reference ai.py:1364-1413): 11 features oriented to the side to move.  Output layout is
+// what the batched net consumes:
+//   grids  [2n][400]  rows 0..n-1 = side-to-move grid, rows n..2n-1 = opponent grid (0/1)
+//   extras [n][105]   a_pieces(7x7 one-hot: active, held, 5 previews) a_b2b a_combo a_garbage
+//                     o_pieces(49) o_b2b o_combo o_garbage color
+// One warp per game; grid cells are produced from the uint16 bitrows with coalesced stores.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "trl_common.cuh"
+#include "trl_tables.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kCells = TRL_ROWS * TRL_COLS;  // 400
+constexpr int kExtras = 105;
+
+template <typename T> __device__ __forceinline__ T to_out(float v);
+template <> __device__ __forceinline__ float to_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(kWarps * 32)
+encode_features_kernel(const TrlGame* __restrict__ games, const int32_t* __restrict__ index, int n,
+                       T* __restrict__ grids, T* __restrict__ extras) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const TrlGame& g = games[index ? index[i] : i];
+    const int turn = g.turn & 1;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const TrlPlayer& p = g.players[side == 0 ? turn : 1 - turn];
+        T* out = grids + ((size_t)side * n + i) * kCells;
+        for (int c = lane; c < kCells; c += 32) {
+            const int row = c / TRL_COLS, col = c - row * TRL_COLS;
+            out[c] = to_out<T>((float)((p.rows[row] >> col) & 1u));
+        }
+        T* ex = extras + (size_t)i * kExtras + side * 52;
+        // 7x7 one-hot table (ai.py:1381-1392): slot 0 active, 1 held, 2..6 previews
+        for (int c = lane; c < 49; c += 32) {
+            const int slot = c / 7, mino = c - slot * 7;
+            int piece = TRL_NONE;
+            if (slot == 0) piece = p.piece;
+            else if (slot == 1) piece = p.held;
+            else if (slot - 2 < p.qlen) piece = p.queue[slot - 2];
+            ex[c] = to_out<T>(piece == mino ? 1.f : 0.f);
+        }
+        if (lane == 0) {
+            ex[49] = to_out<T>((float)p.b2b);
+            ex[50] = to_out<T>((float)p.combo);
+            ex[51] = to_out<T>((float)p.n_recv);
+        }
+    }
+    if (lane == 0) extras[(size_t)i * kExtras + 104] = to_out<T>((float)turn);  // players[turn].color == turn
+}
+
+}  // namespace
+
+extern "C" int trl_encode_features(const TrlGame* games, const int32_t* index, int n, void* grids,
+                                   void* extras, int dtype, void* stream) {
+    if (n < 0 || !games || !grids || !extras || (dtype != 0 && dtype != 1)) return TRL_E_ARG;
+    if (n == 0) return TRL_OK;
+    const int blocks = (n + kWarps - 1) / kWarps;
+    if (dtype == 0)
+        encode_features_kernel<float><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(
+            games, index, n, (float*)grids, (float*)extras);
+    else
+        encode_features_kernel<__nv_bfloat16><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(
+            games, index, n, (__nv_bfloat16*)grids, (__nv_bfloat16*)extras);
+    return trl_check(cudaGetLastError());
+}

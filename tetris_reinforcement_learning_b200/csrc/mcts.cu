@@ -1,0 +1,515 @@
+// mcts.cu — batched MCTS / PUCT self-play search for sm_100a: one warp per game, the tree in
+// HBM as struct-of-arrays (children of a node are one contiguous run), one leaf per game per
+// step so that the network sees a device-resident batch of n_games leaves.
+//
+// Replaces ai.MCTS / amcts (reference ai.py:299-659, 766-996) and the per-move part of
+// play_game (ai.py:1610-1668).  Semantics follow SURVEY A.3 exactly, including the quirks:
+// ">=" (last maximum wins) in selection, un-normalised Gamma root noise, FPU refresh of the
+// played-out node's siblings only when their parent is not the root, move choice on pre-prune
+// visits, pruning with N_root in the denominator.  Scores are computed in double like the
+// reference's Python floats; the only approximations left are libm differences and the
+// summation order of warp reductions (tolerance: DESIGN.md §Parity).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "env_step.cuh"
+#include "trl_common.cuh"
+
+namespace {
+
+constexpr int kWarps = 4;
+constexpr int kGameWords = sizeof(TrlGame) / 4;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+static_assert(sizeof(TrlSearchCtl) == 80, "TrlSearchCtl layout");
+static_assert(sizeof(TrlSearchParams) == 152, "TrlSearchParams layout");
+static_assert(sizeof(TrlSearchBuffers) == 200, "TrlSearchBuffers layout");
+static_assert(sizeof(TrlGameEnd) == 32, "TrlGameEnd layout");
+static_assert(sizeof(TrlSample) == 20 + 400 + 3 * 2 * TRL_SAMPLE_MOVES, "TrlSample layout");
+
+__device__ __forceinline__ double negate_value(double v, bool tanh_mode) { return tanh_mode ? -v : 1.0 - v; }
+
+// Uniform double in [0,1): purpose 3 = playout-cap coin, 4 = move choice.
+__device__ __forceinline__ double trl_uniform(uint64_t seed, uint32_t game_id, uint32_t search_no,
+                                              uint32_t purpose, uint32_t idx) {
+    uint32_t o[4];
+    trl_philox(seed, idx, game_id, purpose, search_no, o);
+    return ((double)(o[0] >> 5) * 67108864.0 + (double)(o[1] >> 6)) / 9007199254740992.0;
+}
+
+// Gamma(alpha, 1): Marsaglia-Tsang with Box-Muller normals, U^(1/alpha) boost for alpha < 1
+// (replaces np.random.gamma, ai.py:489).
+__device__ double trl_gamma(uint64_t seed, uint32_t game_id, uint32_t search_no, uint32_t child, double alpha) {
+    const double a = alpha < 1.0 ? alpha + 1.0 : alpha;
+    const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (uint32_t k = 0; k < 64; ++k) {
+        uint32_t o[4];
+        trl_philox(seed, child, game_id, 5u | (k << 8), search_no, o);
+        const double u1 = ((double)o[0] + 1.0) / 4294967296.0, u2 = (double)o[1] / 4294967296.0;
+        const double x = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+        double v = 1.0 + c * x;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        const double u = ((double)o[2] + 0.5) / 4294967296.0;
+        if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) {
+            double g = d * v;
+            if (alpha < 1.0) g *= pow(((double)o[3] + 0.5) / 4294967296.0, 1.0 / alpha);
+            return g;
+        }
+    }
+    return alpha;  // unreachable in practice (acceptance > 95 % per round)
+}
+
+// warp arg-max of (score, index) with the reference's ">=" rule: among equal scores the
+// LARGEST index wins (ai.py:383).
+__device__ __forceinline__ void warp_argmax_last(double& score, int& idx) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double s2 = __shfl_xor_sync(kFull, score, off);
+        const int i2 = __shfl_xor_sync(kFull, idx, off);
+        if (i2 >= 0 && (idx < 0 || s2 > score || (s2 == score && i2 > idx))) { score = s2; idx = i2; }
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+    return v;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, off));
+    return v;
+}
+
+__device__ __forceinline__ void copy_game(uint32_t* dst, const uint32_t* src, int lane) {
+    for (int w = lane; w < kGameWords; w += 32) dst[w] = src[w];
+}
+
+__device__ __forceinline__ bool game_terminal(const TrlGame* g) {
+    return g->players[0].game_over || g->players[1].game_over;
+}
+
+// ---------------------------------------------------------------------------------------
+// step part 1: select + materialise
+// ---------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kWarps * 32)
+search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
+    __shared__ __align__(16) TrlGame s_game[kWarps];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = blockIdx.x * kWarps + wib;
+    if (g >= B.n_games) return;
+    TrlSearchCtl* ctl = &B.ctl[g];
+    if (!ctl->active) {
+        if (lane == 0) { B.leaf_state[g] = -1; ctl->leaf_kind = 3; }
+        return;
+    }
+    const size_t nb = (size_t)g * B.node_cap, sb = (size_t)g * B.state_cap;
+    const bool tanh_mode = P.use_tanh != 0;
+    uint32_t* sg = reinterpret_cast<uint32_t*>(&s_game[wib]);
+
+    if (ctl->iter == 0) {
+        // new search: root = copy of the real game with queues cut to 5 previews (ai.py:304-309)
+        copy_game(sg, reinterpret_cast<const uint32_t*>(&B.games[g]), lane);
+        __syncwarp();
+        if (lane == 0) {
+            for (int pl = 0; pl < 2; ++pl)
+                if (s_game[wib].players[pl].qlen > TRL_PREVIEWS) s_game[wib].players[pl].qlen = TRL_PREVIEWS;
+            B.parent[nb] = -1; B.slot[nb] = 0; B.visits[nb] = 0; B.value_sum[nb] = 0.0; B.prior[nb] = 0.0;
+            B.move[nb] = 0xFFFF;
+            B.first_child[sb] = -1; B.n_children[sb] = 0; B.fpu[sb] = 0.0;
+            ctl->n_nodes = 1; ctl->n_states = 1; ctl->garbage_ctr = 0; ctl->max_depth = 0;
+            int iters = P.max_iter;
+            uint32_t fast = 0;
+            if (P.training && P.use_playout_cap) {  // ai.py:323-330
+                const double coin = trl_uniform(P.seed, B.games[g].game_id, ctl->search_no, 3u, 0u);
+                if (coin < P.playout_cap_chance) iters = P.iters_long;
+                else { iters = P.iters_short; fast = 1; }
+            }
+            ctl->max_iter = iters; ctl->fast = fast;
+        }
+        __syncwarp();
+        copy_game(reinterpret_cast<uint32_t*>(&B.states[sb]), sg, lane);
+        __syncwarp();
+    }
+
+    // ---- select (ai.py:346-393) ----
+    int node = 0, depth = 0;
+    const bool forced_on = P.use_forced && P.training && !(P.use_playout_cap && ctl->fast);
+    while (true) {
+        const int s = B.slot[nb + node];
+        if (s < 0) break;
+        const int C = B.n_children[sb + s];
+        if (C <= 0) break;
+        const int base = B.first_child[sb + s];
+        const int pv = B.visits[nb + node];
+        const double sqrt_parent = sqrt((double)pv);
+        const double unvisited_scale = P.cpuct * sqrt_parent / P.dpuct;
+        const double fpu_q = B.fpu[sb + s];
+        const bool check_forced = forced_on && node == 0;
+        double best = -1.0;  // max_child_score starts at -1 (ai.py:348)
+        int best_i = -1;
+        for (int c = lane; c < C; c += 32) {
+            const int vc = B.visits[nb + base + c];
+            const double pr = B.prior[nb + base + c];
+            double q, u;
+            if (vc == 0) { q = fpu_q; u = unvisited_scale * pr; }
+            else { q = B.value_sum[nb + base + c] / (double)vc; u = P.cpuct * pr * sqrt_parent / (P.dpuct + (double)vc); }
+            double score = q + u;
+            if (check_forced && vc >= 1 && (double)vc < sqrt(P.c_forced * pr * (double)pv)) score = INFINITY;
+            if (score >= best) { best = score; best_i = c; }
+        }
+        warp_argmax_last(best, best_i);
+        if (best_i < 0) best_i = C - 1;  // every score < -1 (tanh only): the reference would raise
+        node = base + best_i;
+        ++depth;
+    }
+
+    // ---- materialise the leaf (ai.py:398-403) ----
+    int s = B.slot[nb + node];
+    if (node != 0) {
+        const int ps = B.slot[nb + B.parent[nb + node]];
+        if (s < 0) s = ctl->n_states;  // first visit: new state slot (uniform across lanes)
+        copy_game(sg, reinterpret_cast<const uint32_t*>(&B.states[sb + ps]), lane);
+        __syncwarp();
+        if (lane == 0) {
+            trl_env_step_scalar(&s_game[wib], (int)B.move[nb + node], false, P.seed, 1u + ctl->search_no, &ctl->garbage_ctr);
+            if (B.slot[nb + node] < 0) {
+                B.slot[nb + node] = s;
+                B.first_child[sb + s] = -1; B.n_children[sb + s] = 0; B.fpu[sb + s] = 0.0;
+                ctl->n_states = s + 1;
+            }
+        }
+        __syncwarp();
+        copy_game(reinterpret_cast<uint32_t*>(&B.states[sb + s]), sg, lane);
+    } else {
+        copy_game(sg, reinterpret_cast<const uint32_t*>(&B.states[sb]), lane);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const TrlGame* lg = &s_game[wib];
+        int kind = 0;
+        double lv = 0.0;
+        if (game_terminal(lg)) {  // ai.py:472-479
+            kind = 2;
+            const int w = lg->players[0].game_over ? 1 : 0;  // Game.winner (game.py:217-225)
+            const double vmin = tanh_mode ? -1.0 : 0.0;
+            lv = (w == lg->turn) ? 1.0 : vmin;
+        } else {
+            const TrlPlayer* p = &lg->players[lg->turn & 1];
+            if (p->piece == TRL_NONE && p->held == TRL_NONE) kind = 1;  // Game.no_move
+        }
+        ctl->leaf = node; ctl->leaf_kind = kind; ctl->leaf_value = lv;
+        if (depth > ctl->max_depth) ctl->max_depth = depth;
+        B.leaf_state[g] = (kind == 2) ? -1 : (int)(sb + s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// step part 2: expand + backup (+ finish the search and play the move)
+// ---------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float load_out(const void* p, size_t i, int dtype) {
+    return dtype == 0 ? reinterpret_cast<const float*>(p)[i]
+                      : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+
+// End of a search (ai.py:571-648) + the per-move bookkeeping of play_game (ai.py:1611-1668).
+__device__ void finish_search(const TrlSearchBuffers& B, const TrlSearchParams& P, int g, int lane, TrlGame* sgame) {
+    TrlSearchCtl* ctl = &B.ctl[g];
+    const size_t nb = (size_t)g * B.node_cap, sb = (size_t)g * B.state_cap;
+    const int C = B.n_children[sb];
+    const int base = B.first_child[sb];
+    const int root_visits = B.visits[nb];
+    uint32_t* sg = reinterpret_cast<uint32_t*>(sgame);
+
+    int chosen = -1;
+    TrlSample* rec = nullptr;
+    if (C > 0) {
+        // most visited root child, LAST maximum (ai.py:579-587)
+        double bestn = -1.0; int max_i = -1;
+        for (int c = lane; c < C; c += 32) {
+            const double n = (double)B.visits[nb + base + c];
+            if (n >= bestn) { bestn = n; max_i = c; }
+        }
+        warp_argmax_last(bestn, max_i);
+
+        // temperature move choice on pre-prune visits (ai.py:591-612); sequential like
+        // random.choices' accumulate + bisect
+        const double temp = P.training ? P.temperature : 0.0;
+        if (lane == 0) {
+            if (temp == 0.0) {  // np.argmax: FIRST maximum
+                int bi = 0, bn = -1;
+                for (int c = 0; c < C; ++c) { const int n = B.visits[nb + base + c]; if (n > bn) { bn = n; bi = c; } }
+                chosen = bi;
+            } else {
+                const double inv_t = 1.0 / temp;
+                double wsum = 0.0;
+                for (int c = 0; c < C; ++c) wsum += pow((double)B.visits[nb + base + c], inv_t);
+                double total = 0.0;
+                for (int c = 0; c < C; ++c) total += pow((double)B.visits[nb + base + c], inv_t) / wsum;
+                const double x = trl_uniform(P.seed, B.games[g].game_id, ctl->search_no, 4u, 0u) * total;
+                double cum = 0.0;
+                chosen = C - 1;  // bisect(cum, x, 0, C-1): first index with cum > x, capped at C-1
+                for (int c = 0; c < C - 1; ++c) {
+                    cum += pow((double)B.visits[nb + base + c], inv_t) / wsum;
+                    if (cum > x) { chosen = c; break; }
+                }
+            }
+        }
+        chosen = __shfl_sync(kFull, chosen, 0);
+
+        const bool save = !ctl->fast;
+        const bool want_rec = save || P.save_all;
+        uint32_t slot_i = 0;
+        if (want_rec) {
+            if (lane == 0) slot_i = atomicAdd(B.sample_count, 1u);
+            slot_i = __shfl_sync(kFull, slot_i, 0);
+            if (slot_i < (uint32_t)B.sample_cap) rec = &B.samples[slot_i];
+            else if (lane == 0) ctl->status |= TRL_ST_MOVES_TRUNC;
+        }
+        if (rec)
+            for (int c = lane; c < C && c < TRL_SAMPLE_MOVES; c += 32) {
+                rec->moves[c] = B.move[nb + base + c];
+                rec->visits_pre[c] = (uint16_t)B.visits[nb + base + c];
+            }
+
+        // policy-target pruning (ai.py:619-648): mutates root-children visit counts
+        if (P.use_forced && P.training && !ctl->fast) {
+            const int b = base + max_i;
+            const double sqrt_root = sqrt((double)root_visits);
+            const double ref = B.value_sum[nb + b] / (double)B.visits[nb + b] +
+                               P.cpuct * B.prior[nb + b] * sqrt_root / (P.dpuct + (double)B.visits[nb + b]);
+            const double root_fpu = B.fpu[sb];
+            for (int c = lane; c < C; c += 32) {
+                const int id = base + c;
+                int n = B.visits[nb + id];
+                if (id == b || n <= 0) continue;
+                const double pr = B.prior[nb + id];
+                const double q = B.value_sum[nb + id] / (double)n;  // value_avg does not change while pruning
+                (void)root_fpu;
+                const double n_forced = sqrt(P.c_forced * pr * (double)root_visits);
+                const double sc = q + P.cpuct * pr * sqrt_root / (P.dpuct + (double)root_visits);
+                int count = 0;
+                while (true) {
+                    if (n == 1) { n = 0; break; }
+                    if ((double)count < n_forced && sc < ref) { ++count; --n; }
+                    else break;
+                }
+                B.visits[nb + id] = n;
+            }
+            __syncwarp();
+        }
+        if (rec) {
+            uint32_t tot = 0;
+            for (int c = lane; c < C; c += 32) {
+                const int n = B.visits[nb + base + c];
+                if (c < TRL_SAMPLE_MOVES) rec->visits[c] = (uint16_t)n;
+                tot += (uint32_t)n;
+            }
+            for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(kFull, tot, off);
+            copy_game(reinterpret_cast<uint32_t*>(&rec->state), reinterpret_cast<const uint32_t*>(&B.states[sb]), lane);
+            if (lane == 0) {
+                rec->game_id = B.games[g].game_id; rec->search_no = (uint16_t)ctl->search_no;
+                rec->turn = B.games[g].turn; rec->saved = save ? 1 : 0;
+                rec->n_children = (uint16_t)C; rec->chosen_move = B.move[nb + base + chosen];
+                rec->total_visits = tot; rec->iterations = ctl->max_iter;
+            }
+        }
+    }
+
+    // ---- play the move on the real game (ai.py:1668: game.make_move(move)) ----
+    copy_game(sg, reinterpret_cast<const uint32_t*>(&B.games[g]), lane);
+    __syncwarp();
+    if (lane == 0) {
+        TrlGame* rg = sgame;
+        bool over = false;
+        if (C > 0) {
+            const int mover = rg->turn & 1;
+            TrlStepOut o = trl_env_step_scalar(rg, (int)B.move[nb + base + chosen], true, P.seed, 0u, &rg->rng_ctr);
+            if (mover == 0) { ctl->lines_sent0 += o.attack; ctl->lines_cleared0 += o.rows_cleared; }
+            ctl->status |= o.status;
+        } else {
+            ctl->status |= TRL_ST_NO_PIECE;  // root without a legal move: the reference would raise
+            over = true;
+        }
+        ctl->search_no += 1;
+        ctl->iter = 0;
+        over = over || game_terminal(rg) || (int)rg->rounds >= P.max_rounds;  // ai.py:1610
+        if (over) {
+            const uint32_t e = atomicAdd(B.end_count, 1u);
+            if (e < (uint32_t)B.end_cap) {
+                TrlGameEnd ge;
+                ge.game_id = rg->game_id;
+                ge.winner = rg->players[0].game_over ? 1 : (rg->players[1].game_over ? 0 : -1);
+                ge.plies = ctl->search_no; ge.rounds = rg->rounds;
+                ge.pieces0 = rg->players[0].pieces; ge.lines_sent0 = ctl->lines_sent0;
+                ge.lines_cleared0 = ctl->lines_cleared0; ge.pad_ = 0;
+                B.ends[e] = ge;
+            }
+            ctl->games_finished += 1;
+            ctl->search_no = 0; ctl->lines_sent0 = 0; ctl->lines_cleared0 = 0;
+            if (P.restart_finished) {
+                const uint32_t id = atomicAdd(B.next_game_id, P.game_id_stride);
+                trl_game_setup_scalar(rg, id, P.seed);
+            } else {
+                ctl->active = 0;
+            }
+        }
+    }
+    __syncwarp();
+    copy_game(reinterpret_cast<uint32_t*>(&B.games[g]), sg, lane);
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+search_expand_kernel(TrlSearchBuffers B, TrlSearchParams P, const void* __restrict__ values,
+                     const void* __restrict__ logits, int dtype) {
+    __shared__ __align__(16) TrlGame s_game[kWarps];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = blockIdx.x * kWarps + wib;
+    if (g >= B.n_games) return;
+    TrlSearchCtl* ctl = &B.ctl[g];
+    if (!ctl->active || ctl->leaf_kind == 3) return;
+    const size_t nb = (size_t)g * B.node_cap, sb = (size_t)g * B.state_cap;
+    const bool tanh_mode = P.use_tanh != 0;
+    const double vmin = tanh_mode ? -1.0 : 0.0;
+    const int leaf = ctl->leaf;
+    const int kind = ctl->leaf_kind;
+    const int ls = B.slot[nb + leaf];
+
+    double value;
+    if (kind == 2) {
+        value = ctl->leaf_value;
+    } else {
+        value = (double)load_out(values, (size_t)g, dtype);
+        int C = (kind == 0) ? (int)B.n_legal[g] : 0;
+        if (C > B.moves_cap) C = B.moves_cap;
+        if (C > 0 && ctl->n_nodes + C > B.node_cap) {  // arena full: the leaf stays childless
+            C = 0;
+            if (lane == 0) ctl->status |= TRL_ST_QUEUE_OVERFLOW;
+        }
+        if (C > 0) {
+            // priors over the legal moves (ai.py:411-443).  softmax over all 11583 logits followed
+            // by renormalisation over the legal ones == softmax over the legal logits.
+            const uint16_t* mv = B.legal + (size_t)g * B.moves_cap;
+            const size_t lb = (size_t)g * TRL_POLICY_SIZE;
+            double mx = -INFINITY;
+            for (int c = lane; c < C; c += 32) mx = fmax(mx, (double)load_out(logits, lb + mv[c], dtype));
+            mx = warp_max(mx);
+            const bool root_temp = (leaf == 0) && P.use_root_softmax;
+            const double inv_temp = root_temp ? 1.0 / P.root_softmax_temp : 1.0;
+            const int base = ctl->n_nodes;
+            double sum = 0.0;
+            for (int c = lane; c < C; c += 32) {
+                const double l = (double)load_out(logits, lb + mv[c], dtype);
+                double e = exp((l - mx) * inv_temp);
+                if (!(e > 0.0)) e = 1e-25;  // the reference's clamp of underflowed probabilities (ai.py:411)
+                B.prior[nb + base + c] = e;
+                sum += e;
+            }
+            sum = warp_sum(sum);
+            const bool noisy = P.training && !ctl->fast && P.use_noise && leaf == 0;  // ai.py:482-499
+            double alpha = P.dirichlet_alpha;
+            if (noisy && P.use_dirichlet_s) alpha *= P.dirichlet_s / (double)C;
+            const uint32_t gid = B.games[g].game_id;
+            for (int c = lane; c < C; c += 32) {
+                const int id = base + c;
+                double pr = B.prior[nb + id] / sum;
+                if (noisy) {
+                    const double nz = B.noise_override ? B.noise_override[(size_t)g * B.moves_cap + c]
+                                                       : trl_gamma(P.seed, gid, ctl->search_no, (uint32_t)c, alpha);
+                    pr = pr * (1.0 - P.dirichlet_eps) + nz * P.dirichlet_eps;
+                }
+                B.prior[nb + id] = pr;
+                B.visits[nb + id] = 0; B.value_sum[nb + id] = 0.0;
+                B.parent[nb + id] = leaf; B.slot[nb + id] = -1; B.move[nb + id] = mv[c];
+            }
+            if (lane == 0) {
+                B.first_child[sb + ls] = base; B.n_children[sb + ls] = C;
+                // FPU of the fresh children (ai.py:449-456)
+                B.fpu[sb + ls] = P.fpu_reduction ? fmax(vmin, negate_value(value, tanh_mode)) : fmax(vmin, P.fpu_value);
+                ctl->n_nodes = base + C;
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- backup (ai.py:511-533) ----
+    if (lane == 0) {
+        const double pos = negate_value(value, tanh_mode);
+        const double neg = negate_value(pos, tanh_mode);
+        const int leaf_turn = B.states[sb + ls].turn;
+        int n = leaf;
+        while (true) {
+            const int ns = B.slot[nb + n];
+            B.visits[nb + n] += 1;
+            B.value_sum[nb + n] += (B.states[sb + ns].turn == leaf_turn) ? pos : neg;
+            if (n == 0) break;
+            n = B.parent[nb + n];
+        }
+        ctl->iter += 1;
+        ctl->sims += 1;
+    }
+    __syncwarp();
+
+    // ---- FPU refresh of the played-out node's unvisited siblings (ai.py:542-565) ----
+    if (leaf != 0 && P.fpu_reduction) {
+        const int par = B.parent[nb + leaf];
+        if (par != 0) {
+            const int ps = B.slot[nb + par];
+            const int C = B.n_children[sb + ps], base = B.first_child[sb + ps];
+            double explored = 0.0;
+            for (int c = lane; c < C; c += 32)
+                if (B.visits[nb + base + c] > 0) explored += B.prior[nb + base + c];
+            explored = warp_sum(explored);
+            if (lane == 0) {
+                const double qpar = B.value_sum[nb + par] / (double)B.visits[nb + par];
+                B.fpu[sb + ps] = fmax(vmin, negate_value(qpar, tanh_mode) - P.fpu_value * sqrt(explored));
+            }
+        }
+    }
+    __syncwarp();
+
+    if (ctl->iter >= ctl->max_iter) finish_search(B, P, g, lane, &s_game[wib]);
+}
+
+}  // namespace
+
+extern "C" int trl_sizeof_search_ctl(void) { return (int)sizeof(TrlSearchCtl); }
+extern "C" int trl_sizeof_sample(void) { return (int)sizeof(TrlSample); }
+
+static bool buffers_ok(const TrlSearchBuffers* b) {
+    return b && b->n_games >= 0 && b->node_cap > 1 && b->state_cap > 1 && b->moves_cap > 0 && b->prior && b->value_sum &&
+           b->visits && b->parent && b->slot && b->move && b->states && b->first_child && b->n_children && b->fpu &&
+           b->ctl && b->games && b->leaf_state && b->legal && b->n_legal && b->samples && b->sample_count && b->ends &&
+           b->end_count && b->next_game_id;
+}
+
+extern "C" int trl_search_select(const TrlSearchBuffers* buf, const TrlSearchParams* prm, void* stream) {
+    if (!buffers_ok(buf) || !prm) return TRL_E_ARG;
+    if (buf->n_games == 0) return TRL_OK;
+    search_select_kernel<<<(buf->n_games + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(*buf, *prm);
+    return trl_check(cudaGetLastError());
+}
+
+int trl_movegen_indexed(const TrlGame* games, const int32_t* index, int n, uint16_t* moves, int moves_cap,
+                        uint16_t* n_moves, cudaStream_t stream);  // movegen.cu
+
+extern "C" int trl_search_movegen(const TrlSearchBuffers* buf, void* stream) {
+    if (!buffers_ok(buf)) return TRL_E_ARG;
+    return trl_movegen_indexed(buf->states, buf->leaf_state, buf->n_games, buf->legal, buf->moves_cap, buf->n_legal,
+                               (cudaStream_t)stream);
+}
+
+extern "C" int trl_search_expand(const TrlSearchBuffers* buf, const TrlSearchParams* prm, const void* values,
+                                 const void* logits, int dtype, void* stream) {
+    if (!buffers_ok(buf) || !prm || !values || !logits || (dtype != 0 && dtype != 1)) return TRL_E_ARG;
+    if (buf->n_games == 0) return TRL_OK;
+    search_expand_kernel<<<(buf->n_games + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(
+        *buf, *prm, values, logits, dtype);
+    return trl_check(cudaGetLastError());
+}

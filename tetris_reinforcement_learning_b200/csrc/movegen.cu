@@ -172,7 +172,8 @@ __device__ void search_piece(PieceSearch& S, const uint16_t* rows, int type, boo
 // boundary, the tests and the bench up; superseded by the warp-cooperative kernel.
 __global__ void __launch_bounds__(128)
 movegen_thread_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restrict__ cur,
-                      const uint8_t* __restrict__ alt, const TrlGame* __restrict__ games, int n,
+                      const uint8_t* __restrict__ alt, const TrlGame* __restrict__ games,
+                      const int32_t* __restrict__ index, int n,
                       uint32_t* __restrict__ mask_bits, uint32_t* __restrict__ scratch_masks,
                       uint16_t* __restrict__ moves, int moves_cap, uint16_t* __restrict__ n_moves,
                       uint32_t* __restrict__ status) {
@@ -181,7 +182,13 @@ movegen_thread_kernel(const uint16_t* __restrict__ boards, const uint8_t* __rest
     uint16_t rows[TRL_ROWS];
     int c, a;
     if (games) {
-        const TrlPlayer& p = games[i].players[games[i].turn & 1];
+        const int gi = index ? index[i] : i;
+        if (gi < 0) {  // nothing to enumerate for this item
+            if (n_moves) n_moves[i] = 0;
+            if (status) status[i] = 0;
+            return;
+        }
+        const TrlPlayer& p = games[gi].players[games[gi].turn & 1];
         for (int r = 0; r < TRL_ROWS; ++r) rows[r] = p.rows[r];
         c = p.piece;
         a = (p.held != TRL_NONE) ? p.held : (p.qlen > 0 ? p.queue[0] : TRL_NONE);
@@ -225,7 +232,7 @@ movegen_thread_kernel(const uint16_t* __restrict__ boards, const uint8_t* __rest
 // ---------------------------------------------------------------------------------------
 
 static int launch_movegen(const uint16_t* boards, const uint8_t* cur, const uint8_t* alt,
-                          const TrlGame* games, int n, uint32_t* mask_bits, uint16_t* moves,
+                          const TrlGame* games, const int32_t* index, int n, uint32_t* mask_bits, uint16_t* moves,
                           int moves_cap, uint16_t* n_moves, uint32_t* status, cudaStream_t stream) {
     if (n < 0 || (!games && (!boards || !cur || !alt)) || (moves && moves_cap <= 0)) return TRL_E_ARG;
     if (n == 0) return TRL_OK;
@@ -237,22 +244,28 @@ static int launch_movegen(const uint16_t* boards, const uint8_t* cur, const uint
     }
     const int block = 128;
     movegen_thread_kernel<<<(n + block - 1) / block, block, 0, stream>>>(
-        boards, cur, alt, games, n, mask_bits, scratch, moves, moves_cap, n_moves, status);
+        boards, cur, alt, games, index, n, mask_bits, scratch, moves, moves_cap, n_moves, status);
     return trl_check(cudaGetLastError());
 }
 
 extern "C" int trl_movegen(const uint16_t* boards, const uint8_t* cur, const uint8_t* alt, int n,
                            uint32_t* mask_bits, uint16_t* moves, int moves_cap, uint16_t* n_moves,
                            uint32_t* status, void* stream) {
-    return launch_movegen(boards, cur, alt, nullptr, n, mask_bits, moves, moves_cap, n_moves, status,
+    return launch_movegen(boards, cur, alt, nullptr, nullptr, n, mask_bits, moves, moves_cap, n_moves, status,
                           (cudaStream_t)stream);
 }
 
 extern "C" int trl_movegen_games(const TrlGame* games, int n, uint32_t* mask_bits, uint16_t* moves,
                                  int moves_cap, uint16_t* n_moves, uint32_t* status, void* stream) {
     if (!games) return TRL_E_ARG;
-    return launch_movegen(nullptr, nullptr, nullptr, games, n, mask_bits, moves, moves_cap, n_moves,
+    return launch_movegen(nullptr, nullptr, nullptr, games, nullptr, n, mask_bits, moves, moves_cap, n_moves,
                           status, (cudaStream_t)stream);
+}
+
+// Search-internal form: item i enumerates games[index[i]] (index[i] < 0: no moves).
+int trl_movegen_indexed(const TrlGame* games, const int32_t* index, int n, uint16_t* moves, int moves_cap,
+                        uint16_t* n_moves, cudaStream_t stream) {
+    return launch_movegen(nullptr, nullptr, nullptr, games, index, n, nullptr, moves, moves_cap, n_moves, nullptr, stream);
 }
 
 extern "C" int trl_movegen_host(const uint16_t* boards, const uint8_t* cur, const uint8_t* alt, int n,
@@ -290,7 +303,7 @@ extern "C" int trl_movegen_host(const uint16_t* boards, const uint8_t* cur, cons
         rc = trl_check(cudaMemcpyAsync(d_boards, boards + (size_t)off * TRL_ROWS, (size_t)m * TRL_ROWS * 2, cudaMemcpyHostToDevice, s));
         if (!rc) rc = trl_check(cudaMemcpyAsync(d_cur, cur + off, m, cudaMemcpyHostToDevice, s));
         if (!rc) rc = trl_check(cudaMemcpyAsync(d_alt, alt + off, m, cudaMemcpyHostToDevice, s));
-        if (!rc) rc = launch_movegen(d_boards, d_cur, d_alt, nullptr, m, d_mask, d_moves, moves_cap, d_nm, d_status, s);
+        if (!rc) rc = launch_movegen(d_boards, d_cur, d_alt, nullptr, nullptr, m, d_mask, d_moves, moves_cap, d_nm, d_status, s);
         if (!rc && mask_bits) rc = trl_check(cudaMemcpyAsync(mask_bits + (size_t)off * TRL_MASK_WORDS, d_mask, (size_t)m * TRL_MASK_WORDS * 4, cudaMemcpyDeviceToHost, s));
         if (!rc && moves) rc = trl_check(cudaMemcpyAsync(moves + (size_t)off * moves_cap, d_moves, (size_t)m * moves_cap * 2, cudaMemcpyDeviceToHost, s));
         if (!rc && n_moves) rc = trl_check(cudaMemcpyAsync(n_moves + off, d_nm, (size_t)m * 2, cudaMemcpyDeviceToHost, s));

@@ -1,0 +1,257 @@
+"""Device-resident batched self-play engine.
+
+Replaces the body of make_training_set / _make_training_set_async / aplay_game / amcts /
+BatchedEvaluator (reference ai.py:670-996, 1702-1869): G games per GPU advance in lock-step,
+one MCTS simulation per game per step:
+
+    select+materialise (mcts.cu) -> legal placements of the leaves (movegen.cu)
+    -> feature encode (features.cu) -> policy/value net on the G-leaf batch (PyTorch)
+    -> expand+backup(+finish search, play the move, restart finished games) (mcts.cu)
+
+The whole step is stream-ordered on one CUDA stream and captured into one CUDA graph; there are
+no host round-trips inside a step.  Finished searches leave `TrlSample` records (position,
+root children, post-prune visit counts) and finished games `TrlGameEnd` records in HBM ring
+buffers that the host drains between graph replays.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native
+from .const import POLICY_SIZE
+from .state import GAME_DTYPE
+
+SAMPLE_MOVES = 512
+
+CTL_DTYPE = np.dtype({
+    "names": ["iter", "max_iter", "n_nodes", "n_states", "leaf", "leaf_kind", "search_no", "garbage_ctr", "status",
+              "fast", "active", "games_finished", "sims", "lines_sent0", "lines_cleared0", "leaf_value",
+              "max_depth", "pad_"],
+    "formats": ["<i4", "<i4", "<i4", "<i4", "<i4", "<i4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u8",
+                "<i4", "<i4", "<f8", "<i4", "<i4"],
+    "offsets": [0, 4, 8, 12, 16, 20, 24, 28, 32, 36, 40, 44, 48, 56, 60, 64, 72, 76],
+    "itemsize": 80,
+})
+
+SAMPLE_DTYPE = np.dtype({
+    "names": ["game_id", "search_no", "turn", "saved", "n_children", "chosen_move", "total_visits", "iterations",
+              "state", "moves", "visits", "visits_pre"],
+    "formats": ["<u4", "<u2", "u1", "u1", "<u2", "<u2", "<u4", "<i4", GAME_DTYPE,
+                ("<u2", (SAMPLE_MOVES,)), ("<u2", (SAMPLE_MOVES,)), ("<u2", (SAMPLE_MOVES,))],
+    "offsets": [0, 4, 6, 7, 8, 10, 12, 16, 20, 420, 420 + 2 * SAMPLE_MOVES, 420 + 4 * SAMPLE_MOVES],
+    "itemsize": 420 + 6 * SAMPLE_MOVES,
+})
+
+GAME_END_DTYPE = np.dtype({
+    "names": ["game_id", "winner", "plies", "rounds", "pieces0", "lines_sent0", "lines_cleared0", "pad_"],
+    "formats": ["<u4", "<i4", "<u4", "<u4", "<i4", "<i4", "<i4", "<i4"],
+    "offsets": [0, 4, 8, 12, 16, 20, 24, 28],
+    "itemsize": 32,
+})
+
+
+def search_params_from_config(config, seed=0, restart_finished=True, game_id_stride=1, save_all=None, max_rounds=None):
+    """Config (ai.py:97-137) -> TrlSearchParams."""
+    from .const import MAX_MOVES
+    p = _native.SearchParams()
+    p.seed = int(seed)
+    p.cpuct, p.dpuct, p.fpu_value = float(config.CPUCT), float(config.DPUCT), float(config.FpuValue)
+    p.root_softmax_temp = float(config.RootSoftmaxTemp)
+    p.temperature = float(config.temperature)
+    p.playout_cap_chance = float(config.playout_cap_chance)
+    p.dirichlet_alpha, p.dirichlet_s = float(config.DIRICHLET_ALPHA), float(config.DIRICHLET_S)
+    p.dirichlet_eps = float(config.DIRICHLET_EXPLORATION)
+    p.c_forced = float(config.CForcedPlayout)
+    p.max_iter = int(config.MAX_ITER)
+    p.iters_long, p.iters_short = config.playout_iterations()
+    if config.FpuStrategy not in ("reduction", "absolute"):
+        raise ValueError(f"unknown FpuStrategy {config.FpuStrategy!r}")
+    p.fpu_reduction = int(config.FpuStrategy == "reduction")
+    p.use_root_softmax = int(bool(config.use_root_softmax))
+    p.training = int(bool(config.training))
+    p.use_playout_cap = int(bool(config.use_playout_cap_randomization))
+    p.use_noise = int(bool(config.use_dirichlet_noise))
+    p.use_dirichlet_s = int(bool(config.use_dirichlet_s))
+    p.use_forced = int(bool(config.use_forced_playouts_and_policy_target_pruning))
+    p.use_tanh = int(bool(config.use_tanh))
+    p.save_all = int(bool(config.save_all if save_all is None else save_all))
+    p.max_rounds = int(MAX_MOVES if max_rounds is None else max_rounds)
+    p.restart_finished = int(bool(restart_finished))
+    p.game_id_stride = int(game_id_stride)
+    return p
+
+
+class SelfPlayEngine:
+    """G concurrent self-play games on one GPU.
+
+    evaluator(grids [2G,1,40,10], extras [G,105]) -> (values [G] or [G,1], logits [G,11583]);
+    tensors of `feature_dtype` in, float32 or bfloat16 out.  Normally a network's
+    `forward_packed` (see make_net_evaluator); tests inject a deterministic function.
+    """
+
+    def __init__(self, config, evaluator, n_games, device="cuda:0", seed=0, first_game_id=0, game_id_stride=1,
+                 feature_dtype=torch.float32, node_cap=None, sample_cap=None, restart_finished=True, save_all=None,
+                 max_rounds=None, use_cuda_graph=True):
+        if config.ruleset != "s2":
+            raise NotImplementedError("only ruleset 's2' is implemented on the device path")
+        if config.move_algorithm != "convolutional":
+            raise NotImplementedError("only move_algorithm='convolutional' is implemented on the device path")
+        self.lib = _native.lib()
+        self.config, self.evaluator = config, evaluator
+        self.G = int(n_games)
+        self.device = torch.device(device)
+        self.params = search_params_from_config(config, seed, restart_finished, game_id_stride, save_all, max_rounds)
+        self.seed = int(seed)
+        self.feature_dtype = feature_dtype
+        self.use_cuda_graph = use_cuda_graph
+        iters_max = max(self.params.max_iter, self.params.iters_long if (config.training and config.use_playout_cap_randomization) else 0)
+        self.state_cap = iters_max + 2
+        self.node_cap = int(node_cap) if node_cap else max(1024, iters_max * 96)
+        self.moves_cap = SAMPLE_MOVES
+        self.sample_cap = int(sample_cap) if sample_cap else max(4 * self.G, 1024)
+        self.end_cap = max(2 * self.G, 1024)
+        G, dev = self.G, self.device
+        nn_, ns = G * self.node_cap, G * self.state_cap
+        z = lambda n, dt: torch.zeros(n, dtype=dt, device=dev)  # noqa: E731
+        self.t = {
+            "prior": z(nn_, torch.float64), "value_sum": z(nn_, torch.float64), "visits": z(nn_, torch.int32),
+            "parent": z(nn_, torch.int32), "slot": z(nn_, torch.int32), "move": z(nn_, torch.int16),
+            "states": z(ns * 400, torch.uint8), "first_child": z(ns, torch.int32), "n_children": z(ns, torch.int32),
+            "fpu": z(ns, torch.float64),
+            "ctl": z(G * CTL_DTYPE.itemsize, torch.uint8), "games": z(G * 400, torch.uint8),
+            "leaf_state": z(G, torch.int32), "legal": z(G * self.moves_cap, torch.int16), "n_legal": z(G, torch.int16),
+            "samples": z(self.sample_cap * SAMPLE_DTYPE.itemsize, torch.uint8), "sample_count": z(1, torch.int32),
+            "ends": z(self.end_cap * GAME_END_DTYPE.itemsize, torch.uint8), "end_count": z(1, torch.int32),
+            "next_game_id": z(1, torch.int32),
+        }
+        fdt = feature_dtype
+        self.grids = torch.zeros((2 * G, 1, 40, 10), dtype=fdt, device=dev)
+        self.extras = torch.zeros((G, 105), dtype=fdt, device=dev)
+        self.noise_override = None
+        b = _native.SearchBuffers()
+        b.n_games, b.node_cap, b.state_cap, b.moves_cap = G, self.node_cap, self.state_cap, self.moves_cap
+        b.sample_cap, b.end_cap = self.sample_cap, self.end_cap
+        for name, ten in self.t.items():
+            setattr(b, name, ten.data_ptr())
+        b.noise_override = None
+        self.buf = b
+        assert self.lib.trl_sizeof_search_ctl() == CTL_DTYPE.itemsize and self.lib.trl_sizeof_sample() == SAMPLE_DTYPE.itemsize
+        self._graph = None
+        self._values = self._logits = None
+        self.steps_done = 0
+        self.new_games(first_game_id, game_id_stride)
+
+    # ---- state access -----------------------------------------------------------------
+    def new_games(self, first_game_id=0, stride=1):
+        """Fresh Game.setup() in every slot; ids first, first+stride, ..."""
+        games = self.t["games"].view(self.G, 400)
+        if stride == 1:
+            rc = self.lib.trl_game_setup(games.data_ptr(), self.G, int(first_game_id), self.seed,
+                                         torch.cuda.current_stream(self.device).cuda_stream)
+            _native.check(rc, "trl_game_setup")
+        else:
+            from .env import game_setup_host
+            host = np.concatenate([game_setup_host(1, first_game_id + i * stride, self.seed) for i in range(self.G)])
+            self.set_games(host)
+        self.t["next_game_id"].fill_(int(first_game_id + self.G * stride))
+        ctl = np.zeros(self.G, dtype=CTL_DTYPE)
+        ctl["active"] = 1
+        self.set_ctl(ctl)
+
+    def set_games(self, games_np):
+        assert games_np.dtype == GAME_DTYPE and games_np.shape == (self.G,)
+        self.t["games"].copy_(torch.from_numpy(np.ascontiguousarray(games_np).view(np.uint8).reshape(-1)).to(self.device))
+
+    def get_games(self):
+        return self.t["games"].cpu().numpy().view(GAME_DTYPE).reshape(-1)
+
+    def set_ctl(self, ctl_np):
+        assert ctl_np.dtype == CTL_DTYPE and ctl_np.shape == (self.G,)
+        self.t["ctl"].copy_(torch.from_numpy(np.ascontiguousarray(ctl_np).view(np.uint8).reshape(-1)).to(self.device))
+
+    def get_ctl(self):
+        return self.t["ctl"].cpu().numpy().view(CTL_DTYPE).reshape(-1)
+
+    def set_noise_override(self, noise):
+        """noise: float64 [G, moves_cap] Gamma draws used instead of the in-kernel sampler (tests)."""
+        self.noise_override = torch.as_tensor(noise, dtype=torch.float64, device=self.device).contiguous()
+        self.buf.noise_override = self.noise_override.data_ptr()
+        self._graph = None
+
+    # ---- one simulation per game ---------------------------------------------------------
+    def _step_eager(self):
+        lib, st = self.lib, torch.cuda.current_stream(self.device).cuda_stream
+        bp, pp = ctypes.byref(self.buf), ctypes.byref(self.params)
+        _native.check(lib.trl_search_select(bp, pp, st), "trl_search_select")
+        _native.check(lib.trl_search_movegen(bp, st), "trl_search_movegen")
+        dt = 0 if self.feature_dtype == torch.float32 else 1
+        _native.check(lib.trl_encode_features(self.t["states"].data_ptr(), self.t["leaf_state"].data_ptr(), self.G,
+                                              self.grids.data_ptr(), self.extras.data_ptr(), dt, st), "trl_encode_features")
+        with torch.no_grad():
+            values, logits = self.evaluator(self.grids, self.extras)
+        values = values.reshape(-1)
+        if values.dtype != logits.dtype:
+            values = values.to(logits.dtype)
+        if not (values.is_contiguous() and logits.is_contiguous() and logits.shape == (self.G, POLICY_SIZE)):
+            raise ValueError("evaluator must return contiguous values [G] and logits [G, 11583]")
+        if logits.dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("evaluator outputs must be float32 or bfloat16")
+        self._values, self._logits = values, logits  # keep alive (graph-owned memory when captured)
+        _native.check(lib.trl_search_expand(bp, pp, values.data_ptr(), logits.data_ptr(),
+                                            0 if logits.dtype == torch.float32 else 1, st), "trl_search_expand")
+
+    def step(self, n=1):
+        """Advance every game by n simulations."""
+        if not self.use_cuda_graph:
+            for _ in range(n):
+                self._step_eager()
+            self.steps_done += n
+            return
+        if self._graph is None:
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):  # warm-up: allocator, cuDNN/cuBLAS plans, library workspaces
+                    self._step_eager()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self.steps_done += 2
+            n -= 2
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_eager()
+            self._graph = g
+        for _ in range(max(n, 0)):
+            self._graph.replay()
+        self.steps_done += max(n, 0)
+
+    # ---- outputs ----------------------------------------------------------------------------
+    def drain(self):
+        """-> (samples SAMPLE_DTYPE[k], game_ends GAME_END_DTYPE[m]) accumulated since the last drain."""
+        torch.cuda.synchronize(self.device)
+        ns = min(int(self.t["sample_count"].item()), self.sample_cap)
+        ne = min(int(self.t["end_count"].item()), self.end_cap)
+        samples = self.t["samples"][: ns * SAMPLE_DTYPE.itemsize].cpu().numpy().view(SAMPLE_DTYPE).copy()
+        ends = self.t["ends"][: ne * GAME_END_DTYPE.itemsize].cpu().numpy().view(GAME_END_DTYPE).copy()
+        self.t["sample_count"].zero_()
+        self.t["end_count"].zero_()
+        return samples, ends
+
+    def total_sims(self):
+        return int(self.get_ctl()["sims"].sum())
+
+
+def make_net_evaluator(net, dtype=torch.bfloat16, channels_last=True):
+    """Wrap a network (architectures.*) as an engine evaluator: eval mode, `dtype` weights,
+    packed inputs (no host tensors)."""
+    net = net.eval().to(dtype)
+    if channels_last:
+        net = net.to(memory_format=torch.channels_last)
+
+    def evaluate(grids, extras):
+        if channels_last:
+            grids = grids.contiguous(memory_format=torch.channels_last)
+        out = net.forward_packed(grids, extras)
+        return out[0], out[1]
+
+    return evaluate
