@@ -31,7 +31,9 @@ encode_features_kernel(const TrlGame* __restrict__ games, const int32_t* __restr
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (i >= n) return;
-    const TrlGame& g = games[index ? index[i] : i];
+    const int gi = index ? index[i] : i;
+    if (gi < 0) return;  // nothing to encode for this item (its buffers keep their old content)
+    const TrlGame& g = games[gi];
     const int turn = g.turn & 1;
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
