@@ -111,6 +111,91 @@ def cpu_baseline(boards, cur, alt, target_s=12.0):
                                      "it cannot travel to the GPU box"}
 
 
+def run_selfplay(args, rank, world, local_rank):
+    """BASELINE config 3 (4096 concurrent games per GPU, AlphaSame(10,16) random init bf16,
+    MAX_ITER=160, Gamma root noise + FPU reduction): MCTS simulations/s and self-play games/hour.
+    One engine step = one simulation in every game; the whole step is one CUDA graph."""
+    import torch
+    import torch.distributed as dist
+    from tetris_reinforcement_learning_b200 import architectures as arch
+    from tetris_reinforcement_learning_b200.config import Config
+    from tetris_reinforcement_learning_b200.selfplay import SelfPlayEngine, make_net_evaluator, shard_for_rank
+    dev = torch.device("cuda", local_rank)
+    torch.manual_seed(0)
+    mc = arch.AlphaSameConfig(blocks=10, filters=16)
+    net = arch.AlphaSame(mc).to(dev)
+    ev = make_net_evaluator(net, torch.bfloat16)
+    G = args.games
+    sh = shard_for_rank(rank, world, G)
+
+    def engine(max_iter, n_games=G, **kw):
+        cfg = Config(visual=False, ruleset="s2", model="pytorch", model_config=mc, MAX_ITER=max_iter, CPUCT=0.75,
+                     training=True, use_playout_cap_randomization=False, use_dirichlet_noise=True,
+                     FpuStrategy="reduction", use_forced_playouts_and_policy_target_pruning=args.forced)
+        return SelfPlayEngine(cfg, ev, n_games, device=dev, seed=20261018, first_game_id=sh["first_game_id"],
+                              game_id_stride=sh["game_id_stride"], feature_dtype=torch.bfloat16, **kw)
+
+    eng = engine(160)
+    eng.step(12)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.step(args.selfplay_steps)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    samples, _ = eng.drain()
+    ctl = eng.get_ctl()
+    # mean game length in plies, from complete games of a short-search run with the same net
+    n_fast = min(G, 256)
+    fast = engine(8, n_games=n_fast, max_rounds=1000, restart_finished=False)
+    plies = []
+    for _ in range(200):
+        fast.step(64)
+        _, ends = fast.drain()
+        plies.extend(int(e["plies"]) for e in ends)
+        if len(plies) >= n_fast:
+            break
+    mean_plies = float(np.mean(plies)) if plies else float("nan")
+    stats = torch.tensor([ms, float(G * args.selfplay_steps), float(len(samples))], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, sims, nsamples = float(mx[0]), float(sm[1]), float(sm[2])
+    else:
+        sims, nsamples = float(stats[1]), float(stats[2])
+    sims_per_s = sims / (ms * 1e-3)
+    flops_per_eval = 86.5e6  # AlphaSame(10,16), both grids (SURVEY §8d)
+    return {
+        "mcts_sims_per_sec": {
+            "value": sims_per_s, "unit": "sims/s", "games_per_gpu": G, "n_gpus": world, "steps": args.selfplay_steps,
+            "ms_per_step": ms / args.selfplay_steps, "max_iter": 160, "net": "AlphaSame(blocks=10, filters=16) bf16, CUDA graph",
+            "searches_finished": nsamples, "status_nonzero": int((ctl["status"] != 0).sum()),
+            "roofline": {"bound": "tensor", "achieved": sims_per_s / world * flops_per_eval / 1e12,
+                         "peak": load_tensor_peak(), "unit": "TFLOP/s",
+                         "frac": sims_per_s / world * flops_per_eval / 1e12 / load_tensor_peak(),
+                         "note": "the step is bound by the policy/value net (one evaluation per simulation)"},
+        },
+        "selfplay_games_per_hour": {
+            "value": sims_per_s / (160.0 * mean_plies) * 3600.0 if mean_plies == mean_plies else None,
+            "unit": "games/h", "derived": True, "mean_plies_per_game": mean_plies, "games_measured": len(plies),
+            "how": "sims/s / (MAX_ITER x mean plies per game); plies from complete games of a MAX_ITER=8 run of the same net",
+        },
+    }
+
+
+def load_tensor_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["bf16_tflops_sustained"])
+    return 1400.0
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path = the oracle port
     (the reference is pure Python and cannot travel to the GPU box), all host threads."""
@@ -216,6 +301,14 @@ def run_ours(args, rank, world, local_rank):
     h2d = n * (80 + 2)
     d2h = n * (MASK_WORDS * 4 + 2 + 4)
 
+    # free the sweep's buffers before the self-play leg
+    del d_mask, h_mask
+    torch.cuda.empty_cache()
+    also = None
+    if not args.no_selfplay:
+        also = run_selfplay(args, rank, world, local_rank)
+        also["_launches"] = 0
+
     # ---- reduce over ranks: max time, summed work ----
     stats = torch.tensor([total_ms, e2e_s, float(placements), float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
     if world > 1:
@@ -254,6 +347,9 @@ def run_ours(args, rank, world, local_rank):
         from oracle import oracle
         oracle.build()
         line["cpu_baseline"] = cpu_baseline(boards, cur, alt)
+    if also is not None:
+        line["also"] = also
+        line["gpu_launches"] += also.pop("_launches", 0)
     print(json.dumps(line))
 
 
@@ -267,6 +363,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-sample-boards", type=int, default=40_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-selfplay", action="store_true", help="skip the sims/s + games/h leg")
+    ap.add_argument("--games", type=int, default=4096, help="concurrent self-play games per GPU")
+    ap.add_argument("--selfplay-steps", type=int, default=320)
+    ap.add_argument("--forced", action="store_true", help="forced playouts + policy-target pruning (config 4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 

@@ -174,10 +174,12 @@ int trl_env_step_host(TrlGame* games, const uint16_t* moves, int n, TrlStepOut* 
 
 /*
  * Game() + Game.setup() (game.py:8-38): empty boards, one 7-bag each (player 0 first),
- * first piece spawned, turn = 0, rounds = 1.  game_id[i] = first_game_id + i.
+ * first piece spawned, turn = 0, rounds = 1.  game_id[i] = first_game_id + i * id_stride
+ * (id_stride = number of ranks when games are sharded over GPUs).
  */
-int trl_game_setup(TrlGame* games, int n, uint32_t first_game_id, uint64_t seed, void* stream);
-int trl_game_setup_host(TrlGame* games, int n, uint32_t first_game_id, uint64_t seed);
+int trl_game_setup(TrlGame* games, int n, uint32_t first_game_id, uint32_t id_stride, uint64_t seed,
+                   void* stream);
+int trl_game_setup_host(TrlGame* games, int n, uint32_t first_game_id, uint32_t id_stride, uint64_t seed);
 
 /* ------------------------------------------------------------------------------------ */
 /* network input encoding                                                                */

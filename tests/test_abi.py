@@ -50,7 +50,7 @@ def test_bad_arguments_are_rejected_without_a_gpu(built_so):
     assert L.trl_movegen_host(None, None, None, 4, None, None, 0, None, None) == -1
     assert L.trl_env_step(None, None, 1, None, 0, 0, None) == -1
     assert L.trl_movegen(None, None, None, 0, None, None, 0, None, None, None) == -1  # NULL inputs
-    assert L.trl_game_setup(None, 1, 0, 0, None) == -1
+    assert L.trl_game_setup(None, 1, 0, 1, 0, None) == -1
 
 
 def test_missing_library_fails_loudly(monkeypatch):

@@ -78,3 +78,51 @@ def test_networks_are_state_dict_compatible_with_reference(family):
     for w, g_ in zip(want, got):
         assert torch.allclose(w, g_, atol=1e-6, rtol=1e-5)
     assert torch.allclose(want[0], packed[0], atol=1e-6) and torch.allclose(want[1], packed[1], atol=1e-5)
+
+
+def test_sample_layout_and_reflections_match_reference():
+    """samples_from_search / reflect_* / policy targets vs the reference's own play_game block
+    (ai.py:1613-1666), search_statistics (ai.py:1330-1361) and reflect_policy (ai.py:1452-1516)."""
+    import types
+    import numpy as np
+    from oracle import mcts_oracle, oracle
+    from oracle.pin_mcts_against_reference import positions
+    from tetris_reinforcement_learning_b200 import ai as mine
+    from tetris_reinforcement_learning_b200.const import index_to_move
+    ref_ai = rh.full_modules().ai
+    rng = np.random.default_rng(0)
+    for rec in positions(12, 77)[:8]:
+        moves = mcts_oracle.legal_moves(rec[0])
+        visits = rng.integers(0, 9, size=len(moves))
+        visits[rng.integers(0, len(moves))] += 5
+        # a mock reference tree holding the same root children
+        tree = ref_ai.MCTSTree()
+        tree.create_node(identifier="root", data=ref_ai.NodeState())
+        for m, n in zip(moves, visits):
+            st = ref_ai.NodeState(move=index_to_move(int(m)))
+            st.visit_count = int(n)
+            tree.create_node(data=st, parent="root")
+        want_policy = ref_ai.search_statistics(tree)
+        got = mine.policy_target_from_visits(moves, visits)
+        assert np.array_equal(np.asarray(want_policy, dtype=np.float64), got)
+        want_ref = ref_ai.reflect_policy(want_policy)
+        assert np.array_equal(np.asarray(want_ref, dtype=np.float64), mine.reflect_policy_array(got))
+        assert mine.reflect_policy(want_policy) == want_ref
+        # full sample block
+        game = rh.make_game(rec[0])
+        move_data = [*ref_ai.game_to_X(game)]
+        blocks = mine.samples_from_search(rec[0], moves, visits, augment=True)
+        k = 0
+        for a in range(2):
+            for o in range(2):
+                d = [f.copy() if isinstance(f, np.ndarray) else f for f in move_data]
+                if a == 1:
+                    d[0] = ref_ai.reflect_grid(d[0]); d[1] = ref_ai.reflect_pieces(d[1])
+                if o == 1:
+                    d[5] = ref_ai.reflect_grid(d[5]); d[6] = ref_ai.reflect_pieces(d[6])
+                d = [f.tolist() if isinstance(f, np.ndarray) else f for f in d]
+                d.append(want_policy if a == 0 else want_ref)
+                assert blocks[k] == d
+                k += 1
+        plain = mine.samples_from_search(rec[0], moves, visits, augment=False)
+        assert plain[0][:-1] == [f.tolist() if isinstance(f, np.ndarray) else f for f in move_data]

@@ -11,7 +11,7 @@ from .state import GAME_DTYPE, PLAYER_DTYPE
 _SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtrl_b200.so")
 _lib = None
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_void_p, c_int, c_u64, c_u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32
 
@@ -28,8 +28,8 @@ SIGNATURES = {
                                  c_void_p, c_void_p]),
     "trl_env_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_u64, c_void_p]),
     "trl_env_step_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_u64]),
-    "trl_game_setup": (c_int, [c_void_p, c_int, c_u32, c_u64, c_void_p]),
-    "trl_game_setup_host": (c_int, [c_void_p, c_int, c_u32, c_u64]),
+    "trl_game_setup": (c_int, [c_void_p, c_int, c_u32, c_u32, c_u64, c_void_p]),
+    "trl_game_setup_host": (c_int, [c_void_p, c_int, c_u32, c_u32, c_u64]),
     "trl_sizeof_search_ctl": (c_int, []),
     "trl_sizeof_sample": (c_int, []),
     "trl_search_select": (c_int, [c_void_p, c_void_p, c_void_p]),

@@ -40,12 +40,12 @@ env_step_kernel(TrlGame* __restrict__ games, const uint16_t* __restrict__ moves,
 }
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-game_setup_kernel(TrlGame* __restrict__ games, int n, uint32_t first_game_id, uint64_t seed) {
+game_setup_kernel(TrlGame* __restrict__ games, int n, uint32_t first_game_id, uint32_t id_stride, uint64_t seed) {
     __shared__ __align__(16) TrlGame s_games[kWarpsPerBlock];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int i = blockIdx.x * kWarpsPerBlock + wib;
     if (i >= n) return;
-    if (lane == 0) trl_game_setup_scalar(&s_games[wib], first_game_id + (uint32_t)i, seed);
+    if (lane == 0) trl_game_setup_scalar(&s_games[wib], first_game_id + (uint32_t)i * id_stride, seed);
     __syncwarp();
     uint32_t* sg = reinterpret_cast<uint32_t*>(&s_games[wib]);
     uint32_t* gg = reinterpret_cast<uint32_t*>(games + i);
@@ -63,11 +63,12 @@ extern "C" int trl_env_step(TrlGame* games, const uint16_t* moves, int n, TrlSte
     return trl_check(cudaGetLastError());
 }
 
-extern "C" int trl_game_setup(TrlGame* games, int n, uint32_t first_game_id, uint64_t seed, void* stream) {
+extern "C" int trl_game_setup(TrlGame* games, int n, uint32_t first_game_id, uint32_t id_stride, uint64_t seed,
+                              void* stream) {
     if (n < 0 || !games) return TRL_E_ARG;
     if (n == 0) return TRL_OK;
     game_setup_kernel<<<(n + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-        games, n, first_game_id, seed);
+        games, n, first_game_id, id_stride, seed);
     return trl_check(cudaGetLastError());
 }
 
@@ -92,14 +93,14 @@ extern "C" int trl_env_step_host(TrlGame* games, const uint16_t* moves, int n, T
     return rc;
 }
 
-extern "C" int trl_game_setup_host(TrlGame* games, int n, uint32_t first_game_id, uint64_t seed) {
+extern "C" int trl_game_setup_host(TrlGame* games, int n, uint32_t first_game_id, uint32_t id_stride, uint64_t seed) {
     if (n < 0 || !games) return TRL_E_ARG;
     if (n == 0) return TRL_OK;
     cudaStream_t s = trl_host_stream();
     if (!s) return TRL_E_CUDA;
     TrlGame* d_games = (TrlGame*)trl_workspace(TRL_WS_HOST_STAGE, (size_t)n * sizeof(TrlGame));
     if (!d_games) return TRL_E_NOMEM;
-    int rc = trl_game_setup(d_games, n, first_game_id, seed, s);
+    int rc = trl_game_setup(d_games, n, first_game_id, id_stride, seed, s);
     if (!rc) rc = trl_check(cudaMemcpyAsync(games, d_games, (size_t)n * sizeof(TrlGame), cudaMemcpyDeviceToHost, s));
     if (!rc) rc = trl_check(cudaStreamSynchronize(s));
     return rc;

@@ -9,10 +9,10 @@ from . import _native
 from .state import GAME_DTYPE, STEPOUT_DTYPE
 
 
-def game_setup_host(n, first_game_id=0, seed=0):
+def game_setup_host(n, first_game_id=0, seed=0, id_stride=1):
     """n fresh games after Game.setup() (game.py:28-32) -> GAME_DTYPE[n]."""
     games = np.zeros(n, dtype=GAME_DTYPE)
-    rc = _native.lib().trl_game_setup_host(games.ctypes.data, n, int(first_game_id), int(seed))
+    rc = _native.lib().trl_game_setup_host(games.ctypes.data, n, int(first_game_id), int(id_stride), int(seed))
     _native.check(rc, "trl_game_setup_host")
     return games
 
@@ -35,10 +35,10 @@ def env_step_host(games, moves, add_bag=True, seed=0):
     return out
 
 
-def game_setup_device(games, first_game_id=0, seed=0):
+def game_setup_device(games, first_game_id=0, seed=0, id_stride=1):
     """games: uint8[n,400] CUDA tensor, filled in place on the current stream."""
     import torch
-    rc = _native.lib().trl_game_setup(games.data_ptr(), games.shape[0], int(first_game_id), int(seed),
+    rc = _native.lib().trl_game_setup(games.data_ptr(), games.shape[0], int(first_game_id), int(id_stride), int(seed),
                                       torch.cuda.current_stream().cuda_stream)
     _native.check(rc, "trl_game_setup")
 

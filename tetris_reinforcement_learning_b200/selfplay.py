@@ -146,14 +146,9 @@ class SelfPlayEngine:
     def new_games(self, first_game_id=0, stride=1):
         """Fresh Game.setup() in every slot; ids first, first+stride, ..."""
         games = self.t["games"].view(self.G, 400)
-        if stride == 1:
-            rc = self.lib.trl_game_setup(games.data_ptr(), self.G, int(first_game_id), self.seed,
-                                         torch.cuda.current_stream(self.device).cuda_stream)
-            _native.check(rc, "trl_game_setup")
-        else:
-            from .env import game_setup_host
-            host = np.concatenate([game_setup_host(1, first_game_id + i * stride, self.seed) for i in range(self.G)])
-            self.set_games(host)
+        rc = self.lib.trl_game_setup(games.data_ptr(), self.G, int(first_game_id), int(stride), self.seed,
+                                     torch.cuda.current_stream(self.device).cuda_stream)
+        _native.check(rc, "trl_game_setup")
         self.t["next_game_id"].fill_(int(first_game_id + self.G * stride))
         ctl = np.zeros(self.G, dtype=CTL_DTYPE)
         ctl["active"] = 1
@@ -255,3 +250,12 @@ def make_net_evaluator(net, dtype=torch.bfloat16, channels_last=True):
         return out[0], out[1]
 
     return evaluate
+
+
+def shard_for_rank(rank, world, games_per_gpu):
+    """Self-play shards independently: rank r owns game ids r, r + world, r + 2*world, ... so the
+    set of games played (and each game's Philox streams) is the same for any GPU count; there
+    is no collective on the data path.  -> dict(first_game_id, game_id_stride, n_games)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    return {"first_game_id": int(rank), "game_id_stride": int(world), "n_games": int(games_per_gpu)}

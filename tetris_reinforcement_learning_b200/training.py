@@ -1,0 +1,203 @@
+"""Training step and gating battles ("next" rows of the hot-path scope: the callers either side
+of self-play).  Mirrors reference ai.py:1087-1220 (train_network_pytorch), :1871-1973
+(load_data_and_train_model / get_data_filenames) and :1975-2114 (battle_networks).
+
+New capability relative to the reference (BASELINE config 5): when torch.distributed is
+initialised, gradients are averaged across ranks with ONE flat NCCL all-reduce per optimizer
+step (the nets are 6-21 M parameters = 24-83 MB of fp32 gradients, latency-bound on NVLink,
+so bucketing / overlap buys nothing)."""
+import gc
+import json
+import os
+import random
+
+import numpy as np
+import torch
+from torch import nn
+
+from .architectures import AuxBaseResNetConfig, compute_aux_targets
+from .const import COLS, POLICY_SIZE, ROWS
+
+
+def get_data_filenames(config):
+    """Files of the newest `sets_to_train_with` data sets (ai.py:1929-1961)."""
+    from .ai import highest_data_number
+    max_set = highest_data_number(config)
+    names = []
+    for filename in os.listdir(config.data_dir):
+        stem = filename.split(".")[0]
+        if stem.isdigit() and int(stem) > max_set - config.sets_to_train_with:
+            names.append(filename)
+    if config.shuffle:
+        random.shuffle(names)
+    return names
+
+
+def load_data(config):
+    return [json.load(open(f"{config.data_dir}/{f}")) for f in get_data_filenames(config)]
+
+
+def _to_tensors(samples):
+    cols = list(map(list, zip(*samples)))
+    out = []
+    for c in cols:
+        t = torch.tensor(c)
+        if t.dim() == 3 and t.shape[1] == ROWS and t.shape[2] == COLS:
+            t = t.unsqueeze(1).float()
+        out.append(t)
+    return out
+
+
+def allreduce_gradients(model):
+    """Average gradients over all ranks with one flat all-reduce (no-op without a process group)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat /= dist.get_world_size()
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+def train_network_pytorch(config, model, samples, data_number=None, log=True):
+    """AdamW on MSE(value) + CE(policy) (+ aux_weight * MSE(aux)); returns the mean losses."""
+    from .ai import highest_data_number, logs_dir
+    device = next(model.parameters()).device
+    feats = _to_tensors(samples)
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(*feats), batch_size=config.batch_size,
+                                         shuffle=config.shuffle)
+    mse, ce = nn.MSELoss(), nn.CrossEntropyLoss()
+    opt = torch.optim.AdamW(model.parameters(), lr=config.learning_rate, weight_decay=config.weight_decay)
+    has_aux = isinstance(config.model_config, AuxBaseResNetConfig)
+    aux_w = config.model_config.aux_weight if has_aux else 0.0
+    model.train()
+    tot = dict(loss=0.0, value=0.0, policy=0.0, aux=0.0)
+    batches = 0
+    for _ in range(config.epochs):
+        for batch in loader:
+            batch = [b.to(device) for b in batch]
+            y_policy = batch.pop().reshape(-1, POLICY_SIZE).float()
+            y_value = batch.pop().float()
+            out = model(*batch)
+            l_value = mse(out[0].reshape(-1), y_value)
+            l_policy = ce(out[1].reshape(-1, POLICY_SIZE), y_policy)
+            loss = l_value + l_policy
+            if has_aux:
+                l_aux = mse(out[2], compute_aux_targets(batch[0]))
+                loss = loss + aux_w * l_aux
+                tot["aux"] += l_aux.item()
+            loss.backward()
+            allreduce_gradients(model)
+            opt.step()
+            opt.zero_grad()
+            tot["loss"] += loss.item(); tot["value"] += l_value.item(); tot["policy"] += l_policy.item()
+            batches += 1
+    model.eval()
+    avg = {k: v / max(batches, 1) for k, v in tot.items()}
+    print(f"loss: {avg['loss']:>7f}  value: {avg['value']:>7f}  policy: {avg['policy']:>7f}" +
+          (f"  aux: {avg['aux']:>7f}" if has_aux else ""))
+    if log:
+        entry = {"model_version": config.model_version,
+                 "data_number": data_number if data_number is not None else highest_data_number(config),
+                 "loss": avg["loss"], "value_loss": avg["value"], "policy_loss": avg["policy"], "backend": "pytorch"}
+        if has_aux:
+            entry["aux_loss"] = avg["aux"]
+        with open(logs_dir() / "training_log.jsonl", "a") as f:
+            f.write(json.dumps(entry) + "\n")
+    return avg
+
+
+def train_network(config, model, samples):
+    if config.model != "pytorch":
+        raise NotImplementedError("only model='pytorch' is implemented")
+    return train_network_pytorch(config, model, samples)
+
+
+def load_data_and_train_model(config, model, data=None):
+    """'merge' loading: newest sets first, set of age a contributes a random decay_factor**a
+    fraction of its samples (ai.py:1871-1901)."""
+    if config.data_loading_style != "merge":
+        raise NotImplementedError(f"data_loading_style={config.data_loading_style!r}")
+    n_sets = 0
+    if data is None:
+        data = []
+        names = sorted(get_data_filenames(config), key=lambda x: int(x.split(".")[0]), reverse=True)
+        for age, name in enumerate(names):
+            one = json.load(open(f"{config.data_dir}/{name}"))
+            data.extend(random.sample(one, int(len(one) * config.decay_factor ** age)))
+        n_sets = len(names)
+    else:
+        n_sets = len(data)
+        data = [x for one in data for x in one]
+    if config.shuffle:
+        random.shuffle(data)
+    print(f"Training with {len(data)} samples over {n_sets} sets with decay factor {config.decay_factor}")
+    out = train_network(config, model, data)
+    gc.collect()
+    return out
+
+
+def _check_threshold(wins, games, threshold, threshold_type):
+    if threshold is None:
+        return None
+    if threshold_type == "more":
+        if wins[0] > threshold * games:
+            return True
+        if wins[1] >= (1 - threshold) * games:
+            return False
+    elif threshold_type == "moreorequal":
+        if wins[0] >= threshold * games:
+            return True
+        if wins[1] > (1 - threshold) * games:
+            return False
+    return None
+
+
+def battle_networks(NN_1, config_1, NN_2, config_2, threshold, threshold_type, games,
+                    network_1_title="Network 1", network_2_title="Network 2", screen=None, seed=None):
+    """All `games` battles run concurrently on the GPU (the reference's batched variant,
+    ai.py:2071-2114: colours alternate by game index, no early termination, post-hoc threshold).
+    Every search is evaluated by the network that owns the side to move at the ROOT."""
+    from .ai import _engine_for
+    from .selfplay import make_net_evaluator
+    if config_1.ruleset != config_2.ruleset:
+        raise NotImplementedError("Ruleset's aren't equal")
+    keys = ("MAX_ITER", "CPUCT", "DPUCT", "FpuStrategy", "FpuValue", "use_root_softmax", "RootSoftmaxTemp", "use_tanh",
+            "training", "temperature")
+    if any(getattr(config_1, k) != getattr(config_2, k) for k in keys):
+        raise NotImplementedError("battle_networks on the device path needs identical search settings for both sides")
+    dev = torch.device("cuda")
+    ev1 = make_net_evaluator(NN_1.to(dev), torch.bfloat16)
+    ev2 = make_net_evaluator(NN_2.to(dev), torch.bfloat16)
+    side = (torch.arange(games, device=dev) % 2).to(torch.uint8)  # 0: NN_1 plays player 0
+    holder = {}
+
+    def evaluator(grids, extras):
+        v1, l1 = ev1(grids, extras)
+        v2, l2 = ev2(grids, extras)
+        turn = holder["engine"].t["games"].view(games, 400)[:, 384]
+        use2 = ((turn ^ side) & 1).bool()
+        return torch.where(use2, v2.reshape(-1), v1.reshape(-1)), torch.where(use2[:, None], l2, l1)
+
+    eng = _engine_for(config_1, evaluator, games, seed=seed, restart_finished=False)
+    holder["engine"] = eng
+    ends = []
+    while eng.get_ctl()["active"].any():
+        eng.step(max(8, config_1.MAX_ITER))
+        ends.extend(eng.drain()[1])
+    wins = np.zeros(2, dtype=float)
+    for e in ends:
+        s = int(e["game_id"]) % 2
+        w = int(e["winner"])
+        if w == -1:
+            wins += 0.5
+        elif s == 0:
+            wins[w] += 1
+        else:
+            wins[1 - w] += 1
+    return wins, _check_threshold(wins, games, threshold, threshold_type)
