@@ -314,6 +314,25 @@ int trl_search_movegen(const TrlSearchBuffers* buf, void* stream);
 int trl_search_expand(const TrlSearchBuffers* buf, const TrlSearchParams* prm, const void* values,
                       const void* logits, int dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------ */
+/* fused convolutional trunk of the policy/value net (tcgen05 tensor cores)               */
+/* replaces AlphaSame.process_grid (architectures.py:120-126, blocks :27-57) in eval mode  */
+/* for filters = 16, kernels = 1: conv5x5 stem -> n_blocks pre-activation residual blocks  */
+/* -> BN-ReLU -> conv1x1 -> BN-ReLU -> flatten.                                            */
+/* ------------------------------------------------------------------------------------ */
+
+/*
+ * grids    [n_images][400] bf16 0/1 board cells (row-major 40 x 10)
+ * w_packed [2*n_blocks][9][2][2][8][8] bf16: per 3x3 tap the 16x16 weight matrix in the UMMA
+ *          K-major core-matrix order [k chunk][n group][n][k] (bn2 scale folded into conv 1)
+ * consts   [n_blocks*48 + 50] f32: per block bn1 scale[16], bn1 bias[16], bn2 bias[16]; then
+ *          final bn scale[16], bias[16], 1x1 weights[16], last bn scale, bias
+ * stem_lut [5][32][16] f32: partial sums of the 5x5 stem per kernel row and 5-bit input pattern
+ * out      [n_images][400] bf16 trunk features
+ */
+int trl_alphasame_trunk(const void* grids_bf16, int n_images, int n_blocks, const void* w_packed,
+                        const float* consts, const float* stem_lut, void* out_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,67 @@
+"""GPU tests of the fused tcgen05 trunk (floating point: compared with a plain PyTorch fp32
+reference of the same op, tolerance written here)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_net(blocks, seed):
+    import torch
+    from tetris_reinforcement_learning_b200 import architectures as arch
+    torch.manual_seed(seed)
+    net = arch.AlphaSame(arch.AlphaSameConfig(blocks=blocks, filters=16)).to("cuda:0").eval()
+    for m in net.modules():  # non-trivial BatchNorm statistics
+        if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm1d)):
+            m.running_mean.normal_(0, 0.3); m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.7, 1.3); m.bias.data.normal_(0, 0.2)
+    return net
+
+
+@pytest.mark.parametrize("blocks,n", [(1, 3), (2, 700), (10, 2048)])
+def test_trunk_matches_pytorch_fp32(blocks, n):
+    """Tolerance: bf16 operands with fp32 accumulation and an fp32 residual stream ->
+    |err| <= 0.03 * max|ref| + 0.02 elementwise, and mean |err| <= 0.5 % of mean |ref|."""
+    import torch
+    from tetris_reinforcement_learning_b200 import trunk
+    net = _random_net(blocks, 1)
+    g = torch.Generator(device="cuda:0").manual_seed(2)
+    grids = (torch.rand((n, 1, 40, 10), generator=g, device="cuda:0") < 0.35).float()
+    grids[0] = 0          # empty board
+    grids[-1] = 1         # full board
+    with torch.no_grad():
+        ref = net.grid_features(grids)
+    packed = trunk.pack_alphasame_trunk(net)
+    got = trunk.trunk_forward(packed, grids.to(torch.bfloat16)).float()
+    torch.cuda.synchronize()
+    err = (got - ref).abs()
+    scale = ref.abs().max().item()
+    assert torch.isfinite(got).all()
+    assert err.max().item() <= 0.03 * scale + 0.02, (err.max().item(), scale)
+    assert err.mean().item() <= 0.005 * ref.abs().mean().item() + 1e-3, (err.mean().item(), ref.abs().mean().item())
+
+
+def test_fused_evaluator_matches_module_and_runs_in_engine():
+    import torch
+    from tetris_reinforcement_learning_b200 import architectures as arch, trunk
+    from tetris_reinforcement_learning_b200.config import Config
+    from tetris_reinforcement_learning_b200.selfplay import SelfPlayEngine
+    net = _random_net(10, 3)
+    B = 256
+    g = torch.Generator(device="cuda:0").manual_seed(5)
+    grids = (torch.rand((2 * B, 1, 40, 10), generator=g, device="cuda:0") < 0.3).float()
+    extras = torch.randint(0, 2, (B, 105), generator=g, device="cuda:0").float()
+    with torch.no_grad():
+        v_ref, l_ref = net.forward_packed(grids, extras)
+    import copy
+    ev = trunk.make_fused_evaluator(copy.deepcopy(net))
+    with torch.no_grad():
+        v, l = ev(grids.to(torch.bfloat16), extras.to(torch.bfloat16))
+    assert (v.float().reshape(-1) - v_ref.reshape(-1)).abs().max().item() < 0.03
+    assert (l.float() - l_ref).abs().max().item() < 0.05 * l_ref.abs().max().item() + 0.05
+    # inside the engine under a CUDA graph
+    cfg = Config(visual=False, ruleset="s2", model="pytorch", model_config=arch.AlphaSameConfig(), MAX_ITER=8, training=True)
+    eng = SelfPlayEngine(cfg, ev, 128, seed=1, feature_dtype=torch.bfloat16, max_rounds=5)
+    eng.step(200)
+    samples, ends = eng.drain()
+    assert len(samples) > 0 and len(ends) > 0 and (eng.get_ctl()["status"] == 0).all()

@@ -35,6 +35,7 @@ SIGNATURES = {
     "trl_search_select": (c_int, [c_void_p, c_void_p, c_void_p]),
     "trl_search_movegen": (c_int, [c_void_p, c_void_p]),
     "trl_search_expand": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "trl_alphasame_trunk": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "trl_encode_features": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
 }
 

@@ -1,0 +1,80 @@
+"""Host side of the fused tcgen05 trunk (csrc/trunk.cu): BatchNorm folding, weight packing into
+the UMMA core-matrix order, and the evaluator that runs trunk kernel + PyTorch heads.
+
+Applies to AlphaSame with filters = 16 and kernels = 1 (BASELINE's blocks=10 filters=16 net and
+any other depth); other nets use the plain PyTorch evaluator (selfplay.make_net_evaluator)."""
+import torch
+
+from . import _native
+from .architectures import SIDE_FEATS, AlphaSame
+
+
+def supports(net):
+    return (isinstance(net, AlphaSame) and net.conv1.out_channels == 16 and net.kernel1.out_channels == 1
+            and len(net.res_blocks) <= 40)
+
+
+def _fold_bn(bn):
+    s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    return s, bn.bias.detach().float() - bn.running_mean.detach().float() * s
+
+
+def _pack_conv(w):
+    """(16 out, 16 in, 3, 3) -> [9 taps][k chunk 2][n group 2][n 8][k 8] (K-major core matrices)."""
+    t = w.permute(2, 3, 0, 1).reshape(9, 16, 16)          # [tap][o][i]
+    t = t.reshape(9, 2, 8, 2, 8)                           # [tap][ng][n][kc][k]
+    return t.permute(0, 3, 1, 2, 4).contiguous()           # [tap][kc][ng][n][k]
+
+
+def pack_alphasame_trunk(net, device=None):
+    """-> dict(w_packed bf16 [2*blocks, 9*256], consts f32, stem_lut f32 [5,32,16], n_blocks)."""
+    assert supports(net)
+    device = device or next(net.parameters()).device
+    convs, consts = [], []
+    for blk in net.res_blocks:
+        s1, b1 = _fold_bn(blk.conv_block1[0])
+        s2, b2 = _fold_bn(blk.conv_block2[0])
+        w1 = blk.conv_block1[2].weight.detach().float() * s2[:, None, None, None]  # bn2 scale folded
+        w2 = blk.conv_block2[3].weight.detach().float()
+        convs += [_pack_conv(w1), _pack_conv(w2)]
+        consts += [s1, b1, b2]
+    sa, ba = _fold_bn(net.batchnorm1)
+    sb, bb = _fold_bn(net.batchnorm2)
+    consts += [sa, ba, net.kernel1.weight.detach().float().reshape(16), sb.reshape(1), bb.reshape(1)]
+    w_stem = net.conv1.weight.detach().float()[:, 0]                               # [16][5][5]
+    bits = ((torch.arange(32)[:, None] >> torch.arange(5)[None, :]) & 1).float().to(w_stem.device)  # [pat][k]
+    lut = torch.einsum("pk,crk->rpc", bits, w_stem).contiguous()                  # [r][pat][c]
+    return {"w_packed": torch.stack(convs).reshape(len(convs), -1).to(device=device, dtype=torch.bfloat16).contiguous(),
+            "consts": torch.cat([c.reshape(-1) for c in consts]).to(device).contiguous(),
+            "stem_lut": lut.to(device).contiguous(), "n_blocks": len(net.res_blocks)}
+
+
+def trunk_forward(packed, grids, out=None):
+    """grids: bf16 CUDA tensor with n*400 elements ([n,1,40,10] or [n,400]) -> bf16 [n,400]."""
+    n = grids.numel() // 400
+    if grids.dtype != torch.bfloat16 or not grids.is_contiguous():
+        grids = grids.to(torch.bfloat16).contiguous()
+    if out is None:
+        out = torch.empty((n, 400), dtype=torch.bfloat16, device=grids.device)
+    rc = _native.lib().trl_alphasame_trunk(grids.data_ptr(), n, packed["n_blocks"], packed["w_packed"].data_ptr(),
+                                           packed["consts"].data_ptr(), packed["stem_lut"].data_ptr(), out.data_ptr(),
+                                           torch.cuda.current_stream(grids.device).cuda_stream)
+    _native.check(rc, "trl_alphasame_trunk")
+    return out
+
+
+def make_fused_evaluator(net, dtype=torch.bfloat16):
+    """Engine evaluator: fused tcgen05 trunk on both grids, then the (GEMM-shaped) heads in PyTorch."""
+    assert supports(net) and dtype == torch.bfloat16
+    net = net.eval()
+    packed = pack_alphasame_trunk(net)
+    heads = {"osidedense": net.osidedense.to(dtype), "policy": net.policy_head.to(dtype), "value": net.value_head.to(dtype)}
+
+    def evaluate(grids, extras):
+        b = extras.shape[0]
+        feats = trunk_forward(packed, grids)
+        x = torch.cat([feats[:b], extras[:, :SIDE_FEATS], heads["osidedense"](feats[b:]), extras[:, SIDE_FEATS:]], dim=1)
+        return heads["value"](x), heads["policy"](x)
+
+    evaluate.packed = packed
+    return evaluate
