@@ -119,12 +119,12 @@ def run_selfplay(args, rank, world, local_rank):
     import torch.distributed as dist
     from tetris_reinforcement_learning_b200 import architectures as arch
     from tetris_reinforcement_learning_b200.config import Config
-    from tetris_reinforcement_learning_b200.selfplay import SelfPlayEngine, make_net_evaluator, shard_for_rank
+    from tetris_reinforcement_learning_b200.selfplay import SelfPlayEngine, best_evaluator, make_net_evaluator, shard_for_rank
     dev = torch.device("cuda", local_rank)
     torch.manual_seed(0)
     mc = arch.AlphaSameConfig(blocks=10, filters=16)
     net = arch.AlphaSame(mc).to(dev)
-    ev = make_net_evaluator(net, torch.bfloat16)
+    ev = make_net_evaluator(net, torch.bfloat16) if args.net_path == "pytorch" else best_evaluator(net, torch.bfloat16)
     G = args.games
     sh = shard_for_rank(rank, world, G)
 
@@ -154,7 +154,7 @@ def run_selfplay(args, rank, world, local_rank):
     n_fast = min(G, 256)
     fast = engine(8, n_games=n_fast, max_rounds=1000, restart_finished=False)
     plies = []
-    for _ in range(200):
+    for _ in range(0 if args.no_game_length else 200):
         fast.step(64)
         _, ends = fast.drain()
         plies.extend(int(e["plies"]) for e in ends)
@@ -173,7 +173,8 @@ def run_selfplay(args, rank, world, local_rank):
     return {
         "mcts_sims_per_sec": {
             "value": sims_per_s, "unit": "sims/s", "games_per_gpu": G, "n_gpus": world, "steps": args.selfplay_steps,
-            "ms_per_step": ms / args.selfplay_steps, "max_iter": 160, "net": "AlphaSame(blocks=10, filters=16) bf16, CUDA graph",
+            "ms_per_step": ms / args.selfplay_steps, "max_iter": 160, "net": "AlphaSame(blocks=10, filters=16) bf16, " + ("PyTorch/cuDNN" if args.net_path == "pytorch" else
+                                                               "fused tcgen05 trunk + PyTorch heads") + ", CUDA graph",
             "searches_finished": nsamples, "status_nonzero": int((ctl["status"] != 0).sum()),
             "roofline": {"bound": "tensor", "achieved": sims_per_s / world * flops_per_eval / 1e12,
                          "peak": load_tensor_peak(), "unit": "TFLOP/s",
@@ -366,6 +367,8 @@ def main():
     ap.add_argument("--no-selfplay", action="store_true", help="skip the sims/s + games/h leg")
     ap.add_argument("--games", type=int, default=4096, help="concurrent self-play games per GPU")
     ap.add_argument("--selfplay-steps", type=int, default=320)
+    ap.add_argument("--no-game-length", action="store_true", help="skip the game-length run (profiling)")
+    ap.add_argument("--net-path", default="fused", choices=["fused", "pytorch"])
     ap.add_argument("--forced", action="store_true", help="forced playouts + policy-target pruning (config 4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)

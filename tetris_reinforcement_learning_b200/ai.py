@@ -251,13 +251,17 @@ def samples_from_search(state_rec, moves, visits, augment=True):
 # ---------------------------------------------------------------------------------------------
 
 def _engine_for(config, net, n_games, seed=None, **kw):
-    from .selfplay import SelfPlayEngine, make_net_evaluator
+    from .selfplay import SelfPlayEngine, best_evaluator
     if not torch.cuda.is_available():
         raise RuntimeError("self-play needs a CUDA device: the search, rules and placements run in libtrl_b200.so "
                            "(there is no CPU fallback)")
     seed = int(time.time_ns() & 0x7FFFFFFF) if seed is None else seed
     dtype = kw.pop("dtype", torch.bfloat16)
-    evaluator = net if callable(net) and not isinstance(net, torch.nn.Module) else make_net_evaluator(net.to("cuda"), dtype)
+    if callable(net) and not isinstance(net, torch.nn.Module):
+        evaluator = net
+    else:
+        import copy
+        evaluator = best_evaluator(copy.deepcopy(net).to("cuda"), dtype)  # the caller's module is left untouched
     return SelfPlayEngine(config, evaluator, n_games, seed=seed, feature_dtype=dtype, **kw)
 
 

@@ -236,6 +236,15 @@ class SelfPlayEngine:
         return int(self.get_ctl()["sims"].sum())
 
 
+def best_evaluator(net, dtype=torch.bfloat16):
+    """The fastest evaluator for `net`: the fused tcgen05 trunk + PyTorch heads where the
+    architecture allows it (AlphaSame, 16 filters), else the plain PyTorch path."""
+    from . import trunk
+    if dtype == torch.bfloat16 and trunk.supports(net):
+        return trunk.make_fused_evaluator(net, dtype)
+    return make_net_evaluator(net, dtype)
+
+
 def make_net_evaluator(net, dtype=torch.bfloat16, channels_last=True):
     """Wrap a network (architectures.*) as an engine evaluator: eval mode, `dtype` weights,
     packed inputs (no host tensors)."""

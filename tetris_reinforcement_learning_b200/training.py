@@ -164,7 +164,8 @@ def battle_networks(NN_1, config_1, NN_2, config_2, threshold, threshold_type, g
     ai.py:2071-2114: colours alternate by game index, no early termination, post-hoc threshold).
     Every search is evaluated by the network that owns the side to move at the ROOT."""
     from .ai import _engine_for
-    from .selfplay import make_net_evaluator
+    import copy
+    from .selfplay import best_evaluator
     if config_1.ruleset != config_2.ruleset:
         raise NotImplementedError("Ruleset's aren't equal")
     keys = ("MAX_ITER", "CPUCT", "DPUCT", "FpuStrategy", "FpuValue", "use_root_softmax", "RootSoftmaxTemp", "use_tanh",
@@ -172,8 +173,8 @@ def battle_networks(NN_1, config_1, NN_2, config_2, threshold, threshold_type, g
     if any(getattr(config_1, k) != getattr(config_2, k) for k in keys):
         raise NotImplementedError("battle_networks on the device path needs identical search settings for both sides")
     dev = torch.device("cuda")
-    ev1 = make_net_evaluator(NN_1.to(dev), torch.bfloat16)
-    ev2 = make_net_evaluator(NN_2.to(dev), torch.bfloat16)
+    ev1 = best_evaluator(copy.deepcopy(NN_1).to(dev), torch.bfloat16)
+    ev2 = best_evaluator(copy.deepcopy(NN_2).to(dev), torch.bfloat16)
     side = (torch.arange(games, device=dev) % 2).to(torch.uint8)  # 0: NN_1 plays player 0
     holder = {}
 

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=10)
     ap.add_argument("--filters", type=int, default=16)
     ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--fused", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
@@ -29,7 +30,22 @@ def main():
     dt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     cfg = Config(visual=False, ruleset="s2", model="pytorch", model_config=mc, MAX_ITER=args.iters, CPUCT=0.75,
                  training=True, use_playout_cap_randomization=False)
-    ev = make_net_evaluator(net, dt)
+    if args.fused:
+        from tetris_reinforcement_learning_b200 import trunk
+        ev = trunk.make_fused_evaluator(net)
+        g2 = torch.zeros((2 * args.games, 1, 40, 10), dtype=dt, device=dev)
+        for _ in range(3):
+            trunk.trunk_forward(ev.packed, g2)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            trunk.trunk_forward(ev.packed, g2)
+        b.record(); torch.cuda.synchronize()
+        tms = a.elapsed_time(b) / 20
+        print(f"fused trunk alone: {tms:.3f} ms for {2 * args.games} images -> {2 * args.games * 37.2e6 / tms / 1e9:.1f} TFLOP/s")
+    else:
+        ev = make_net_evaluator(net, dt)
     # net alone
     G = args.games
     grids = torch.zeros((2 * G, 1, 40, 10), dtype=dt, device=dev)
