@@ -308,11 +308,11 @@ int trl_search_select(const TrlSearchBuffers* buf, const TrlSearchParams* prm, v
 int trl_search_movegen(const TrlSearchBuffers* buf, void* stream);
 
 /* Step part 2: expand the leaf with the network outputs (values [n_games], logits
- * [n_games][11583]; dtype 0 = float32, 1 = bfloat16), root noise, backup, FPU refresh; when a
+ * [n_games][logits_stride >= 11583]; dtype 0 = float32, 1 = bfloat16), root noise, backup, FPU refresh; when a
  * search has used its iteration budget: choose the move, prune, emit the sample, play the move
  * on the real game, emit the game end and restart. */
 int trl_search_expand(const TrlSearchBuffers* buf, const TrlSearchParams* prm, const void* values,
-                      const void* logits, int dtype, void* stream);
+                      const void* logits, int logits_stride, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------ */
 /* fused convolutional trunk of the policy/value net (tcgen05 tensor cores)               */

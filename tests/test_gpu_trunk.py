@@ -58,7 +58,8 @@ def test_fused_evaluator_matches_module_and_runs_in_engine():
     with torch.no_grad():
         v, l = ev(grids.to(torch.bfloat16), extras.to(torch.bfloat16))
     assert (v.float().reshape(-1) - v_ref.reshape(-1)).abs().max().item() < 0.03
-    assert (l.float() - l_ref).abs().max().item() < 0.05 * l_ref.abs().max().item() + 0.05
+    assert l.shape[1] >= 11583
+    assert (l[:, :11583].float() - l_ref).abs().max().item() < 0.05 * l_ref.abs().max().item() + 0.05
     # inside the engine under a CUDA graph
     cfg = Config(visual=False, ruleset="s2", model="pytorch", model_config=arch.AlphaSameConfig(), MAX_ITER=8, training=True)
     eng = SelfPlayEngine(cfg, ev, 128, seed=1, feature_dtype=torch.bfloat16, max_rounds=5)

@@ -367,7 +367,7 @@ __device__ void finish_search(const TrlSearchBuffers& B, const TrlSearchParams& 
 
 __global__ void __launch_bounds__(kWarps * 32)
 search_expand_kernel(TrlSearchBuffers B, TrlSearchParams P, const void* __restrict__ values,
-                     const void* __restrict__ logits, int dtype) {
+                     const void* __restrict__ logits, int logits_stride, int dtype) {
     __shared__ __align__(16) TrlGame s_game[kWarps];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = blockIdx.x * kWarps + wib;
@@ -396,7 +396,7 @@ search_expand_kernel(TrlSearchBuffers B, TrlSearchParams P, const void* __restri
             // priors over the legal moves (ai.py:411-443).  softmax over all 11583 logits followed
             // by renormalisation over the legal ones == softmax over the legal logits.
             const uint16_t* mv = B.legal + (size_t)g * B.moves_cap;
-            const size_t lb = (size_t)g * TRL_POLICY_SIZE;
+            const size_t lb = (size_t)g * (size_t)logits_stride;
             double mx = -INFINITY;
             for (int c = lane; c < C; c += 32) mx = fmax(mx, (double)load_out(logits, lb + mv[c], dtype));
             mx = warp_max(mx);
@@ -506,10 +506,11 @@ extern "C" int trl_search_movegen(const TrlSearchBuffers* buf, void* stream) {
 }
 
 extern "C" int trl_search_expand(const TrlSearchBuffers* buf, const TrlSearchParams* prm, const void* values,
-                                 const void* logits, int dtype, void* stream) {
-    if (!buffers_ok(buf) || !prm || !values || !logits || (dtype != 0 && dtype != 1)) return TRL_E_ARG;
+                                 const void* logits, int logits_stride, int dtype, void* stream) {
+    if (!buffers_ok(buf) || !prm || !values || !logits || logits_stride < TRL_POLICY_SIZE || (dtype != 0 && dtype != 1))
+        return TRL_E_ARG;
     if (buf->n_games == 0) return TRL_OK;
     search_expand_kernel<<<(buf->n_games + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(
-        *buf, *prm, values, logits, dtype);
+        *buf, *prm, values, logits, logits_stride, dtype);
     return trl_check(cudaGetLastError());
 }

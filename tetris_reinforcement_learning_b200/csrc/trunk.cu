@@ -129,9 +129,11 @@ alphasame_trunk_kernel(const __nv_bfloat16* __restrict__ grids, int n_images, in
                        const uint4* __restrict__ w_packed,   // [2*n_blocks][9*512 B]
                        const float* __restrict__ consts,     // [n_blocks*48 + 50]
                        const float* __restrict__ stem_lut,   // [5][32][16]
-                       __nv_bfloat16* __restrict__ out) {    // [n_images][400]
+                       __nv_bfloat16* __restrict__ out,      // [n_images][400]
+                       int* __restrict__ next_image) {       // work counter (zeroed before launch)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_tmem_base;
+    __shared__ int s_img;
     const int tid = threadIdx.x, warp = tid >> 5;
     uint8_t* bufT = smem + kOffT;
     uint8_t* bufU = smem + kOffU;
@@ -171,10 +173,15 @@ alphasame_trunk_kernel(const __nv_bfloat16* __restrict__ grids, int n_images, in
     }
 
     uint32_t phase = 0;
-    for (int img = blockIdx.x; img < n_images; img += gridDim.x) {
+    // Images are handed out dynamically: a CTA that becomes resident late (e.g. while another
+    // kernel shares the GPU) simply takes fewer images instead of delaying the whole launch.
+    while (true) {
         // ---- input: 400 bf16 {0,1} -> bit rows with a 2-cell border (for the 5x5 stem) ----
+        if (tid == 0) s_img = atomicAdd(next_image, 1);
         if (tid < 48) s_rows[tid] = 0;
         __syncthreads();
+        const int img = s_img;
+        if (img >= n_images) break;
         const __nv_bfloat16* gin = grids + (size_t)img * 400;
         for (int c = tid; c < 400; c += kThreads) {
             if (__bfloat162float(gin[c]) != 0.f) atomicOr(&s_rows[c / 10 + 2], 1u << (c % 10 + 2));
@@ -298,8 +305,12 @@ extern "C" int trl_alphasame_trunk(const void* grids_bf16, int n_images, int n_b
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = sms * 3;  // 3 resident CTAs per SM (shared memory bound), persistent over images
     if (grid > n_images) grid = n_images;
+    int* counter = (int*)trl_workspace(TRL_WS_TRUNK_COUNTER, 256);
+    if (!counter) return TRL_E_NOMEM;
+    int rc = trl_check(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
+    if (rc) return rc;
     alphasame_trunk_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)grids_bf16, n_images, n_blocks, (const uint4*)w_packed, consts, stem_lut,
-        (__nv_bfloat16*)out_bf16);
+        (__nv_bfloat16*)out_bf16, counter);
     return trl_check(cudaGetLastError());
 }

@@ -138,6 +138,7 @@ class SelfPlayEngine:
         self.buf = b
         assert self.lib.trl_sizeof_search_ctl() == CTL_DTYPE.itemsize and self.lib.trl_sizeof_sample() == SAMPLE_DTYPE.itemsize
         self._graph = None
+        self._side = None
         self._values = self._logits = None
         self.steps_done = 0
         self.new_games(first_game_id, game_id_stride)
@@ -176,10 +177,16 @@ class SelfPlayEngine:
 
     # ---- one simulation per game ---------------------------------------------------------
     def _step_eager(self):
-        lib, st = self.lib, torch.cuda.current_stream(self.device).cuda_stream
+        main = torch.cuda.current_stream(self.device)
+        lib, st = self.lib, main.cuda_stream
         bp, pp = ctypes.byref(self.buf), ctypes.byref(self.params)
         _native.check(lib.trl_search_select(bp, pp, st), "trl_search_select")
-        _native.check(lib.trl_search_movegen(bp, st), "trl_search_movegen")
+        # the leaves' legal placements only feed `expand`: enumerate them on a forked stream,
+        # concurrently with feature encoding and the network (joined before expand)
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        self._side.wait_stream(main)
+        _native.check(lib.trl_search_movegen(bp, self._side.cuda_stream), "trl_search_movegen")
         dt = 0 if self.feature_dtype == torch.float32 else 1
         _native.check(lib.trl_encode_features(self.t["states"].data_ptr(), self.t["leaf_state"].data_ptr(), self.G,
                                               self.grids.data_ptr(), self.extras.data_ptr(), dt, st), "trl_encode_features")
@@ -188,12 +195,14 @@ class SelfPlayEngine:
         values = values.reshape(-1)
         if values.dtype != logits.dtype:
             values = values.to(logits.dtype)
-        if not (values.is_contiguous() and logits.is_contiguous() and logits.shape == (self.G, POLICY_SIZE)):
-            raise ValueError("evaluator must return contiguous values [G] and logits [G, 11583]")
+        if not (values.is_contiguous() and logits.dim() == 2 and logits.shape[0] == self.G and
+                logits.shape[1] >= POLICY_SIZE and logits.stride(1) == 1):
+            raise ValueError("evaluator must return contiguous values [G] and row-major logits [G, >=11583]")
         if logits.dtype not in (torch.float32, torch.bfloat16):
             raise ValueError("evaluator outputs must be float32 or bfloat16")
         self._values, self._logits = values, logits  # keep alive (graph-owned memory when captured)
-        _native.check(lib.trl_search_expand(bp, pp, values.data_ptr(), logits.data_ptr(),
+        main.wait_stream(self._side)
+        _native.check(lib.trl_search_expand(bp, pp, values.data_ptr(), logits.data_ptr(), logits.stride(0),
                                             0 if logits.dtype == torch.float32 else 1, st), "trl_search_expand")
 
     def step(self, n=1):

@@ -68,13 +68,34 @@ def make_fused_evaluator(net, dtype=torch.bfloat16):
     assert supports(net) and dtype == torch.bfloat16
     net = net.eval()
     packed = pack_alphasame_trunk(net)
-    heads = {"osidedense": net.osidedense.to(dtype), "policy": net.policy_head.to(dtype), "value": net.value_head.to(dtype)}
+    osidedense, value_head = net.osidedense.to(dtype), net.value_head.to(dtype)
+    # The head input has 521 features; cuBLAS needs K % 8 == 0 for its tensor-core kernels, so the
+    # policy / first value layer weights get zero columns up to 528 and x gets matching zeros.
+    k_in = net.policy_head.in_features
+    k_pad = (k_in + 15) // 16 * 16
+    dev = net.policy_head.weight.device
+
+    def padded(linear):
+        n_pad = (linear.out_features + 7) // 8 * 8     # row pitch of the output must be 16-byte aligned too
+        w = torch.zeros((n_pad, k_pad), dtype=dtype, device=dev)
+        w[:linear.out_features, :k_in] = linear.weight.detach().to(dtype)
+        b = torch.zeros(n_pad, dtype=dtype, device=dev)
+        b[:linear.out_features] = linear.bias.detach().to(dtype)
+        return w.contiguous(), b.contiguous()
+
+    w_pol, b_pol = padded(net.policy_head)
+    w_val, b_val = padded(value_head[0])
+    value_tail = value_head[1:]
+    zeros = {}
 
     def evaluate(grids, extras):
         b = extras.shape[0]
         feats = trunk_forward(packed, grids)
-        x = torch.cat([feats[:b], extras[:, :SIDE_FEATS], heads["osidedense"](feats[b:]), extras[:, SIDE_FEATS:]], dim=1)
-        return heads["value"](x), heads["policy"](x)
+        if b not in zeros:
+            zeros[b] = torch.zeros((b, k_pad - k_in), dtype=dtype, device=extras.device)
+        x = torch.cat([feats[:b], extras[:, :SIDE_FEATS], osidedense(feats[b:]), extras[:, SIDE_FEATS:], zeros[b]], dim=1)
+        value = value_tail(torch.nn.functional.linear(x, w_val, b_val))
+        return value, torch.nn.functional.linear(x, w_pol, b_pol)   # logits [G, 11584], last column unused
 
     evaluate.packed = packed
     return evaluate

@@ -97,7 +97,7 @@ def main():
         with torch.no_grad():
             v, l = ev(eng.grids, eng.extras)
         v = v.reshape(-1).to(l.dtype); evs[4].record()
-        lib.trl_search_expand(bp, pp, v.data_ptr(), l.data_ptr(), 0 if l.dtype == torch.float32 else 1, st); evs[5].record()
+        lib.trl_search_expand(bp, pp, v.data_ptr(), l.data_ptr(), l.stride(0), 0 if l.dtype == torch.float32 else 1, st); evs[5].record()
         torch.cuda.synchronize()
         for i, nme in enumerate(names):
             acc[nme] += evs[i].elapsed_time(evs[i + 1])
