@@ -11,7 +11,7 @@ from .architectures import SIDE_FEATS, AlphaSame
 
 def supports(net):
     return (isinstance(net, AlphaSame) and net.conv1.out_channels == 16 and net.kernel1.out_channels == 1
-            and len(net.res_blocks) <= 40)
+            and len(net.res_blocks) <= 20)
 
 
 def _fold_bn(bn):
