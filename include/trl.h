@@ -333,6 +333,18 @@ int trl_search_expand(const TrlSearchBuffers* buf, const TrlSearchParams* prm, c
 int trl_alphasame_trunk(const void* grids_bf16, int n_images, int n_blocks, const void* w_packed,
                         const float* consts, const float* stem_lut, void* out_bf16, void* stream);
 
+/*
+ * Same operator, row-Toeplitz formulation (csrc/trunk_rows.cu): one MMA row per board row, the
+ * horizontal taps folded into N (M=128 N=48 K=16 per input column and vertical tap), all weights
+ * resident in shared memory, column-wavefront overlap of tensor pipe and epilogue.
+ * w_packed [2*n_blocks][3 dy][2][6][8][8] bf16: per vertical tap the 48 x 16 matrix
+ *          B[(j, oc), ic] = w[oc][ic][dy][2 - j] in K-major core-matrix order [k chunk][n group][n][k].
+ * Other arguments as above.  n_blocks <= trl_alphasame_trunk_rows_max_blocks().
+ */
+int trl_alphasame_trunk_rows(const void* grids_bf16, int n_images, int n_blocks, const void* w_packed,
+                             const float* consts, const float* stem_lut, void* out_bf16, void* stream);
+int trl_alphasame_trunk_rows_max_blocks(void);
+
 #ifdef __cplusplus
 }
 #endif

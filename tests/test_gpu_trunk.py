@@ -18,8 +18,9 @@ def _random_net(blocks, seed):
     return net
 
 
-@pytest.mark.parametrize("blocks,n", [(1, 3), (2, 700), (10, 2048)])
-def test_trunk_matches_pytorch_fp32(blocks, n):
+@pytest.mark.parametrize("layout", ["rows", "taps"])
+@pytest.mark.parametrize("blocks,n", [(1, 3), (1, 1), (2, 700), (10, 2048), (3, 4000)])
+def test_trunk_matches_pytorch_fp32(blocks, n, layout):
     """Tolerance: bf16 operands with fp32 accumulation and an fp32 residual stream ->
     |err| <= 0.03 * max|ref| + 0.02 elementwise, and mean |err| <= 0.5 % of mean |ref|."""
     import torch
@@ -31,7 +32,7 @@ def test_trunk_matches_pytorch_fp32(blocks, n):
     grids[-1] = 1         # full board
     with torch.no_grad():
         ref = net.grid_features(grids)
-    packed = trunk.pack_alphasame_trunk(net)
+    packed = trunk.pack_alphasame_trunk(net, layout=layout)
     got = trunk.trunk_forward(packed, grids.to(torch.bfloat16)).float()
     torch.cuda.synchronize()
     err = (got - ref).abs()

@@ -11,7 +11,7 @@ from .state import GAME_DTYPE, PLAYER_DTYPE
 _SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtrl_b200.so")
 _lib = None
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_void_p, c_int, c_u64, c_u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32
 
@@ -36,6 +36,8 @@ SIGNATURES = {
     "trl_search_movegen": (c_int, [c_void_p, c_void_p]),
     "trl_search_expand": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "trl_alphasame_trunk": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "trl_alphasame_trunk_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "trl_alphasame_trunk_rows_max_blocks": (c_int, []),
     "trl_encode_features": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
 }
 

@@ -1,0 +1,394 @@
+// trunk_rows.cu — fused convolutional trunk of AlphaSame (filters = 16, kernels = 1), third
+// formulation: ROW-TOEPLITZ implicit GEMM on tcgen05 with a column-wavefront software pipeline.
+//
+// Replaces AlphaSame.process_grid (reference architectures.py:120-126, ResidualBlock :27-57) in
+// eval mode: conv5x5 (1->16) -> blocks x [BN-ReLU-Conv3x3, BN-ReLU-Conv3x3, +skip] -> BN-ReLU ->
+// Conv1x1 (16->1) -> BN-ReLU -> flatten(400).  BatchNorm is folded on the host (trunk.py).
+//
+// Why a third formulation.  With M = pixels, N = 16 output channels and one MMA per 3x3 tap
+// (trunk.cu) every activation byte is fetched from shared memory NINE times by the tensor core and
+// the kernel sits on the 128 B/clk/SM shared-memory operand bandwidth (measured with
+// tools/ubench/umma_rate.cu: M128 N16 K16 SS costs 36 clk of operand fetch against an 8 clk math
+// floor).  Here an MMA row is a BOARD ROW and the horizontal taps are folded into N:
+//
+//     D[row r, (x_out, oc)] += A[row r + dy - 1, (x_in, ic)] * B_dy[(x_out - x_in + 1, oc), ic]
+//
+// For one input column x_in the three output columns x_in-1, x_in, x_in+1 are adjacent accumulator
+// columns, so ONE tcgen05.mma M=128 N=48 K=16 per (x_in, dy) does the work of three taps for 128
+// board rows; the B matrix (48 x 16) does not depend on x_in.  Operand fetch per image and
+// convolution drops from 9 to 3 reads of the activations (432 clk instead of 1296 clk at 128 B/clk).
+//
+// Mapping (one persistent CTA per SM, 17 warps):
+//   * group = 3 images = 128 MMA rows ("slots"): slot 0 zero halo, image j rows y -> slot 1+41j+y,
+//     one shared zero halo slot between images, slots 124..127 unused.  TMEM lane = slot.
+//   * operand buffer in shared memory: [x_in 10][k half 2][row 136] x 16 B (8 channels bf16);
+//     slot s lives at row s+1, so the vertical tap dy is the same buffer with the UMMA descriptor
+//     start moved by dy rows (no im2col copy).  This is the canonical K-major no-swizzle layout.
+//   * TMEM: X (fp32 residual stream) columns [0,160) = (x_out, oc); D1 columns [160,320).  The
+//     second convolution of a block accumulates straight onto X (free skip connection); D1 is
+//     zeroed by the epilogue after it is read so every MMA accumulates.
+//   * warp 16 lane 0 issues the MMAs column by column and commits one mbarrier per column;
+//     16 epilogue warps (4 sets x 128 lanes, set k owns columns x = k mod 4) turn finished
+//     accumulator columns into the next layer's operand columns IN PLACE and signal them back:
+//     the tensor pipe starts layer L+1 on column 0 while the epilogue still drains layer L.
+//   * all 2*blocks weight matrices stay resident in shared memory for the CTA's lifetime.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "trl_common.cuh"
+
+namespace {
+
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;      // 512
+constexpr int kThreads = kEpiThreads + 32;       // + the MMA warp
+constexpr int kImgs = 3;                         // images per group
+constexpr int kSlotStride = 41;                  // 40 rows + one shared halo slot
+constexpr int kRowsBuf = 136;                    // operand rows per plane (slot s -> row s + 1)
+constexpr int kPlaneBytes = kRowsBuf * 16;       // 2176
+constexpr int kColBytes = 2 * kPlaneBytes;       // 4352: one x_in column, two 8-channel planes
+constexpr int kActBytes = 10 * kColBytes;        // 43520
+constexpr int kWDyBytes = 48 * 16 * 2;           // 1536: B matrix of one vertical tap
+constexpr int kWLayerBytes = 3 * kWDyBytes;      // 4608
+constexpr int kLutFloats = 5 * 32 * 16;
+constexpr int kTmemCols = 512;
+constexpr int kColX = 0, kColD = 160;
+constexpr int kMaxBlocks = 18;                   // resident weights: 36 x 4608 B
+
+__host__ __device__ constexpr int off_w() { return kActBytes; }
+__host__ __device__ inline int off_lut(int n_layers) { return off_w() + n_layers * kWLayerBytes; }
+__host__ __device__ inline int off_const(int n_layers) { return off_lut(n_layers) + kLutFloats * 4; }
+__host__ __device__ inline int off_rows(int n_layers) { return off_const(n_layers) + ((n_layers / 2) * 48 + 64) * 4; }
+__host__ __device__ inline int off_bar(int n_layers) { return off_rows(n_layers) + kImgs * 44 * 4; }
+__host__ __device__ inline int smem_bytes(int n_layers) { return off_bar(n_layers) + 20 * 8 + 16; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor: start>>4 [0,14) | LBO>>4 [16,30) (stride
+// between the two 8-element K chunks) | SBO>>4 [32,46) (stride between 8-row core matrices) | version 1
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128
+__host__ __device__ constexpr uint32_t idesc(uint32_t n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// D[tmem] += A[smem] * B[smem], executed by the WHOLE (converged) MMA warp: elect.sync picks the
+// issuing lane inside the asm, so every operand stays warp-uniform and ptxas keeps descriptors,
+// addresses and the loop in uniform registers (back-to-back UTCHMMA, no per-lane replay loop).
+// The descriptors are passed as (lo, hi) words: the start-address field is the low 14 bits, so
+// moving an operand is one 32-bit add.
+__device__ __forceinline__ void umma_acc(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t id) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, {%7, %7, %7, %7}, p;\n\t}\n"
+        :: "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(id), "r"(1u), "r"(0u) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar) {   // whole warp, one elected lane commits
+    asm volatile(
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" :: "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n\t"
+        "@q bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&d)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) d[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&d)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+        :: "r"(taddr), "r"(__float_as_uint(d[0])), "r"(__float_as_uint(d[1])), "r"(__float_as_uint(d[2])),
+           "r"(__float_as_uint(d[3])), "r"(__float_as_uint(d[4])), "r"(__float_as_uint(d[5])), "r"(__float_as_uint(d[6])),
+           "r"(__float_as_uint(d[7])), "r"(__float_as_uint(d[8])), "r"(__float_as_uint(d[9])), "r"(__float_as_uint(d[10])),
+           "r"(__float_as_uint(d[11])), "r"(__float_as_uint(d[12])), "r"(__float_as_uint(d[13])), "r"(__float_as_uint(d[14])),
+           "r"(__float_as_uint(d[15])) : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};\n"
+        :: "r"(taddr), "r"(0u) : "memory");
+}
+
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// the 16 channels of (column x, slot) -> two 16-byte stores (one per 8-channel plane)
+__device__ __forceinline__ void store_operand(uint8_t* act, int x, int slot, const float (&v)[16]) {
+    uint4 a, b;
+    a.x = pack_bf16x2(v[0], v[1]);   a.y = pack_bf16x2(v[2], v[3]);
+    a.z = pack_bf16x2(v[4], v[5]);   a.w = pack_bf16x2(v[6], v[7]);
+    b.x = pack_bf16x2(v[8], v[9]);   b.y = pack_bf16x2(v[10], v[11]);
+    b.z = pack_bf16x2(v[12], v[13]); b.w = pack_bf16x2(v[14], v[15]);
+    uint8_t* p = act + x * kColBytes + (slot + 1) * 16;
+    *reinterpret_cast<uint4*>(p) = a;
+    *reinterpret_cast<uint4*>(p + kPlaneBytes) = b;
+}
+
+// operand column written (generic proxy) -> visible to the tensor core (async proxy); TMEM traffic
+// of this thread ordered before the hand-off; one arrival per warp.
+__device__ __forceinline__ void publish_column(uint32_t bar_o) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar_o);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_images, int n_blocks,
+                            const uint4* __restrict__ w_packed,   // [2*n_blocks][3][2][6][8][8] bf16
+                            const float* __restrict__ consts,     // [n_blocks*48 + 50]
+                            const float* __restrict__ stem_lut,   // [5][32][16]
+                            __nv_bfloat16* __restrict__ out,      // [n_images][400]
+                            int* __restrict__ next_group,         // work counter (zeroed before launch)
+                            long long* __restrict__ trace) {      // optional [layer][column][4] clock stamps of CTA 0's first group
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ int s_group;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
+    const int n_layers = 2 * n_blocks;
+    uint8_t* act = smem;
+    float* s_lut = reinterpret_cast<float*>(smem + off_lut(n_layers));
+    float* s_const = reinterpret_cast<float*>(smem + off_const(n_layers));
+    uint32_t* s_rows = reinterpret_cast<uint32_t*>(smem + off_rows(n_layers));
+    const uint32_t bar_m = smem_u32(smem + off_bar(n_layers));   // M[c]: MMAs of input column c complete
+    const uint32_t bar_o = bar_m + 80;                            // O[c]: operand column c written
+    const int n_groups = (n_images + kImgs - 1) / kImgs;
+
+    // ---- one-time setup ----
+    for (int i = tid; i < kActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < n_layers * (kWLayerBytes / 16); i += kThreads)
+        reinterpret_cast<uint4*>(smem + off_w())[i] = w_packed[i];
+    for (int i = tid; i < kLutFloats; i += kThreads) s_lut[i] = stem_lut[i];
+    for (int i = tid; i < n_blocks * 48 + 50; i += kThreads) s_const[i] = consts[i];
+    if (tid == 0) {
+        for (int c = 0; c < 10; ++c) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_m + 8 * c));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" :: "r"(bar_o + 8 * c));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kEpiWarps) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem_base)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, s_tmem_base, 0);
+
+    // epilogue thread geometry
+    const int set = warp >> 2;                              // owns columns x = set, set+4, set+8
+    const int slot = (warp & 3) * 32 + lane;                // MMA row = TMEM lane
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int sj = (slot >= 1 && slot < 1 + kImgs * kSlotStride) ? (slot - 1) / kSlotStride : -1;
+    const int sy = (slot >= 1) ? (slot - 1) % kSlotStride : kSlotStride - 1;
+    if (warp < kEpiWarps) {   // D1 starts zeroed: every MMA accumulates
+        for (int x = set; x < 10; x += 4) tmem_st16_zero(tmem_lane + (uint32_t)(kColD + 16 * x));
+        tmem_wait_st();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+
+    int group_iter = 0;
+    while (true) {
+        if (tid == 0) s_group = atomicAdd(next_group, 1);
+        if (tid < kImgs * 44) s_rows[tid] = 0;
+        __syncthreads();
+        const int g = s_group;
+        if (g >= n_groups) break;
+        const bool first_group = (group_iter++ == 0);
+
+        if (warp == kEpiWarps) {
+            // ================= MMA issuer (warp-uniform; elect.sync inside umma_acc / umma_commit) =================
+            {
+                const uint64_t ad = umma_desc(smem_u32(act), kPlaneBytes, 128u);
+                const uint64_t bd = umma_desc(smem_u32(smem + off_w()), 768u, 128u);
+                const uint32_t a_lo = (uint32_t)ad, a_hi = (uint32_t)(ad >> 32), b_hi = (uint32_t)(bd >> 32);
+                uint32_t b_lo = (uint32_t)bd;
+                for (int layer = 0; layer < n_layers; ++layer, b_lo += kWLayerBytes / 16) {
+                    const uint32_t par = (uint32_t)(layer & 1);
+                    const uint32_t dst = tmem_base + ((layer & 1) ? kColX : kColD);
+#pragma unroll
+                    for (int c = 0; c < 10; ++c) {
+                        mbar_wait(bar_o + 8 * c, par);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (trace && blockIdx.x == 0 && first_group && lane == 0) trace[(layer * 10 + c) * 4] = clock64();
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const uint32_t a = a_lo + (uint32_t)(c * (kColBytes / 16) + dy);   // column c, rows shifted by dy
+                            const uint32_t b = b_lo + (uint32_t)(dy * (kWDyBytes / 16));
+                            if (c == 0)        // x_out = 0, 1 (skip the x_out = -1 rows of B)
+                                umma_acc(dst, a, a_hi, b + 16u, b_hi, idesc(32));
+                            else if (c == 9)   // x_out = 8, 9
+                                umma_acc(dst + 128u, a, a_hi, b, b_hi, idesc(32));
+                            else
+                                umma_acc(dst + (uint32_t)(16 * (c - 1)), a, a_hi, b, b_hi, idesc(48));
+                        }
+                        umma_commit(bar_m + 8 * c);
+                    }
+                }
+            }
+            __syncwarp();
+        } else {
+            // ================= input, stem, epilogues =================
+            for (int i = tid; i < kImgs * 400; i += kEpiThreads) {
+                const int j = i / 400, c = i % 400;
+                const int img = g * kImgs + j;
+                if (img < n_images && __bfloat162float(grids[(size_t)img * 400 + c]) != 0.f)
+                    atomicOr(&s_rows[j * 44 + c / 10 + 2], 1u << (c % 10 + 2));
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            const bool inside = (sj >= 0 && sy < 40 && g * kImgs + sj < n_images);
+
+            // ---- stem: X = conv5x5(grid) by table lookup -> TMEM; operand = relu(bn1_0(X)) ----
+            for (int x = set; x < 10; x += 4) {
+                float xv[16], t[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) { xv[c] = 0.f; t[c] = 0.f; }
+                if (inside) {
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) {
+                        const uint32_t pat = (s_rows[sj * 44 + sy + r] >> x) & 31u;
+                        const float4* l = reinterpret_cast<const float4*>(s_lut + (r * 32 + pat) * 16);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 v = l[q];
+                            xv[4 * q] += v.x; xv[4 * q + 1] += v.y; xv[4 * q + 2] += v.z; xv[4 * q + 3] += v.w;
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) t[c] = fmaxf(fmaf(s_const[c], xv[c], s_const[16 + c]), 0.f);
+                }
+                tmem_st16(tmem_lane + (uint32_t)(kColX + 16 * x), xv);
+                store_operand(act, x, slot, t);
+                tmem_wait_st();
+                publish_column(bar_o + 8 * x);
+            }
+
+            // ---- 2 * n_blocks convolutions, column by column behind the tensor pipe ----
+            for (int layer = 0; layer < n_layers; ++layer) {
+                const uint32_t par = (uint32_t)(layer & 1);
+                const bool second = layer & 1;
+                const bool last = (layer == n_layers - 1);
+                const float* cb = s_const + (layer >> 1) * 48;
+                for (int x = set; x < 10; x += 4) {
+                    mbar_wait(bar_m + 8 * (x < 9 ? x + 1 : 9), par);   // columns x-1..x+1 of this layer are final
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const bool tr = trace && blockIdx.x == 0 && first_group && (tid & 127) == 0;
+                    if (tr) trace[(layer * 10 + x) * 4 + 1] = clock64();
+                    float d[16], v[16];
+                    if (!second) {
+                        // U = relu(conv1'(T) + c2)   (bn2 scale folded into the weights)
+                        const uint32_t ta = tmem_lane + (uint32_t)(kColD + 16 * x);
+                        tmem_ld16(ta, d);
+                        if (tr) trace[(layer * 10 + x) * 4 + 2] = clock64();
+                        tmem_st16_zero(ta);
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) v[c] = inside ? fmaxf(d[c] + cb[32 + c], 0.f) : 0.f;
+                        store_operand(act, x, slot, v);
+                        tmem_wait_st();
+                        publish_column(bar_o + 8 * x);
+                        if (tr) trace[(layer * 10 + x) * 4 + 3] = clock64();
+                    } else {
+                        // X (in TMEM) already holds X + conv2(U); next operand T = relu(bn1_next(X))
+                        tmem_ld16(tmem_lane + (uint32_t)(kColX + 16 * x), d);
+                        if (tr) trace[(layer * 10 + x) * 4 + 2] = clock64();
+                        if (!last) {
+                            const float* nb = cb + 48;
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) v[c] = inside ? fmaxf(fmaf(nb[c], d[c], nb[16 + c]), 0.f) : 0.f;
+                            store_operand(act, x, slot, v);
+                            publish_column(bar_o + 8 * x);
+                            if (tr) trace[(layer * 10 + x) * 4 + 3] = clock64();
+                        } else if (inside) {
+                            // head of the trunk: BN-ReLU, 1x1 conv to one channel, BN-ReLU, flatten
+                            const float* fc = s_const + n_blocks * 48;
+                            float acc = 0.f;
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) acc = fmaf(fc[32 + c], fmaxf(fmaf(fc[c], d[c], fc[16 + c]), 0.f), acc);
+                            out[(size_t)(g * kImgs + sj) * 400 + sy * 10 + x] = __float2bfloat16(fmaxf(fmaf(fc[48], acc, fc[49]), 0.f));
+                        }
+                    }
+                }
+            }
+            // the next group's stem overwrites X in TMEM: order this group's TMEM reads before it
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        }
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == kEpiWarps) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+}  // namespace
+
+extern "C" int trl_alphasame_trunk_rows_max_blocks(void) { return kMaxBlocks; }
+
+// Profiling aid (tools/trunk_trace.py): device buffer of 2*n_blocks*10*4 int64 clock stamps written
+// by CTA 0 for its first group; nullptr (default) disables tracing.
+static long long* g_trace = nullptr;
+extern "C" void trl_debug_trunk_rows_trace(void* device_buffer) { g_trace = (long long*)device_buffer; }
+
+extern "C" int trl_alphasame_trunk_rows(const void* grids_bf16, int n_images, int n_blocks, const void* w_packed,
+                                        const float* consts, const float* stem_lut, void* out_bf16, void* stream) {
+    if (n_images < 0 || n_blocks < 1 || n_blocks > kMaxBlocks || !grids_bf16 || !w_packed || !consts || !stem_lut || !out_bf16)
+        return TRL_E_ARG;
+    if (n_images == 0) return TRL_OK;
+    const int smem = smem_bytes(2 * n_blocks);
+    static int configured = 0;
+    if (configured < smem) {
+        int rc = trl_check(cudaFuncSetAttribute(alphasame_trunk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (rc) return rc;
+        configured = smem;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_groups = (n_images + kImgs - 1) / kImgs;
+    int grid = sms < n_groups ? sms : n_groups;   // one persistent CTA per SM (it owns all 512 TMEM columns)
+    int* counter = (int*)trl_workspace(TRL_WS_TRUNK_COUNTER, 256);
+    if (!counter) return TRL_E_NOMEM;
+    int rc = trl_check(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
+    if (rc) return rc;
+    alphasame_trunk_rows_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)grids_bf16, n_images, n_blocks, (const uint4*)w_packed, consts, stem_lut,
+        (__nv_bfloat16*)out_bf16, counter, g_trace);
+    return trl_check(cudaGetLastError());
+}

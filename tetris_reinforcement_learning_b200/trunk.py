@@ -19,16 +19,36 @@ def _fold_bn(bn):
     return s, bn.bias.detach().float() - bn.running_mean.detach().float() * s
 
 
-def _pack_conv(w):
+def _pack_conv_taps(w):
     """(16 out, 16 in, 3, 3) -> [9 taps][k chunk 2][n group 2][n 8][k 8] (K-major core matrices)."""
     t = w.permute(2, 3, 0, 1).reshape(9, 16, 16)          # [tap][o][i]
     t = t.reshape(9, 2, 8, 2, 8)                           # [tap][ng][n][kc][k]
     return t.permute(0, 3, 1, 2, 4).contiguous()           # [tap][kc][ng][n][k]
 
 
-def pack_alphasame_trunk(net, device=None):
-    """-> dict(w_packed bf16 [2*blocks, 9*256], consts f32, stem_lut f32 [5,32,16], n_blocks)."""
+def _pack_conv_rows(w):
+    """(16 out, 16 in, 3 dy, 3 dx) -> [dy 3][k chunk 2][n group 6][n 8][k 8]: per vertical tap the
+    48 x 16 matrix B[(j, oc), ic] = w[oc, ic, dy, 2 - j] that maps input column x_in to the output
+    columns x_in - 1 + j (row-Toeplitz form of csrc/trunk_rows.cu), in K-major core-matrix order."""
+    t = w.permute(2, 3, 0, 1).flip(1)                      # [dy][j = 2 - dx][oc][ic]
+    t = t.reshape(3, 48, 16).reshape(3, 6, 8, 2, 8)        # [dy][ng][n][kc][k]
+    return t.permute(0, 3, 1, 2, 4).contiguous()           # [dy][kc][ng][n][k]
+
+
+def rows_kernel_supports(net):
+    """The row-Toeplitz kernel keeps every layer's weights resident in shared memory."""
+    return supports(net) and len(net.res_blocks) <= _native.lib().trl_alphasame_trunk_rows_max_blocks()
+
+
+def pack_alphasame_trunk(net, device=None, layout=None):
+    """-> dict(w_packed bf16 [2*blocks, 9*256], consts f32, stem_lut f32 [5,32,16], n_blocks, layout).
+
+    layout 'rows' (csrc/trunk_rows.cu, default when the depth allows it) or 'taps' (csrc/trunk.cu)."""
     assert supports(net)
+    if layout is None:
+        layout = "rows" if rows_kernel_supports(net) else "taps"
+    assert layout in ("rows", "taps")
+    _pack_conv = _pack_conv_rows if layout == "rows" else _pack_conv_taps
     device = device or next(net.parameters()).device
     convs, consts = [], []
     for blk in net.res_blocks:
@@ -46,7 +66,7 @@ def pack_alphasame_trunk(net, device=None):
     lut = torch.einsum("pk,crk->rpc", bits, w_stem).contiguous()                  # [r][pat][c]
     return {"w_packed": torch.stack(convs).reshape(len(convs), -1).to(device=device, dtype=torch.bfloat16).contiguous(),
             "consts": torch.cat([c.reshape(-1) for c in consts]).to(device).contiguous(),
-            "stem_lut": lut.to(device).contiguous(), "n_blocks": len(net.res_blocks)}
+            "stem_lut": lut.to(device).contiguous(), "n_blocks": len(net.res_blocks), "layout": layout}
 
 
 def trunk_forward(packed, grids, out=None):
@@ -56,18 +76,18 @@ def trunk_forward(packed, grids, out=None):
         grids = grids.to(torch.bfloat16).contiguous()
     if out is None:
         out = torch.empty((n, 400), dtype=torch.bfloat16, device=grids.device)
-    rc = _native.lib().trl_alphasame_trunk(grids.data_ptr(), n, packed["n_blocks"], packed["w_packed"].data_ptr(),
-                                           packed["consts"].data_ptr(), packed["stem_lut"].data_ptr(), out.data_ptr(),
-                                           torch.cuda.current_stream(grids.device).cuda_stream)
+    fn = _native.lib().trl_alphasame_trunk_rows if packed.get("layout") == "rows" else _native.lib().trl_alphasame_trunk
+    rc = fn(grids.data_ptr(), n, packed["n_blocks"], packed["w_packed"].data_ptr(), packed["consts"].data_ptr(),
+            packed["stem_lut"].data_ptr(), out.data_ptr(), torch.cuda.current_stream(grids.device).cuda_stream)
     _native.check(rc, "trl_alphasame_trunk")
     return out
 
 
-def make_fused_evaluator(net, dtype=torch.bfloat16):
+def make_fused_evaluator(net, dtype=torch.bfloat16, layout=None):
     """Engine evaluator: fused tcgen05 trunk on both grids, then the (GEMM-shaped) heads in PyTorch."""
     assert supports(net) and dtype == torch.bfloat16
     net = net.eval()
-    packed = pack_alphasame_trunk(net)
+    packed = pack_alphasame_trunk(net, layout=layout)
     osidedense, value_head = net.osidedense.to(dtype), net.value_head.to(dtype)
     # The head input has 521 features; cuBLAS needs K % 8 == 0 for its tensor-core kernels, so the
     # policy / first value layer weights get zero columns up to 528 and x gets matching zeros.
