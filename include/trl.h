@@ -339,10 +339,12 @@ int trl_alphasame_trunk(const void* grids_bf16, int n_images, int n_blocks, cons
  * resident in shared memory, column-wavefront overlap of tensor pipe and epilogue.
  * w_packed [2*n_blocks][3 dy][2][6][8][8] bf16: per vertical tap the 48 x 16 matrix
  *          B[(j, oc), ic] = w[oc][ic][dy][2 - j] in K-major core-matrix order [k chunk][n group][n][k].
+ * stem_w   [5 dy][2][20][8][8] bf16: the 5x5 stem as 5 MMAs (M=128 N=160 K=16): per kernel row the
+ *          160 x 16 matrix B[(x_out, oc), k] = w[oc][dy][k - x_out] (k = input column + 2, else 0).
  * Other arguments as above.  n_blocks <= trl_alphasame_trunk_rows_max_blocks().
  */
 int trl_alphasame_trunk_rows(const void* grids_bf16, int n_images, int n_blocks, const void* w_packed,
-                             const float* consts, const float* stem_lut, void* out_bf16, void* stream);
+                             const float* consts, const void* stem_w, void* out_bf16, void* stream);
 int trl_alphasame_trunk_rows_max_blocks(void);
 
 #ifdef __cplusplus

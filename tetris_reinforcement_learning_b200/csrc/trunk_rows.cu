@@ -18,19 +18,20 @@
 // board rows; the B matrix (48 x 16) does not depend on x_in.  Operand fetch per image and
 // convolution drops from 9 to 3 reads of the activations (432 clk instead of 1296 clk at 128 B/clk).
 //
-// Mapping (one persistent CTA per SM, 17 warps):
-//   * group = 3 images = 128 MMA rows ("slots"): slot 0 zero halo, image j rows y -> slot 1+41j+y,
-//     one shared zero halo slot between images, slots 124..127 unused.  TMEM lane = slot.
+// Mapping (one persistent CTA per SM, 21 warps):
+//   * group = 3 images = 128 MMA rows ("slots"): image j row y -> slot 2 + 42 j + y, two zero halo
+//     slots around every image (2 + 40 + 2 + 40 + 2 + 40 + 2 = 128).  TMEM lane = slot.
 //   * operand buffer in shared memory: [x_in 10][k half 2][row 136] x 16 B (8 channels bf16);
 //     slot s lives at row s+1, so the vertical tap dy is the same buffer with the UMMA descriptor
 //     start moved by dy rows (no im2col copy).  This is the canonical K-major no-swizzle layout.
 //   * TMEM: X (fp32 residual stream) columns [0,160) = (x_out, oc); D1 columns [160,320).  The
 //     second convolution of a block accumulates straight onto X (free skip connection); D1 is
 //     zeroed by the epilogue after it is read so every MMA accumulates.
-//   * warp 16 lane 0 issues the MMAs column by column and commits one mbarrier per column;
-//     16 epilogue warps (4 sets x 128 lanes, set k owns columns x = k mod 4) turn finished
-//     accumulator columns into the next layer's operand columns IN PLACE and signal them back:
-//     the tensor pipe starts layer L+1 on column 0 while the epilogue still drains layer L.
+//   * the MMA warp (warp-uniform code, elect.sync) issues the MMAs column by column and commits one
+//     mbarrier per column; 20 epilogue warps (5 sets x 128 lanes, set p owns columns 2p, 2p+1)
+//     turn finished accumulator columns into the next layer's operand columns IN PLACE and signal
+//     them back: the tensor pipe starts layer L+1 on column 0 while the epilogue still drains L.
+//   * the binary 5x5 stem is 5 more MMAs (M=128 N=160 K=16: K = the 14 board columns incl. halo).
 //   * all 2*blocks weight matrices stay resident in shared memory for the CTA's lifetime.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -40,28 +41,30 @@
 
 namespace {
 
-constexpr int kEpiWarps = 16;
-constexpr int kEpiThreads = kEpiWarps * 32;      // 512
+constexpr int kEpiWarps = 20;                    // 5 sets x 4 warps; set p owns the column pair (2p, 2p+1)
+constexpr int kEpiThreads = kEpiWarps * 32;      // 640
 constexpr int kThreads = kEpiThreads + 32;       // + the MMA warp
 constexpr int kImgs = 3;                         // images per group
-constexpr int kSlotStride = 41;                  // 40 rows + one shared halo slot
-constexpr int kRowsBuf = 136;                    // operand rows per plane (slot s -> row s + 1)
+constexpr int kSlotStride = 42;                  // 40 rows + two halo slots (the 5x5 stem needs two)
+constexpr int kRowsBuf = 136;                    // operand rows per plane
 constexpr int kPlaneBytes = kRowsBuf * 16;       // 2176
 constexpr int kColBytes = 2 * kPlaneBytes;       // 4352: one x_in column, two 8-channel planes
-constexpr int kActBytes = 10 * kColBytes;        // 43520
+constexpr int kActBytes = 10 * kColBytes;        // 43520  (slot s -> row s + 1)
+constexpr int kStemInBytes = kColBytes;          // 4352: board cells as a K=16 operand (slot s -> row s + 2)
+constexpr int kStemWDyBytes = 160 * 16 * 2;      // 5120: Toeplitz matrix of one stem kernel row
+constexpr int kStemWBytes = 5 * kStemWDyBytes;   // 25600
 constexpr int kWDyBytes = 48 * 16 * 2;           // 1536: B matrix of one vertical tap
 constexpr int kWLayerBytes = 3 * kWDyBytes;      // 4608
-constexpr int kLutFloats = 5 * 32 * 16;
 constexpr int kTmemCols = 512;
 constexpr int kColX = 0, kColD = 160;
-constexpr int kMaxBlocks = 18;                   // resident weights: 36 x 4608 B
+constexpr int kMaxBlocks = 16;                   // resident weights: 32 x 4608 B
 
-__host__ __device__ constexpr int off_w() { return kActBytes; }
-__host__ __device__ inline int off_lut(int n_layers) { return off_w() + n_layers * kWLayerBytes; }
-__host__ __device__ inline int off_const(int n_layers) { return off_lut(n_layers) + kLutFloats * 4; }
-__host__ __device__ inline int off_rows(int n_layers) { return off_const(n_layers) + ((n_layers / 2) * 48 + 64) * 4; }
-__host__ __device__ inline int off_bar(int n_layers) { return off_rows(n_layers) + kImgs * 44 * 4; }
-__host__ __device__ inline int smem_bytes(int n_layers) { return off_bar(n_layers) + 20 * 8 + 16; }
+constexpr int kOffStemIn = kActBytes;
+constexpr int kOffStemW = kOffStemIn + kStemInBytes;
+constexpr int kOffBar = kOffStemW + kStemWBytes;          // I, M[10], O[5]
+constexpr int kOffConst = kOffBar + 22 * 8;
+__host__ __device__ inline int off_w(int n_blocks) { return kOffConst + ((n_blocks * 48 + 50 + 3) / 4) * 16; }
+__host__ __device__ inline int smem_bytes(int n_blocks) { return off_w(n_blocks) + 2 * n_blocks * kWLayerBytes; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -82,13 +85,13 @@ __host__ __device__ constexpr uint32_t idesc(uint32_t n) {
 // addresses and the loop in uniform registers (back-to-back UTCHMMA, no per-lane replay loop).
 // The descriptors are passed as (lo, hi) words: the start-address field is the low 14 bits, so
 // moving an operand is one 32-bit add.
-__device__ __forceinline__ void umma_acc(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                         uint32_t id) {
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                     uint32_t id, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\telect.sync _|e, 0xffffffff;\n\t"
         "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.b32 p, %6, 0;\n\t"
         "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, {%7, %7, %7, %7}, p;\n\t}\n"
-        :: "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(id), "r"(1u), "r"(0u) : "memory");
+        :: "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(id), "r"(accumulate), "r"(0u) : "memory");
 }
 
 __device__ __forceinline__ void umma_commit(uint32_t bar) {   // whole warp, one elected lane commits
@@ -99,7 +102,9 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {   // whole warp, one
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
-        "{\n\t.reg .pred q;\n\tWAIT_%=:\n\t"
+        "{\n\t.reg .pred q;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q, [%0], %1;\n\t"   // usually already complete: no suspend
+        "@q bra DONE_%=;\n\tWAIT_%=:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n\t"
         "@q bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" :: "r"(bar), "r"(parity) : "memory");
 }
@@ -164,14 +169,24 @@ __device__ __forceinline__ void publish_column(uint32_t bar_o) {
     if ((threadIdx.x & 31) == 0) mbar_arrive(bar_o);
 }
 
+// 16 per-channel constants of the running layer in registers (shared-memory bandwidth belongs to
+// the tensor core: at the operand-fetch bound every LDS in the epilogue is a stolen MMA cycle).
+__device__ __forceinline__ void load16(const float* p, float (&r)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 v = reinterpret_cast<const float4*>(p)[q];
+        r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_images, int n_blocks,
                             const uint4* __restrict__ w_packed,   // [2*n_blocks][3][2][6][8][8] bf16
                             const float* __restrict__ consts,     // [n_blocks*48 + 50]
-                            const float* __restrict__ stem_lut,   // [5][32][16]
+                            const uint4* __restrict__ stem_w,     // [5][2][20][8][8] bf16
                             __nv_bfloat16* __restrict__ out,      // [n_images][400]
                             int* __restrict__ next_group,         // work counter (zeroed before launch)
-                            long long* __restrict__ trace) {      // optional [layer][column][4] clock stamps of CTA 0's first group
+                            long long* __restrict__ trace) {      // optional [pseudo-layer][column][4] clock stamps (CTA 0, first group)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_group;
@@ -179,24 +194,23 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
     const int n_layers = 2 * n_blocks;
     uint8_t* act = smem;
-    float* s_lut = reinterpret_cast<float*>(smem + off_lut(n_layers));
-    float* s_const = reinterpret_cast<float*>(smem + off_const(n_layers));
-    uint32_t* s_rows = reinterpret_cast<uint32_t*>(smem + off_rows(n_layers));
-    const uint32_t bar_m = smem_u32(smem + off_bar(n_layers));   // M[c]: MMAs of input column c complete
-    const uint32_t bar_o = bar_m + 80;                            // O[c]: operand column c written
+    uint8_t* stem_in = smem + kOffStemIn;
+    float* s_const = reinterpret_cast<float*>(smem + kOffConst);
+    const uint32_t bar_i = smem_u32(smem + kOffBar);   // I   : board cells of the group staged
+    const uint32_t bar_m = bar_i + 8;                  // M[c]: MMAs of input column c complete
+    const uint32_t bar_o = bar_m + 80;                 // O[p]: operand columns 2p, 2p+1 written
     const int n_groups = (n_images + kImgs - 1) / kImgs;
 
     // ---- one-time setup ----
-    for (int i = tid; i < kActBytes / 16; i += kThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (kActBytes + kStemInBytes) / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < kStemWBytes / 16; i += kThreads) reinterpret_cast<uint4*>(smem + kOffStemW)[i] = stem_w[i];
     for (int i = tid; i < n_layers * (kWLayerBytes / 16); i += kThreads)
-        reinterpret_cast<uint4*>(smem + off_w())[i] = w_packed[i];
-    for (int i = tid; i < kLutFloats; i += kThreads) s_lut[i] = stem_lut[i];
+        reinterpret_cast<uint4*>(smem + off_w(n_blocks))[i] = w_packed[i];
     for (int i = tid; i < n_blocks * 48 + 50; i += kThreads) s_const[i] = consts[i];
     if (tid == 0) {
-        for (int c = 0; c < 10; ++c) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_m + 8 * c));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" :: "r"(bar_o + 8 * c));
-        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" :: "r"(bar_i));
+        for (int c = 0; c < 10; ++c) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_m + 8 * c));
+        for (int c = 0; c < 5; ++c) asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" :: "r"(bar_o + 8 * c));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kEpiWarps) {
@@ -209,139 +223,149 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, s_tmem_base, 0);
 
-    // epilogue thread geometry
-    const int set = warp >> 2;                              // owns columns x = set, set+4, set+8
-    const int slot = (warp & 3) * 32 + lane;                // MMA row = TMEM lane
+    // epilogue thread geometry: slot = MMA row = TMEM lane; image j row y lives in slot 2 + 42 j + y
+    const int set = warp >> 2;                              // owns columns 2*set, 2*set + 1
+    const int slot = (warp & 3) * 32 + lane;
     const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const int sj = (slot >= 1 && slot < 1 + kImgs * kSlotStride) ? (slot - 1) / kSlotStride : -1;
-    const int sy = (slot >= 1) ? (slot - 1) % kSlotStride : kSlotStride - 1;
-    if (warp < kEpiWarps) {   // D1 starts zeroed: every MMA accumulates
-        for (int x = set; x < 10; x += 4) tmem_st16_zero(tmem_lane + (uint32_t)(kColD + 16 * x));
+    const int sj = (slot >= 2) ? (slot - 2) / kSlotStride : 0;
+    const int sy = (slot >= 2) ? (slot - 2) % kSlotStride : 40;     // 40, 41: halo
+    if (warp < kEpiWarps) {   // D1 starts zeroed: every MMA of a first convolution accumulates
+        tmem_st16_zero(tmem_lane + (uint32_t)(kColD + 32 * set));
+        tmem_st16_zero(tmem_lane + (uint32_t)(kColD + 32 * set + 16));
         tmem_wait_st();
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
 
+    uint32_t ph_i = 0, ph = 0;   // running mbarrier parities (every barrier completes once per pseudo-layer)
     int group_iter = 0;
     while (true) {
         if (tid == 0) s_group = atomicAdd(next_group, 1);
-        if (tid < kImgs * 44) s_rows[tid] = 0;
         __syncthreads();
         const int g = s_group;
         if (g >= n_groups) break;
         const bool first_group = (group_iter++ == 0);
 
         if (warp == kEpiWarps) {
-            // ================= MMA issuer (warp-uniform; elect.sync inside umma_acc / umma_commit) =================
-            {
-                const uint64_t ad = umma_desc(smem_u32(act), kPlaneBytes, 128u);
-                const uint64_t bd = umma_desc(smem_u32(smem + off_w()), 768u, 128u);
-                const uint32_t a_lo = (uint32_t)ad, a_hi = (uint32_t)(ad >> 32), b_hi = (uint32_t)(bd >> 32);
-                uint32_t b_lo = (uint32_t)bd;
-                for (int layer = 0; layer < n_layers; ++layer, b_lo += kWLayerBytes / 16) {
-                    const uint32_t par = (uint32_t)(layer & 1);
-                    const uint32_t dst = tmem_base + ((layer & 1) ? kColX : kColD);
+            // ============ MMA issuer (warp-uniform; elect.sync inside umma / umma_commit) ============
+            const uint64_t ad = umma_desc(smem_u32(act), kPlaneBytes, 128u);
+            const uint64_t bd = umma_desc(smem_u32(smem + off_w(n_blocks)), 768u, 128u);
+            const uint32_t a_lo = (uint32_t)ad, a_hi = (uint32_t)(ad >> 32), b_hi = (uint32_t)(bd >> 32);
+            uint32_t b_lo = (uint32_t)bd;
+            {   // stem: X = conv5x5(cells) as 5 MMAs M=128 N=160 K=16 (K = 14 board columns incl. halo)
+                const uint64_t sa = umma_desc(smem_u32(stem_in), kPlaneBytes, 128u);
+                const uint64_t sb = umma_desc(smem_u32(smem + kOffStemW), 20u * 128u, 128u);
+                mbar_wait(bar_i, ph_i);
+                ph_i ^= 1u;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (trace && blockIdx.x == 0 && first_group && lane == 0) trace[0] = clock64();
 #pragma unroll
-                    for (int c = 0; c < 10; ++c) {
-                        mbar_wait(bar_o + 8 * c, par);
+                for (int dy = 0; dy < 5; ++dy)
+                    umma(tmem_base + kColX, (uint32_t)sa + (uint32_t)dy, (uint32_t)(sa >> 32),
+                         (uint32_t)sb + (uint32_t)(dy * (kStemWDyBytes / 16)), (uint32_t)(sb >> 32), idesc(160), dy > 0 ? 1u : 0u);
+#pragma unroll
+                for (int c = 0; c < 10; ++c) umma_commit(bar_m + 8 * c);
+            }
+            for (int layer = 0; layer < n_layers; ++layer, b_lo += kWLayerBytes / 16) {
+                const uint32_t dst = tmem_base + ((layer & 1) ? kColX : kColD);
+#pragma unroll
+                for (int c = 0; c < 10; ++c) {
+                    if (!(c & 1)) {
+                        mbar_wait(bar_o + 8 * (c >> 1), ph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        if (trace && blockIdx.x == 0 && first_group && lane == 0) trace[(layer * 10 + c) * 4] = clock64();
-#pragma unroll
-                        for (int dy = 0; dy < 3; ++dy) {
-                            const uint32_t a = a_lo + (uint32_t)(c * (kColBytes / 16) + dy);   // column c, rows shifted by dy
-                            const uint32_t b = b_lo + (uint32_t)(dy * (kWDyBytes / 16));
-                            if (c == 0)        // x_out = 0, 1 (skip the x_out = -1 rows of B)
-                                umma_acc(dst, a, a_hi, b + 16u, b_hi, idesc(32));
-                            else if (c == 9)   // x_out = 8, 9
-                                umma_acc(dst + 128u, a, a_hi, b, b_hi, idesc(32));
-                            else
-                                umma_acc(dst + (uint32_t)(16 * (c - 1)), a, a_hi, b, b_hi, idesc(48));
-                        }
-                        umma_commit(bar_m + 8 * c);
                     }
+                    if (trace && blockIdx.x == 0 && first_group && lane == 0) trace[((layer + 1) * 10 + c) * 4] = clock64();
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const uint32_t a = a_lo + (uint32_t)(c * (kColBytes / 16) + dy);   // column c, rows shifted by dy
+                        const uint32_t b = b_lo + (uint32_t)(dy * (kWDyBytes / 16));
+                        if (c == 0)        // x_out = 0, 1 (skip the x_out = -1 rows of B)
+                            umma(dst, a, a_hi, b + 16u, b_hi, idesc(32), 1u);
+                        else if (c == 9)   // x_out = 8, 9
+                            umma(dst + 128u, a, a_hi, b, b_hi, idesc(32), 1u);
+                        else
+                            umma(dst + (uint32_t)(16 * (c - 1)), a, a_hi, b, b_hi, idesc(48), 1u);
+                    }
+                    umma_commit(bar_m + 8 * c);
                 }
+                ph ^= 1u;
             }
             __syncwarp();
         } else {
-            // ================= input, stem, epilogues =================
-            for (int i = tid; i < kImgs * 400; i += kEpiThreads) {
-                const int j = i / 400, c = i % 400;
-                const int img = g * kImgs + j;
-                if (img < n_images && __bfloat162float(grids[(size_t)img * 400 + c]) != 0.f)
-                    atomicOr(&s_rows[j * 44 + c / 10 + 2], 1u << (c % 10 + 2));
-            }
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            const bool inside = (sj >= 0 && sy < 40 && g * kImgs + sj < n_images);
-
-            // ---- stem: X = conv5x5(grid) by table lookup -> TMEM; operand = relu(bn1_0(X)) ----
-            for (int x = set; x < 10; x += 4) {
-                float xv[16], t[16];
+            // ============ input staging, epilogues ============
+            const bool inside = (sy < 40 && sj < kImgs && g * kImgs + sj < n_images);
+            if (set == 0) {
+                // board cells of this slot's row as one K=16 operand row: k = x + 2 (zero halo columns)
+                uint32_t cells[8];
 #pragma unroll
-                for (int c = 0; c < 16; ++c) { xv[c] = 0.f; t[c] = 0.f; }
+                for (int q = 0; q < 8; ++q) cells[q] = 0u;
                 if (inside) {
+                    const uint32_t* src = reinterpret_cast<const uint32_t*>(grids + ((size_t)(g * kImgs + sj) * 400 + sy * 10));
 #pragma unroll
-                    for (int r = 0; r < 5; ++r) {
-                        const uint32_t pat = (s_rows[sj * 44 + sy + r] >> x) & 31u;
-                        const float4* l = reinterpret_cast<const float4*>(s_lut + (r * 32 + pat) * 16);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 v = l[q];
-                            xv[4 * q] += v.x; xv[4 * q + 1] += v.y; xv[4 * q + 2] += v.z; xv[4 * q + 3] += v.w;
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) t[c] = fmaxf(fmaf(s_const[c], xv[c], s_const[16 + c]), 0.f);
+                    for (int q = 0; q < 5; ++q) cells[q + 1] = src[q];   // 10 bf16 cells = 5 words, k = 2..11
                 }
-                tmem_st16(tmem_lane + (uint32_t)(kColX + 16 * x), xv);
-                store_operand(act, x, slot, t);
-                tmem_wait_st();
-                publish_column(bar_o + 8 * x);
+                uint8_t* p = stem_in + (slot + 2) * 16;
+                *reinterpret_cast<uint4*>(p) = make_uint4(cells[0], cells[1], cells[2], cells[3]);
+                *reinterpret_cast<uint4*>(p + kPlaneBytes) = make_uint4(cells[4], cells[5], cells[6], cells[7]);
+                publish_column(bar_i);
             }
 
-            // ---- 2 * n_blocks convolutions, column by column behind the tensor pipe ----
-            for (int layer = 0; layer < n_layers; ++layer) {
-                const uint32_t par = (uint32_t)(layer & 1);
-                const bool second = layer & 1;
+            // pseudo-layer 0 = stem, then the 2 * n_blocks convolutions, column by column behind the tensor pipe
+            for (int pl = 0; pl <= n_layers; ++pl) {
+                const int layer = pl - 1;
+                const bool first_conv = (pl > 0) && !(layer & 1);
                 const bool last = (layer == n_layers - 1);
-                const float* cb = s_const + (layer >> 1) * 48;
-                for (int x = set; x < 10; x += 4) {
-                    mbar_wait(bar_m + 8 * (x < 9 ? x + 1 : 9), par);   // columns x-1..x+1 of this layer are final
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const bool tr = trace && blockIdx.x == 0 && first_group && (tid & 127) == 0;
-                    if (tr) trace[(layer * 10 + x) * 4 + 1] = clock64();
+                float ka[16], kb[16];
+                if (first_conv) {
+                    load16(s_const + (layer >> 1) * 48 + 32, kb);              // bn2 bias (scale folded into the weights)
+                } else if (!last) {
+                    const float* nb = s_const + (pl == 0 ? 0 : (layer >> 1) + 1) * 48;
+                    load16(nb, ka);                                            // next block's bn1 scale, bias
+                    load16(nb + 16, kb);
+                } else {
+                    const float* fc = s_const + n_blocks * 48;
+                    load16(fc, ka);
+                    load16(fc + 16, kb);
+                }
+                mbar_wait(bar_m + 8 * (set < 4 ? 2 * set + 2 : 9), ph);   // columns 2p-1..2p+2 of this layer are final
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const bool tr = trace && blockIdx.x == 0 && first_group && (tid & 127) == 0;
+                if (tr) trace[(pl * 10 + 2 * set) * 4 + 1] = clock64();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int x = 2 * set + h;
                     float d[16], v[16];
-                    if (!second) {
-                        // U = relu(conv1'(T) + c2)   (bn2 scale folded into the weights)
+                    if (first_conv) {
+                        // U = relu(conv1'(T) + c2)
                         const uint32_t ta = tmem_lane + (uint32_t)(kColD + 16 * x);
                         tmem_ld16(ta, d);
-                        if (tr) trace[(layer * 10 + x) * 4 + 2] = clock64();
                         tmem_st16_zero(ta);
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) v[c] = inside ? fmaxf(d[c] + cb[32 + c], 0.f) : 0.f;
+                        for (int c = 0; c < 16; ++c) v[c] = inside ? fmaxf(d[c] + kb[c], 0.f) : 0.f;
                         store_operand(act, x, slot, v);
-                        tmem_wait_st();
-                        publish_column(bar_o + 8 * x);
-                        if (tr) trace[(layer * 10 + x) * 4 + 3] = clock64();
                     } else {
-                        // X (in TMEM) already holds X + conv2(U); next operand T = relu(bn1_next(X))
+                        // X (in TMEM) holds the stem output / X + conv2(U); next operand T = relu(bn1_next(X))
                         tmem_ld16(tmem_lane + (uint32_t)(kColX + 16 * x), d);
-                        if (tr) trace[(layer * 10 + x) * 4 + 2] = clock64();
                         if (!last) {
-                            const float* nb = cb + 48;
 #pragma unroll
-                            for (int c = 0; c < 16; ++c) v[c] = inside ? fmaxf(fmaf(nb[c], d[c], nb[16 + c]), 0.f) : 0.f;
+                            for (int c = 0; c < 16; ++c) v[c] = inside ? fmaxf(fmaf(ka[c], d[c], kb[c]), 0.f) : 0.f;
                             store_operand(act, x, slot, v);
-                            publish_column(bar_o + 8 * x);
-                            if (tr) trace[(layer * 10 + x) * 4 + 3] = clock64();
                         } else if (inside) {
                             // head of the trunk: BN-ReLU, 1x1 conv to one channel, BN-ReLU, flatten
                             const float* fc = s_const + n_blocks * 48;
                             float acc = 0.f;
 #pragma unroll
-                            for (int c = 0; c < 16; ++c) acc = fmaf(fc[32 + c], fmaxf(fmaf(fc[c], d[c], fc[16 + c]), 0.f), acc);
+                            for (int c = 0; c < 16; ++c) acc = fmaf(fc[32 + c], fmaxf(fmaf(ka[c], d[c], kb[c]), 0.f), acc);
                             out[(size_t)(g * kImgs + sj) * 400 + sy * 10 + x] = __float2bfloat16(fmaxf(fmaf(fc[48], acc, fc[49]), 0.f));
                         }
                     }
+                    if (tr && h == 0) trace[(pl * 10 + 2 * set) * 4 + 2] = clock64();
                 }
+                if (!last) {
+                    if (first_conv) tmem_wait_st();
+                    publish_column(bar_o + 8 * set);
+                    if (tr) trace[(pl * 10 + 2 * set) * 4 + 3] = clock64();
+                }
+                ph ^= 1u;
             }
             // the next group's stem overwrites X in TMEM: order this group's TMEM reads before it
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -367,11 +391,11 @@ static long long* g_trace = nullptr;
 extern "C" void trl_debug_trunk_rows_trace(void* device_buffer) { g_trace = (long long*)device_buffer; }
 
 extern "C" int trl_alphasame_trunk_rows(const void* grids_bf16, int n_images, int n_blocks, const void* w_packed,
-                                        const float* consts, const float* stem_lut, void* out_bf16, void* stream) {
-    if (n_images < 0 || n_blocks < 1 || n_blocks > kMaxBlocks || !grids_bf16 || !w_packed || !consts || !stem_lut || !out_bf16)
+                                        const float* consts, const void* stem_w, void* out_bf16, void* stream) {
+    if (n_images < 0 || n_blocks < 1 || n_blocks > kMaxBlocks || !grids_bf16 || !w_packed || !consts || !stem_w || !out_bf16)
         return TRL_E_ARG;
     if (n_images == 0) return TRL_OK;
-    const int smem = smem_bytes(2 * n_blocks);
+    const int smem = smem_bytes(n_blocks);
     static int configured = 0;
     if (configured < smem) {
         int rc = trl_check(cudaFuncSetAttribute(alphasame_trunk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -388,7 +412,7 @@ extern "C" int trl_alphasame_trunk_rows(const void* grids_bf16, int n_images, in
     int rc = trl_check(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
     if (rc) return rc;
     alphasame_trunk_rows_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)grids_bf16, n_images, n_blocks, (const uint4*)w_packed, consts, stem_lut,
+        (const __nv_bfloat16*)grids_bf16, n_images, n_blocks, (const uint4*)w_packed, consts, (const uint4*)stem_w,
         (__nv_bfloat16*)out_bf16, counter, g_trace);
     return trl_check(cudaGetLastError());
 }

@@ -64,7 +64,16 @@ def pack_alphasame_trunk(net, device=None, layout=None):
     w_stem = net.conv1.weight.detach().float()[:, 0]                               # [16][5][5]
     bits = ((torch.arange(32)[:, None] >> torch.arange(5)[None, :]) & 1).float().to(w_stem.device)  # [pat][k]
     lut = torch.einsum("pk,crk->rpc", bits, w_stem).contiguous()                  # [r][pat][c]
-    return {"w_packed": torch.stack(convs).reshape(len(convs), -1).to(device=device, dtype=torch.bfloat16).contiguous(),
+    # row-Toeplitz stem (csrc/trunk_rows.cu): per kernel row dy the 160 x 16 matrix
+    # B[(x_out, oc), k] = w[oc][dy][k - x_out] (k = input column + 2), K-major core-matrix order
+    kk, xo = torch.arange(16)[None, :], torch.arange(10)[:, None]
+    dx = (kk - xo)                                                                 # [x_out][k]
+    ok = ((dx >= 0) & (dx < 5)).to(w_stem.device)
+    tz = w_stem.permute(1, 0, 2)[:, :, dx.clamp(0, 4).to(w_stem.device)] * ok     # [dy][oc][x_out][k]
+    tz = tz.permute(0, 2, 1, 3).reshape(5, 160, 16).reshape(5, 20, 8, 2, 8)       # [dy][ng][n][kc][k]
+    stem_w = tz.permute(0, 3, 1, 2, 4).contiguous()                               # [dy][kc][ng][n][k]
+    return {"stem_w": stem_w.reshape(-1).to(device=device, dtype=torch.bfloat16).contiguous(),
+            "w_packed": torch.stack(convs).reshape(len(convs), -1).to(device=device, dtype=torch.bfloat16).contiguous(),
             "consts": torch.cat([c.reshape(-1) for c in consts]).to(device).contiguous(),
             "stem_lut": lut.to(device).contiguous(), "n_blocks": len(net.res_blocks), "layout": layout}
 
@@ -76,9 +85,11 @@ def trunk_forward(packed, grids, out=None):
         grids = grids.to(torch.bfloat16).contiguous()
     if out is None:
         out = torch.empty((n, 400), dtype=torch.bfloat16, device=grids.device)
-    fn = _native.lib().trl_alphasame_trunk_rows if packed.get("layout") == "rows" else _native.lib().trl_alphasame_trunk
+    rows = packed.get("layout") == "rows"
+    fn = _native.lib().trl_alphasame_trunk_rows if rows else _native.lib().trl_alphasame_trunk
+    stem = packed["stem_w"] if rows else packed["stem_lut"]
     rc = fn(grids.data_ptr(), n, packed["n_blocks"], packed["w_packed"].data_ptr(), packed["consts"].data_ptr(),
-            packed["stem_lut"].data_ptr(), out.data_ptr(), torch.cuda.current_stream(grids.device).cuda_stream)
+            stem.data_ptr(), out.data_ptr(), torch.cuda.current_stream(grids.device).cuda_stream)
     _native.check(rc, "trl_alphasame_trunk")
     return out
 

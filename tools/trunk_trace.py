@@ -15,17 +15,19 @@ grids = (torch.rand((n, 1, 40, 10), device="cuda:0") < 0.3).to(torch.bfloat16)
 packed = trunk.pack_alphasame_trunk(net, layout="rows")
 L = _native.lib()
 trunk.trunk_forward(packed, grids)
-buf = torch.zeros(20 * 10 * 4, dtype=torch.int64, device="cuda:0")
+buf = torch.zeros(21 * 10 * 4, dtype=torch.int64, device="cuda:0")
 L.trl_debug_trunk_rows_trace.argtypes = [ctypes.c_void_p]
 L.trl_debug_trunk_rows_trace(buf.data_ptr())
 trunk.trunk_forward(packed, grids)
 torch.cuda.synchronize()
 L.trl_debug_trunk_rows_trace(None)
-t = buf.cpu().view(20, 10, 4)
+t = buf.cpu().view(21, 10, 4)
 t0 = int(t[0, 0, 0])
 print("layer col :  issue  epi_wake  ld_done  published   (clk since first issue)")
-for layer in (0, 1, 10, 11):
+for layer in (0, 1, 2, 11, 12):
     for c in range(10):
+        if c & 1 and int(t[layer, c, 1]) == 0 and int(t[layer, c, 0]) == 0:
+            continue
         r = [int(v) - t0 if int(v) else -1 for v in t[layer, c]]
         print(f"{layer:3d} {c:2d} : {r[0]:7d} {r[1]:7d} {r[2]:7d} {r[3]:7d}   wake-issue {r[1]-r[0]:6d}  epi {r[3]-r[1]:6d}")
-print("clk per layer (issue col0 L -> L+1):", [int(t[l + 1, 0, 0] - t[l, 0, 0]) for l in range(19)])
+print("clk per layer (issue col0 L -> L+1):", [int(t[l + 1, 0, 0] - t[l, 0, 0]) for l in range(1, 20)])
