@@ -151,6 +151,11 @@ int trl_movegen_host(const uint16_t* boards, const uint8_t* cur, const uint8_t* 
                      uint32_t* mask_bits, uint16_t* moves, int moves_cap, uint16_t* n_moves,
                      uint32_t* status);
 
+/* Kernel used by every trl_movegen* entry point: 0 = one thread per call (csrc/movegen.cu),
+ * 1 = one warp per piece search (csrc/movegen_warp.cu), -1 = automatic (default).  Both produce
+ * bit-identical outputs; the choice only trades latency against throughput. */
+void trl_movegen_select_kernel(int kernel);
+
 /* ------------------------------------------------------------------------------------ */
 /* env step                                                                              */
 /* replaces Game.make_move(move, add_bag, add_history=False)                             */

@@ -14,10 +14,13 @@ from tetris_reinforcement_learning_b200.state import (GAME_DTYPE, STEPOUT_DTYPE,
                                                       rows_to_grid, unpack_mask)
 
 
-@pytest.fixture(scope="module")
-def mg():
-    from tetris_reinforcement_learning_b200 import move_generation
-    return move_generation
+@pytest.fixture(scope="module", params=["warp", "thread"])
+def mg(request):
+    """move_generation with one of the two bit-exact kernels forced (csrc/movegen_warp.cu, csrc/movegen.cu)."""
+    from tetris_reinforcement_learning_b200 import _native, move_generation
+    _native.lib().trl_movegen_select_kernel(1 if request.param == "warp" else 0)
+    yield move_generation
+    _native.lib().trl_movegen_select_kernel(-1)
 
 
 @pytest.fixture(scope="module")

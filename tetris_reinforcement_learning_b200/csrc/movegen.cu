@@ -231,11 +231,25 @@ movegen_thread_kernel(const uint16_t* __restrict__ boards, const uint8_t* __rest
 // C ABI
 // ---------------------------------------------------------------------------------------
 
+// movegen_warp.cu
+int trl_launch_movegen_warp(const uint16_t* boards, const uint8_t* cur, const uint8_t* alt, const TrlGame* games,
+                            const int32_t* index, int n, uint32_t* mask_bits, uint16_t* moves, int moves_cap,
+                            uint16_t* n_moves, uint32_t* status, cudaStream_t stream);
+
+// Which kernel enumerates: 0 = one thread per call (movegen_thread_kernel), 1 = one warp per piece
+// search (movegen_warp_kernel), -1 = automatic.  Both are bit-exact; they differ in latency/throughput.
+static int g_movegen_kernel = -1;
+extern "C" void trl_movegen_select_kernel(int kernel) { g_movegen_kernel = kernel; }
+
 static int launch_movegen(const uint16_t* boards, const uint8_t* cur, const uint8_t* alt,
                           const TrlGame* games, const int32_t* index, int n, uint32_t* mask_bits, uint16_t* moves,
-                          int moves_cap, uint16_t* n_moves, uint32_t* status, cudaStream_t stream) {
+                          int moves_cap, uint16_t* n_moves, uint32_t* status, cudaStream_t stream, int n_total = 0) {
     if (n < 0 || (!games && (!boards || !cur || !alt)) || (moves && moves_cap <= 0)) return TRL_E_ARG;
     if (n == 0) return TRL_OK;
+    // automatic: the warp kernel wins by ~10x on latency-bound batches (one self-play step = a few
+    // thousand calls); the thread kernel still has ~1.6x more throughput on multi-million-call sweeps
+    if (g_movegen_kernel == 1 || (g_movegen_kernel < 0 && (n_total > n ? n_total : n) <= (1 << 17)))
+        return trl_launch_movegen_warp(boards, cur, alt, games, index, n, mask_bits, moves, moves_cap, n_moves, status, stream);
     uint32_t* scratch = nullptr;
     if (!mask_bits) {
         // the v0 kernel builds the mask in global memory; without a caller buffer use the workspace
@@ -303,7 +317,7 @@ extern "C" int trl_movegen_host(const uint16_t* boards, const uint8_t* cur, cons
         rc = trl_check(cudaMemcpyAsync(d_boards, boards + (size_t)off * TRL_ROWS, (size_t)m * TRL_ROWS * 2, cudaMemcpyHostToDevice, s));
         if (!rc) rc = trl_check(cudaMemcpyAsync(d_cur, cur + off, m, cudaMemcpyHostToDevice, s));
         if (!rc) rc = trl_check(cudaMemcpyAsync(d_alt, alt + off, m, cudaMemcpyHostToDevice, s));
-        if (!rc) rc = launch_movegen(d_boards, d_cur, d_alt, nullptr, nullptr, m, d_mask, d_moves, moves_cap, d_nm, d_status, s);
+        if (!rc) rc = launch_movegen(d_boards, d_cur, d_alt, nullptr, nullptr, m, d_mask, d_moves, moves_cap, d_nm, d_status, s, n);
         if (!rc && mask_bits) rc = trl_check(cudaMemcpyAsync(mask_bits + (size_t)off * TRL_MASK_WORDS, d_mask, (size_t)m * TRL_MASK_WORDS * 4, cudaMemcpyDeviceToHost, s));
         if (!rc && moves) rc = trl_check(cudaMemcpyAsync(moves + (size_t)off * moves_cap, d_moves, (size_t)m * moves_cap * 2, cudaMemcpyDeviceToHost, s));
         if (!rc && n_moves) rc = trl_check(cudaMemcpyAsync(n_moves + off, d_nm, (size_t)m * 2, cudaMemcpyDeviceToHost, s));

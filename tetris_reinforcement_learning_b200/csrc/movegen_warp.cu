@@ -1,0 +1,446 @@
+// movegen_warp.cu — warp-cooperative legal-placement enumeration (one WARP per piece search).
+//
+// Same operator and the same bit-exact contract as movegen.cu (reference
+// move_generation.get_move_matrix(player, 'convolutional'), move_generation.py:77-149, 325-528,
+// 650-749, including the FIFO-order dependent choice between the two T-spin plane groups, SURVEY
+// 0.6 / A.2), re-organised so that a search runs in a few thousand warp instructions instead of
+// ~10^5 dependent thread instructions:
+//
+//   * a call (board, current piece, hold-or-next piece) is two warps, one per piece type; a block
+//     of 8 warps owns 4 calls.  All search state lives in shared memory:
+//       vv[rot][row]  low 16 bits = validity row, high 16 bits = visited row     (4 x 46 words)
+//       fu[rot][row]  low 16 bits = flagged,      high 16 bits = used-last-kick  (T only)
+//       fifo[1024]    the exploration queue, entries (mx, my, rot, roc, ulk) as in movegen.cu
+//   * the queue is consumed 32 entries at a time: every lane tests one entry (stuck? visited?),
+//     a ballot finds the first entry that starts a flood fill, the entries before it only
+//     produce their "arrived by a kick and stuck" emission (move_generation.py:384-394);
+//   * the flood fill of one rotation is a serial scan over rows whose horizontal expansion is an
+//     O(1) carry-propagation trick (open + seed), not a fix-point loop;
+//   * kicks are evaluated for ALL edge cells of ALL rows of the fill at once: lane = row, bit =
+//     column, one AND/shift per (kick direction, kick index) against the target rotation's
+//     validity row ("first valid kick wins" = a running `remaining` mask, :443-481);
+//   * new queue entries are appended in the reference's order (row, column LSB->MSB, direction)
+//     with a warp prefix sum over per-row counts, so FIFO order — and with it the T-spin plane —
+//     is reproduced exactly.  "Last flagged emission wins" (:671-677) is order dependent only when
+//     emissions with different used-last-kick flags hit the same cell: the common case (all equal)
+//     is applied with shared-memory atomics, the mixed case serially in reference order;
+//   * the answer placed = visited & ~valid[row+1] is OR-ed into a per-call bit mask in shared
+//     memory, written out coalesced, and scanned into the ascending move list (= np.argwhere order).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "trl_common.cuh"
+#include "trl_tables.cuh"
+
+namespace {
+
+constexpr int kFifoCap = 1024;            // live entries; adversarial cave boards peak < 500
+constexpr int kCallsPerBlock = 4;
+constexpr int kWarps = 2 * kCallsPerBlock;
+constexpr int kVRows = TRL_MAP_H + 2;     // rows 44, 45 stay 0: "below the map" is never valid
+
+struct PieceState {
+    uint32_t vv[4][kVRows];
+    uint32_t fu[4][kVRows];
+    uint16_t fifo[kFifoCap];
+};
+
+struct CallState {
+    uint32_t mask[TRL_MASK_WORDS + 2];
+    uint16_t rows[TRL_ROWS];
+    int cur, alt, skip;
+    uint32_t status;
+};
+
+__device__ __forceinline__ uint32_t fifo_pack(int mx, int my, int rot, int roc, int ulk) {
+    return (uint32_t)(mx | (my << 4) | (rot << 10) | (roc << 12) | (ulk << 13));
+}
+
+// All cells reachable from `seed` by horizontal moves through `open` (seed must be a subset of
+// open): the carry of open + seed runs through every run of ones above a seed.
+__device__ __forceinline__ uint32_t hflood(uint32_t seed, uint32_t open) {
+    const uint32_t up = ((open + seed) ^ open) & open;
+    const uint32_t ro = __brev(open), rs = __brev(seed);
+    const uint32_t dn = __brev(((ro + rs) ^ ro) & ro);
+    return up | dn | seed;
+}
+
+// OR an 11-bit policy row chunk into the bit-packed mask in shared memory.
+__device__ __forceinline__ void or_chunk(uint32_t* mask, int plane, int row, uint32_t bits11) {
+    if (!bits11) return;
+    const int bit = (plane * TRL_POLICY_ROWS + row) * TRL_POLICY_COLS;
+    const int w = bit >> 5, s = bit & 31;
+    atomicOr(&mask[w], bits11 << s);
+    if (s > 21) atomicOr(&mask[w + 1], bits11 >> (32 - s));
+}
+
+// set / clear one used-last-kick bit and raise the flagged bit of a stuck cell
+__device__ __forceinline__ void flag_cell(uint32_t* fu_row, uint32_t bit, bool ulk) {
+    if (ulk) atomicOr(fu_row, bit | (bit << 16));
+    else { atomicOr(fu_row, bit); atomicAnd(fu_row, ~(bit << 16)); }
+}
+
+// One piece type of one call, executed by one converged warp.
+__device__ void search_piece_warp(PieceState& S, const uint16_t* rows, int type, bool via_hold, uint32_t* mask,
+                                  uint32_t& status, const uint32_t (*kpack)[4][3][2]) {
+    const int lane = threadIdx.x & 31;
+    uint32_t minos[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) minos[r] = c_minos[type][r];
+    const int sx = trl_spawn_x(type);
+    // Player.hold_piece -> create_piece spawn test (player.py:37-44, move_generation.py:112-121)
+    if (via_hold && !trl_fits(rows, minos[0], sx, TRL_SPAWN_Y)) return;
+
+    // _build_validity_maps (move_generation.py:490-528): lane = row
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        for (int my = lane; my < kVRows; my += 32) {
+            S.vv[r][my] = (my < TRL_MAP_H) ? trl_valid_row(rows, minos[r], my) : 0u;
+            S.fu[r][my] = 0u;
+        }
+    }
+    // _set_starting_position (move_generation.py:164-180)
+    int hi = TRL_ROWS;
+    for (int i = lane; i < TRL_ROWS; i += 32)
+        if (rows[i] & TRL_FULL_ROW) hi = min(hi, i);
+    hi = __reduce_min_sync(0xffffffffu, hi);
+    const int sy = max(hi - (int)c_matrix_size[type], TRL_SPAWN_Y);
+    __syncwarp();
+    if (!((S.vv[0][sy + 2] >> (sx + 2)) & 1u)) return;  // :351-352
+
+    const bool is_T = (type == P_T);
+    const bool rotates = (type != P_O);
+    const int tab = (type == P_I) ? 1 : 0;
+
+    uint32_t head = 0, tail = 1;
+    if (lane == 0) S.fifo[0] = (uint16_t)fifo_pack(sx + 2, sy + 2, 0, 0, 0);
+    __syncwarp();
+
+    while (head != tail) {
+        // ---- consume up to 32 queue entries: (A) emissions, find the first entry that fills ----
+        const int n = min(32u, tail - head);
+        const uint32_t e = (lane < n) ? S.fifo[(head + lane) & (kFifoCap - 1)] : 0u;
+        const int mx = e & 15, my = (e >> 4) & 63, rot = (e >> 10) & 3;
+        const uint32_t bit = 1u << mx;
+        const uint32_t w = S.vv[rot][my];
+        const bool stuck = !(S.vv[rot][my + 1] & bit);
+        const bool need = (lane < n) && !((w >> 16) & bit) && (w & bit);   // :397-398, :406-407
+        const uint32_t m_need = __ballot_sync(0xffffffffu, need);
+        const int first = m_need ? (__ffs(m_need) - 1) : 32;
+        if (is_T) {
+            // arrived by a kick and stuck: flagged emission BEFORE the visited test (:384-394)
+            const bool emit = (lane < n) && (lane <= first) && ((e >> 12) & 1u) && stuck;
+            const uint32_t m_emit = __ballot_sync(0xffffffffu, emit);
+            if (m_emit) {
+                const bool u = (e >> 13) & 1u;
+                const uint32_t m_true = __ballot_sync(0xffffffffu, emit && u);
+                if (m_true == 0u || m_true == m_emit) {
+                    if (emit) flag_cell(&S.fu[rot][my], bit, u);
+                } else if (emit) {   // mixed flags: the LAST emission of a cell wins (lane order = pop order)
+                    const uint32_t grp = __match_any_sync(m_emit, e & 0xFFFu);
+                    if ((31 - __clz(grp)) == lane) flag_cell(&S.fu[rot][my], bit, u);
+                    else atomicOr(&S.fu[rot][my], bit);
+                }
+            }
+        }
+        head += (first < n) ? (uint32_t)(first + 1) : (uint32_t)n;
+        __syncwarp();
+        if (first >= n) continue;
+
+        // ---- flood fill of rotation frot from (fmx, fmy), rows downward (:409-425, :485-488) ----
+        const int frot = __shfl_sync(0xffffffffu, rot, first);
+        const int fmy = __shfl_sync(0xffffffffu, my, first);
+        uint32_t reach = __shfl_sync(0xffffffffu, bit, first);
+        int fy = fmy;
+        while (reach) {
+            // one batch of at most 32 rows; lane l keeps the filled cells of row base + l
+            const int base = fy;
+            uint32_t myr = 0;
+            uint32_t cur = S.vv[frot][fy];
+            while (reach && fy < base + 32) {
+                const uint32_t open = cur & ~(cur >> 16) & 0xFFFFu;
+                const uint32_t r = hflood(reach, open);
+                if (lane == fy - base) { myr = r; S.vv[frot][fy] = cur | (r << 16); }   // :425
+                const uint32_t nxt = S.vv[frot][fy + 1];
+                reach = r & nxt & ~(nxt >> 16);
+                cur = nxt;
+                ++fy;
+            }
+            const int nrows = fy - base;
+            __syncwarp();
+            if (!rotates) continue;
+
+            // ---- kicks of every edge cell of the batch: lane = row, bit = column (:427-483) ----
+            const int ky_row = base + lane;
+            uint32_t edges = 0;
+            if (lane < nrows) {
+                const uint32_t vr = S.vv[frot][ky_row] & 0xFFFFu, nx = S.vv[frot][ky_row + 1] & 0xFFFFu;
+                edges = (myr & ~nx) | (myr & ~(vr << 1)) | (myr & ~(vr >> 1));
+            }
+            uint32_t Pu[3] = {0, 0, 0}, Im[3] = {0, 0, 0};      // sources whose kick pushes / emits at once
+            uint32_t k0[3] = {0, 0, 0}, k1[3] = {0, 0, 0}, k2[3] = {0, 0, 0};   // bit planes of the winning kick index
+#pragma unroll
+            for (int kd = 0; kd < 3; ++kd) {
+                const int nrot = (frot + kd + 1) & 3;
+                const TrlKicks& K = c_kicks[tab][frot][kd];
+                const int kn = K.n;
+                uint32_t rem = edges;
+#pragma unroll
+                for (int ki = 0; ki < 6; ++ki) {
+                    if (ki >= kn) break;
+                    const int kx = K.k[ki][0], ty = ky_row - K.k[ki][1];
+                    const bool in = (unsigned)ty < (unsigned)TRL_MAP_H;
+                    const uint32_t tw = in ? S.vv[nrot][ty] : 0u;
+                    const uint32_t tn = in ? S.vv[nrot][ty + 1] : 0u;
+                    // source bit ex <-> target bit ex + kx
+                    const uint32_t tv = kx >= 0 ? ((tw & 0xFFFFu) >> kx) : ((tw & 0xFFFFu) << -kx);
+                    const uint32_t cand = rem & tv & 0x3FFFu;       // first valid kick of these sources
+                    rem &= ~cand;
+                    if (ty < 2 || !cand) continue;                   // origin y < 0: direction abandoned (:463-464)
+                    const uint32_t tvis = kx >= 0 ? ((tw >> 16) >> kx) : ((tw >> 16) << -kx);
+                    const uint32_t tfree = kx >= 0 ? ((tn & 0xFFFFu) >> kx) : ((tn & 0xFFFFu) << -kx);
+                    const uint32_t pu = cand & ~tvis, im = cand & tvis & ~tfree;
+                    Pu[kd] |= pu;
+                    Im[kd] |= im;
+                    const uint32_t s = pu | im;
+                    if (ki & 1) k0[kd] |= s;
+                    if (ki & 2) k1[kd] |= s;
+                    if (ki & 4) k2[kd] |= s;
+                }
+            }
+            // ---- append the pushes in reference order: row, column LSB->MSB, direction ----
+            const int cnt = __popc(Pu[0]) + __popc(Pu[1]) + __popc(Pu[2]);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const bool room = (tail - head) + (uint32_t)total <= (uint32_t)kFifoCap;
+            if (!room) status |= TRL_ST_QUEUE_OVERFLOW;
+            const uint32_t any_im = is_T ? __ballot_sync(0xffffffffu, (Im[0] | Im[1] | Im[2]) != 0u) : 0u;
+            if ((total && room) || any_im) {
+                // per-lane pass over this row's events in (column, direction) order
+                uint32_t off = tail + (uint32_t)(incl - cnt);
+                uint32_t ev = Pu[0] | Pu[1] | Pu[2] | (is_T ? (Im[0] | Im[1] | Im[2]) : 0u);
+                bool has_t = false, has_f = false;
+                // first pass: pushes (and the flag mix of the immediate emissions)
+                while (ev) {
+                    const int ex = __ffs(ev) - 1;
+                    ev &= ev - 1;
+#pragma unroll
+                    for (int kd = 0; kd < 3; ++kd) {
+                        const bool p = (Pu[kd] >> ex) & 1u, i = (Im[kd] >> ex) & 1u;
+                        if (!(p || i)) continue;
+                        const int ki = ((k0[kd] >> ex) & 1u) | (((k1[kd] >> ex) & 1u) << 1) | (((k2[kd] >> ex) & 1u) << 2);
+                        const int kn = c_kicks[tab][frot][kd].n;
+                        const int nulk = (is_T && kd != 1 && ki == kn - 1) ? 1 : 0;
+                        if (p) {
+                            if (room) {
+                                const int kx = (int)(((*kpack)[frot][kd][0] >> (4 * ki)) & 15u) - 2;
+                                const int ky = (int)(((*kpack)[frot][kd][1] >> (4 * ki)) & 15u) - 2;
+                                S.fifo[off & (kFifoCap - 1)] = (uint16_t)fifo_pack(ex + kx, ky_row - ky, (frot + kd + 1) & 3, 1, nulk);
+                                ++off;
+                            }
+                        } else if (nulk) has_t = true;
+                        else has_f = true;
+                    }
+                }
+                if (room) tail += (uint32_t)total;
+                if (any_im) {
+                    // immediate flagged emissions: target already visited and stuck (:471-479)
+                    const bool mixed = __any_sync(0xffffffffu, has_t) && __any_sync(0xffffffffu, has_f);
+                    const int l_end = mixed ? nrows : 1;
+                    for (int l = 0; l < l_end; ++l) {           // mixed flags: rows strictly in order
+                        if (mixed && lane != l) { __syncwarp(); continue; }
+                        uint32_t iv = Im[0] | Im[1] | Im[2];
+                        while (iv) {
+                            const int ex = __ffs(iv) - 1;
+                            iv &= iv - 1;
+#pragma unroll
+                            for (int kd = 0; kd < 3; ++kd) {
+                                if (!((Im[kd] >> ex) & 1u)) continue;
+                                const int ki = ((k0[kd] >> ex) & 1u) | (((k1[kd] >> ex) & 1u) << 1) | (((k2[kd] >> ex) & 1u) << 2);
+                                const int kn = c_kicks[tab][frot][kd].n;
+                                const bool nulk = (kd != 1 && ki == kn - 1);
+                                const int kx = (int)(((*kpack)[frot][kd][0] >> (4 * ki)) & 15u) - 2;
+                                const int ky = (int)(((*kpack)[frot][kd][1] >> (4 * ki)) & 15u) - 2;
+                                flag_cell(&S.fu[(frot + kd + 1) & 3][ky_row - ky], 1u << (ex + kx), nulk);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+
+    // ---- _convert_placements_to_policy (move_generation.py:650-749): lane = row ----
+    const int pbase = c_plane_base[type];
+    const int nrot_planes = c_plane_nrot[type];
+    const bool zsi = (type == P_Z || type == P_S || type == P_I);
+    for (int rot = 0; rot < 4; ++rot) {
+        if (type == P_O && rot > 0) break;
+        for (int my = 2 + lane; my < TRL_MAP_H - 1; my += 32) {
+            const uint32_t wv = S.vv[rot][my];
+            const uint32_t placed = (wv >> 16) & ~S.vv[rot][my + 1] & 0xFFFFu;
+            if (!placed) continue;
+            int row = my - 2;
+            uint32_t bits = placed;  // bit mx == policy column x + 2
+            if (zsi) {               // rot 2 -> (rot 0, row + 1); rot 3 -> (rot 1, col - 1)
+                if (rot == 2) row += 1;
+                else if (rot == 3) bits >>= 1;
+            }
+            if (!is_T) {
+                or_chunk(mask, pbase + rot % nrot_planes, row, bits & 0x7FFu);
+            } else {
+                const uint32_t fw = S.fu[rot][my];
+                const uint32_t f = fw & placed, u = fw >> 16;
+                or_chunk(mask, pbase + rot, row, (placed & ~f) & 0x7FFu);
+                or_chunk(mask, pbase + 4 + rot, row, (f & ~u) & 0x7FFu);
+                or_chunk(mask, pbase + 8 + rot, row, (f & u) & 0x7FFu);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+movegen_warp_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restrict__ cur,
+                    const uint8_t* __restrict__ alt, const TrlGame* __restrict__ games,
+                    const int32_t* __restrict__ index, int n, uint32_t* __restrict__ mask_bits,
+                    uint16_t* __restrict__ moves, int moves_cap, uint16_t* __restrict__ n_moves,
+                    uint32_t* __restrict__ status) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    PieceState* ps = reinterpret_cast<PieceState*>(smem_raw);
+    CallState* cs = reinterpret_cast<CallState*>(smem_raw + sizeof(PieceState) * kWarps);
+    __shared__ uint32_t s_kpack[2][4][3][2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int slot = warp >> 1, which = warp & 1;
+    const int i = blockIdx.x * kCallsPerBlock + slot;
+    CallState& C = cs[slot];
+
+    if (tid < 24) {   // kick offsets packed 4 bits each (+2) so a lane can index them by kick number
+        const int t = tid / 12, r = (tid / 3) % 4, kd = tid % 3;
+        const TrlKicks& K = c_kicks[t][r][kd];
+        uint32_t px = 0, py = 0;
+        for (int ki = 0; ki < K.n; ++ki) {
+            px |= (uint32_t)(K.k[ki][0] + 2) << (4 * ki);
+            py |= (uint32_t)(K.k[ki][1] + 2) << (4 * ki);
+        }
+        s_kpack[t][r][kd][0] = px;
+        s_kpack[t][r][kd][1] = py;
+    }
+    // ---- stage the call: board rows, piece types, zeroed mask (both warps of the call) ----
+    if (i < n) {
+        for (int w2 = which * 32 + lane; w2 < TRL_MASK_WORDS + 2; w2 += 64) C.mask[w2] = 0u;
+        if (which == 0) {
+            int c = TRL_NONE, a = TRL_NONE, skip = 0;
+            if (games) {
+                const int gi = index ? index[i] : i;
+                if (gi < 0) skip = 1;
+                else {
+                    const TrlPlayer& p = games[gi].players[games[gi].turn & 1];
+                    for (int r = lane; r < TRL_ROWS; r += 32) C.rows[r] = p.rows[r];
+                    c = p.piece;
+                    a = (p.held != TRL_NONE) ? p.held : (p.qlen > 0 ? p.queue[0] : TRL_NONE);
+                }
+            } else {
+                for (int r = lane; r < TRL_ROWS; r += 32) C.rows[r] = boards[(size_t)i * TRL_ROWS + r];
+                c = cur[i];
+                a = alt[i];
+            }
+            if (c > 6 && c != TRL_NONE) c = TRL_NONE;
+            if (a > 6 && a != TRL_NONE) a = TRL_NONE;
+            if (lane == 0) {
+                C.cur = c; C.alt = a; C.skip = skip;
+                C.status = (!skip && c == TRL_NONE && a == TRL_NONE) ? TRL_ST_NO_PIECE : 0u;
+            }
+        }
+    }
+    __syncthreads();
+
+    if (i < n && !C.skip) {
+        const int c = C.cur, a = C.alt;
+        uint32_t st = 0;
+        const int tab = 0;
+        (void)tab;
+        if (which == 0 && c != TRL_NONE) search_piece_warp(ps[warp], C.rows, c, false, C.mask, st, &s_kpack[c == P_I ? 1 : 0]);
+        if (which == 1 && a != TRL_NONE && a != c) search_piece_warp(ps[warp], C.rows, a, true, C.mask, st, &s_kpack[a == P_I ? 1 : 0]);
+        st = __reduce_or_sync(0xffffffffu, st);
+        if (st && lane == 0) atomicOr(&C.status, st);
+    }
+    __syncthreads();
+
+    // ---- outputs: coalesced mask, ascending move list (= argwhere order), count, status ----
+    if (i < n && which == 0) {
+        if (C.skip) {
+            if (lane == 0) {
+                if (n_moves) n_moves[i] = 0;
+                if (status) status[i] = 0;
+            }
+            return;
+        }
+        if (mask_bits) {
+            uint32_t* gm = mask_bits + (size_t)i * TRL_MASK_WORDS;
+            for (int w2 = lane; w2 < TRL_MASK_WORDS; w2 += 32) gm[w2] = C.mask[w2];
+        }
+        // lane owns 12 consecutive words (the last lanes fewer): counts -> prefix -> ordered writes
+        const int w0 = lane * 12;
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const int w2 = w0 + k;
+            if (w2 < TRL_MASK_WORDS) cnt += __popc(C.mask[w2]);
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t st = C.status;
+        if (moves) {
+            uint16_t* mv = moves + (size_t)i * moves_cap;
+            int pos = incl - cnt;
+            for (int k = 0; k < 12; ++k) {
+                const int w2 = w0 + k;
+                if (w2 >= TRL_MASK_WORDS) break;
+                uint32_t m = C.mask[w2];
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (pos < moves_cap) mv[pos] = (uint16_t)(w2 * 32 + b);
+                    ++pos;
+                }
+            }
+            if (total > moves_cap) st |= TRL_ST_MOVES_TRUNC;
+        }
+        if (lane == 0) {
+            if (n_moves) n_moves[i] = (uint16_t)total;
+            if (status) status[i] = st;
+        }
+    }
+}
+
+}  // namespace
+
+// Launch the warp-cooperative kernel (same argument contract as movegen.cu's launch_movegen).
+int trl_launch_movegen_warp(const uint16_t* boards, const uint8_t* cur, const uint8_t* alt, const TrlGame* games,
+                            const int32_t* index, int n, uint32_t* mask_bits, uint16_t* moves, int moves_cap,
+                            uint16_t* n_moves, uint32_t* status, cudaStream_t stream) {
+    const size_t smem = sizeof(PieceState) * kWarps + sizeof(CallState) * kCallsPerBlock;
+    static bool configured = false;
+    if (!configured) {
+        int rc = trl_check(cudaFuncSetAttribute(movegen_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (rc) return rc;
+        configured = true;
+    }
+    const int blocks = (n + kCallsPerBlock - 1) / kCallsPerBlock;
+    movegen_warp_kernel<<<blocks, kWarps * 32, smem, stream>>>(boards, cur, alt, games, index, n, mask_bits, moves,
+                                                              moves_cap, n_moves, status);
+    return trl_check(cudaGetLastError());
+}
