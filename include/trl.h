@@ -352,6 +352,18 @@ int trl_alphasame_trunk_rows(const void* grids_bf16, int n_images, int n_blocks,
                              const float* consts, const void* stem_w, void* out_bf16, void* stream);
 int trl_alphasame_trunk_rows_max_blocks(void);
 
+/*
+ * Tail of AlphaSame.forward between the trunk and the policy GEMM (architectures.py:128-142), fused:
+ * osidedense (Linear 400->16, BN1d, ReLU) on the opponent features, the 521-wide concatenation
+ * (written 528 wide, zero padded, bf16) and the value head (Linear 521->16, BN1d, ReLU, Linear 16->1,
+ * Sigmoid|Tanh).  feats [2n][400] bf16 (own grids, then opponent grids), extras [n][105] bf16,
+ * weights fp32 [trl_alphasame_heads_weight_floats()]: Wo_t[400][16], bo[16], Wv_t[528][16], bv[16],
+ * w2[16], b2 (BatchNorm folded).  x_out [n][528] bf16, value_out [n] bf16.
+ */
+int trl_alphasame_heads(const void* feats_bf16, const void* extras_bf16, int n_leaves, const float* weights,
+                        int use_tanh, void* x_out_bf16, void* value_out_bf16, void* stream);
+int trl_alphasame_heads_weight_floats(void);
+
 #ifdef __cplusplus
 }
 #endif

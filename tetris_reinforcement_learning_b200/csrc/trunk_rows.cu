@@ -143,18 +143,20 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
+// relu + round to bf16 of two floats in ONE instruction (F2FP.RELU.BF16.PACK_AB)
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 
-// the 16 channels of (column x, slot) -> two 16-byte stores (one per 8-channel plane)
-__device__ __forceinline__ void store_operand(uint8_t* act, int x, int slot, const float (&v)[16]) {
+// relu(v[0..16)) of (column x, slot) -> two 16-byte stores (one per 8-channel plane)
+__device__ __forceinline__ void store_operand_relu(uint8_t* act, int x, int slot, const float (&v)[16]) {
     uint4 a, b;
-    a.x = pack_bf16x2(v[0], v[1]);   a.y = pack_bf16x2(v[2], v[3]);
-    a.z = pack_bf16x2(v[4], v[5]);   a.w = pack_bf16x2(v[6], v[7]);
-    b.x = pack_bf16x2(v[8], v[9]);   b.y = pack_bf16x2(v[10], v[11]);
-    b.z = pack_bf16x2(v[12], v[13]); b.w = pack_bf16x2(v[14], v[15]);
+    a.x = pack_relu_bf16x2(v[0], v[1]);   a.y = pack_relu_bf16x2(v[2], v[3]);
+    a.z = pack_relu_bf16x2(v[4], v[5]);   a.w = pack_relu_bf16x2(v[6], v[7]);
+    b.x = pack_relu_bf16x2(v[8], v[9]);   b.y = pack_relu_bf16x2(v[10], v[11]);
+    b.z = pack_relu_bf16x2(v[12], v[13]); b.w = pack_relu_bf16x2(v[14], v[15]);
     uint8_t* p = act + x * kColBytes + (slot + 1) * 16;
     *reinterpret_cast<uint4*>(p) = a;
     *reinterpret_cast<uint4*>(p + kPlaneBytes) = b;
@@ -314,9 +316,13 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
                 const int layer = pl - 1;
                 const bool first_conv = (pl > 0) && !(layer & 1);
                 const bool last = (layer == n_layers - 1);
+                // next operand = relu(ka * acc + kb) per channel, with the halo mask folded into the
+                // constants (halo slots and missing images get ka = kb = 0 -> exact zeros)
                 float ka[16], kb[16];
                 if (first_conv) {
                     load16(s_const + (layer >> 1) * 48 + 32, kb);              // bn2 bias (scale folded into the weights)
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) ka[c] = 1.f;
                 } else if (!last) {
                     const float* nb = s_const + (pl == 0 ? 0 : (layer >> 1) + 1) * 48;
                     load16(nb, ka);                                            // next block's bn1 scale, bias
@@ -326,7 +332,14 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
                     load16(fc, ka);
                     load16(fc + 16, kb);
                 }
-                mbar_wait(bar_m + 8 * (set < 4 ? 2 * set + 2 : 9), ph);   // columns 2p-1..2p+2 of this layer are final
+                if (!inside) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) { ka[c] = 0.f; kb[c] = 0.f; }
+                }
+                // columns 2p-1..2p+2 of this layer are final.  Only the set's first warp polls the mbarrier;
+                // the other three sleep on a hardware barrier.
+                if ((warp & 3) == 0) mbar_wait(bar_m + 8 * (set < 4 ? 2 * set + 2 : 9), ph);
+                asm volatile("bar.sync %0, 128;" :: "r"(1 + set) : "memory");
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const bool tr = trace && blockIdx.x == 0 && first_group && (tid & 127) == 0;
                 if (tr) trace[(pl * 10 + 2 * set) * 4 + 1] = clock64();
@@ -334,34 +347,30 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
                 for (int h = 0; h < 2; ++h) {
                     const int x = 2 * set + h;
                     float d[16], v[16];
-                    if (first_conv) {
-                        // U = relu(conv1'(T) + c2)
-                        const uint32_t ta = tmem_lane + (uint32_t)(kColD + 16 * x);
-                        tmem_ld16(ta, d);
-                        tmem_st16_zero(ta);
+                    const uint32_t ta = tmem_lane + (uint32_t)((first_conv ? kColD : kColX) + 16 * x);
+                    tmem_ld16(ta, d);
+                    if (first_conv) tmem_st16_zero(ta);      // D1 is accumulate-only: leave it zeroed
+                    if (!last) {
+                        // first conv: U = relu(conv1'(T) + c2);  else T = relu(bn1_next(X)), X = stem / X + conv2(U)
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) v[c] = inside ? fmaxf(d[c] + kb[c], 0.f) : 0.f;
-                        store_operand(act, x, slot, v);
-                    } else {
-                        // X (in TMEM) holds the stem output / X + conv2(U); next operand T = relu(bn1_next(X))
-                        tmem_ld16(tmem_lane + (uint32_t)(kColX + 16 * x), d);
-                        if (!last) {
+                        for (int c = 0; c < 16; ++c) v[c] = fmaf(ka[c], d[c], kb[c]);
+                        store_operand_relu(act, x, slot, v);
+                    } else if (inside) {
+                        // head of the trunk: BN-ReLU, 1x1 conv to one channel, BN-ReLU, flatten
+                        const float* fc = s_const + n_blocks * 48;
+                        float acc = 0.f;
 #pragma unroll
-                            for (int c = 0; c < 16; ++c) v[c] = inside ? fmaxf(fmaf(ka[c], d[c], kb[c]), 0.f) : 0.f;
-                            store_operand(act, x, slot, v);
-                        } else if (inside) {
-                            // head of the trunk: BN-ReLU, 1x1 conv to one channel, BN-ReLU, flatten
-                            const float* fc = s_const + n_blocks * 48;
-                            float acc = 0.f;
-#pragma unroll
-                            for (int c = 0; c < 16; ++c) acc = fmaf(fc[32 + c], fmaxf(fmaf(ka[c], d[c], kb[c]), 0.f), acc);
-                            out[(size_t)(g * kImgs + sj) * 400 + sy * 10 + x] = __float2bfloat16(fmaxf(fmaf(fc[48], acc, fc[49]), 0.f));
-                        }
+                        for (int c = 0; c < 16; ++c) acc = fmaf(fc[32 + c], fmaxf(fmaf(ka[c], d[c], kb[c]), 0.f), acc);
+                        out[(size_t)(g * kImgs + sj) * 400 + sy * 10 + x] = __float2bfloat16(fmaxf(fmaf(fc[48], acc, fc[49]), 0.f));
                     }
                     if (tr && h == 0) trace[(pl * 10 + 2 * set) * 4 + 2] = clock64();
                 }
                 if (!last) {
+                    if (tr) trace[(pl * 10 + 2 * set + 1) * 4 + 1] = clock64();
                     if (first_conv) tmem_wait_st();
+                    if (tr) trace[(pl * 10 + 2 * set + 1) * 4 + 2] = clock64();
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (tr) trace[(pl * 10 + 2 * set + 1) * 4 + 3] = clock64();
                     publish_column(bar_o + 8 * set);
                     if (tr) trace[(pl * 10 + 2 * set) * 4 + 3] = clock64();
                 }

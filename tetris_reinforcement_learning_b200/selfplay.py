@@ -92,7 +92,7 @@ class SelfPlayEngine:
 
     def __init__(self, config, evaluator, n_games, device="cuda:0", seed=0, first_game_id=0, game_id_stride=1,
                  feature_dtype=torch.float32, node_cap=None, sample_cap=None, restart_finished=True, save_all=None,
-                 max_rounds=None, use_cuda_graph=True):
+                 max_rounds=None, use_cuda_graph=True, overlap_movegen=True):
         if config.ruleset != "s2":
             raise NotImplementedError("only ruleset 's2' is implemented on the device path")
         if config.move_algorithm != "convolutional":
@@ -105,6 +105,7 @@ class SelfPlayEngine:
         self.seed = int(seed)
         self.feature_dtype = feature_dtype
         self.use_cuda_graph = use_cuda_graph
+        self.overlap_movegen = overlap_movegen
         iters_max = max(self.params.max_iter, self.params.iters_long if (config.training and config.use_playout_cap_randomization) else 0)
         self.state_cap = iters_max + 2
         self.node_cap = int(node_cap) if node_cap else max(1024, iters_max * 96)
@@ -183,10 +184,13 @@ class SelfPlayEngine:
         _native.check(lib.trl_search_select(bp, pp, st), "trl_search_select")
         # the leaves' legal placements only feed `expand`: enumerate them on a forked stream,
         # concurrently with feature encoding and the network (joined before expand)
-        if self._side is None:
-            self._side = torch.cuda.Stream(self.device)
-        self._side.wait_stream(main)
-        _native.check(lib.trl_search_movegen(bp, self._side.cuda_stream), "trl_search_movegen")
+        if self.overlap_movegen:
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.device)
+            self._side.wait_stream(main)
+            _native.check(lib.trl_search_movegen(bp, self._side.cuda_stream), "trl_search_movegen")
+        else:
+            _native.check(lib.trl_search_movegen(bp, st), "trl_search_movegen")
         dt = 0 if self.feature_dtype == torch.float32 else 1
         _native.check(lib.trl_encode_features(self.t["states"].data_ptr(), self.t["leaf_state"].data_ptr(), self.G,
                                               self.grids.data_ptr(), self.extras.data_ptr(), dt, st), "trl_encode_features")
@@ -201,7 +205,8 @@ class SelfPlayEngine:
         if logits.dtype not in (torch.float32, torch.bfloat16):
             raise ValueError("evaluator outputs must be float32 or bfloat16")
         self._values, self._logits = values, logits  # keep alive (graph-owned memory when captured)
-        main.wait_stream(self._side)
+        if self.overlap_movegen:
+            main.wait_stream(self._side)
         _native.check(lib.trl_search_expand(bp, pp, values.data_ptr(), logits.data_ptr(), logits.stride(0),
                                             0 if logits.dtype == torch.float32 else 1, st), "trl_search_expand")
 

@@ -94,12 +94,34 @@ def trunk_forward(packed, grids, out=None):
     return out
 
 
-def make_fused_evaluator(net, dtype=torch.bfloat16, layout=None):
-    """Engine evaluator: fused tcgen05 trunk on both grids, then the (GEMM-shaped) heads in PyTorch."""
+def _fold_linear_bn(linear, bn):
+    """Linear followed by eval-mode BatchNorm1d -> (weight [out, in], bias [out]) in fp32."""
+    s, t = _fold_bn(bn)
+    return linear.weight.detach().float() * s[:, None], linear.bias.detach().float() * s + t
+
+
+def pack_alphasame_heads(net, device=None):
+    """fp32 weights of csrc/heads.cu: Wo_t[400][16], bo[16], Wv_t[528][16], bv[16], w2[16], b2, pad."""
+    device = device or next(net.parameters()).device
+    wo, bo = _fold_linear_bn(net.osidedense[0], net.osidedense[1])
+    wv, bv = _fold_linear_bn(net.value_head[0], net.value_head[1])
+    wv_t = torch.zeros((528, 16), dtype=torch.float32, device=wv.device)
+    wv_t[:wv.shape[1]] = wv.t()
+    lin2 = net.value_head[3]
+    parts = [wo.t().contiguous().reshape(-1), bo, wv_t.reshape(-1), bv, lin2.weight.detach().float().reshape(16),
+             lin2.bias.detach().float().reshape(1), torch.zeros(3, device=wv.device)]
+    out = torch.cat(parts).to(device).contiguous()
+    assert out.numel() == _native.lib().trl_alphasame_heads_weight_floats()
+    return out
+
+
+def make_fused_evaluator(net, dtype=torch.bfloat16, layout=None, fused_heads=True):
+    """Engine evaluator: fused tcgen05 trunk on both grids, one fused kernel for the opponent
+    summary + concatenation + value head (csrc/heads.cu), and the policy head as a library GEMM."""
     assert supports(net) and dtype == torch.bfloat16
     net = net.eval()
     packed = pack_alphasame_trunk(net, layout=layout)
-    osidedense, value_head = net.osidedense.to(dtype), net.value_head.to(dtype)
+    use_tanh = int(isinstance(net.value_head[-1], torch.nn.Tanh))
     # The head input has 521 features; cuBLAS needs K % 8 == 0 for its tensor-core kernels, so the
     # policy / first value layer weights get zero columns up to 528 and x gets matching zeros.
     k_in = net.policy_head.in_features
@@ -115,18 +137,35 @@ def make_fused_evaluator(net, dtype=torch.bfloat16, layout=None):
         return w.contiguous(), b.contiguous()
 
     w_pol, b_pol = padded(net.policy_head)
-    w_val, b_val = padded(value_head[0])
-    value_tail = value_head[1:]
-    zeros = {}
+    if fused_heads:
+        w_heads = pack_alphasame_heads(net)
+        lib = _native.lib()
 
-    def evaluate(grids, extras):
-        b = extras.shape[0]
-        feats = trunk_forward(packed, grids)
-        if b not in zeros:
-            zeros[b] = torch.zeros((b, k_pad - k_in), dtype=dtype, device=extras.device)
-        x = torch.cat([feats[:b], extras[:, :SIDE_FEATS], osidedense(feats[b:]), extras[:, SIDE_FEATS:], zeros[b]], dim=1)
-        value = value_tail(torch.nn.functional.linear(x, w_val, b_val))
-        return value, torch.nn.functional.linear(x, w_pol, b_pol)   # logits [G, 11584], last column unused
+        def evaluate(grids, extras):
+            b = extras.shape[0]
+            feats = trunk_forward(packed, grids)
+            x = torch.empty((b, k_pad), dtype=dtype, device=extras.device)
+            value = torch.empty(b, dtype=dtype, device=extras.device)
+            if extras.dtype != dtype or not extras.is_contiguous():
+                extras = extras.to(dtype).contiguous()
+            rc = lib.trl_alphasame_heads(feats.data_ptr(), extras.data_ptr(), b, w_heads.data_ptr(), use_tanh,
+                                         x.data_ptr(), value.data_ptr(), torch.cuda.current_stream(extras.device).cuda_stream)
+            _native.check(rc, "trl_alphasame_heads")
+            return value, torch.nn.functional.linear(x, w_pol, b_pol)   # logits [G, 11584], last column unused
+    else:
+        osidedense, value_head = net.osidedense.to(dtype), net.value_head.to(dtype)
+        w_val, b_val = padded(value_head[0])
+        value_tail = value_head[1:]
+        zeros = {}
+
+        def evaluate(grids, extras):
+            b = extras.shape[0]
+            feats = trunk_forward(packed, grids)
+            if b not in zeros:
+                zeros[b] = torch.zeros((b, k_pad - k_in), dtype=dtype, device=extras.device)
+            x = torch.cat([feats[:b], extras[:, :SIDE_FEATS], osidedense(feats[b:]), extras[:, SIDE_FEATS:], zeros[b]], dim=1)
+            value = value_tail(torch.nn.functional.linear(x, w_val, b_val))
+            return value, torch.nn.functional.linear(x, w_pol, b_pol)
 
     evaluate.packed = packed
     return evaluate

@@ -25,9 +25,9 @@ t = buf.cpu().view(21, 10, 4)
 t0 = int(t[0, 0, 0])
 print("layer col :  issue  epi_wake  ld_done  published   (clk since first issue)")
 for layer in (0, 1, 2, 11, 12):
-    for c in range(10):
-        if c & 1 and int(t[layer, c, 1]) == 0 and int(t[layer, c, 0]) == 0:
-            continue
+    for c in range(0, 10, 2):
         r = [int(v) - t0 if int(v) else -1 for v in t[layer, c]]
-        print(f"{layer:3d} {c:2d} : {r[0]:7d} {r[1]:7d} {r[2]:7d} {r[3]:7d}   wake-issue {r[1]-r[0]:6d}  epi {r[3]-r[1]:6d}")
+        q = [int(v) - t0 if int(v) else -1 for v in t[layer, c + 1]]
+        print(f"{layer:3d} {c:2d} : issue {r[0]:7d} (c+1 {q[0]:7d})  wake {r[1]:7d}  col0 +{r[2]-r[1]:5d}  col1 +{q[1]-r[2]:5d}  "
+              f"wait_st +{q[2]-q[1]:5d}  proxyfence +{q[3]-q[2]:5d}  publish +{r[3]-q[3]:5d}   epi total {r[3]-r[1]:6d}")
 print("clk per layer (issue col0 L -> L+1):", [int(t[l + 1, 0, 0] - t[l, 0, 0]) for l in range(1, 20)])
