@@ -300,13 +300,16 @@ typedef struct TrlSearchBuffers {
     TrlSample* samples; uint32_t* sample_count; TrlGameEnd* ends; uint32_t* end_count;
     uint32_t* next_game_id;                  /* [1] id given to the next restarted game     */
     const double* noise_override;            /* [n_games * moves_cap] or NULL (tests)       */
+    int32_t* leaf_parent;                    /* [n_games] state index of the leaf's parent, -1 = the leaf is
+                                                the root / nothing to evaluate (may be NULL)            */
 } TrlSearchBuffers;
 
 int trl_sizeof_search_ctl(void);
 int trl_sizeof_sample(void);
 
 /* Step part 1: (start a search if needed,) select a leaf per game and materialise its state;
- * writes leaf_state[g] = index into `states` of the position the net must evaluate, or -1. */
+ * writes leaf_state[g] = index into `states` of the position the net must evaluate, or -1, and
+ * (if leaf_parent != NULL) leaf_parent[g] = index of the state it was reached from, or -1. */
 int trl_search_select(const TrlSearchBuffers* buf, const TrlSearchParams* prm, void* stream);
 
 /* Legal placements for the selected leaves: trl_movegen_games on states[leaf_state[g]]. */
@@ -351,6 +354,37 @@ int trl_alphasame_trunk(const void* grids_bf16, int n_images, int n_blocks, cons
 int trl_alphasame_trunk_rows(const void* grids_bf16, int n_images, int n_blocks, const void* w_packed,
                              const float* consts, const void* stem_w, void* out_bf16, void* stream);
 int trl_alphasame_trunk_rows_max_blocks(void);
+
+/*
+ * Trunk-feature reuse inside a search (exact, not an approximation).  A move only changes the
+ * MOVER's board (player.py:154-176; garbage rises on the mover's own board, game.py:100-117, the
+ * opponent only gets entries appended to its pending list), and AlphaSame runs the SAME trunk on
+ * both boards (architectures.py:120-133).  So for a leaf reached from `parent`, the features of
+ * the side to move's board are those already computed for `parent`; only the mover's new board
+ * needs the trunk.  `cache` holds [n_states][2 players][400] bf16 trunk outputs.
+ *
+ * trl_encode_features_cached: per leaf g (leaf_state[g] >= 0) writes extras[g] (as
+ * trl_encode_features), copies cache[parent][side to move] -> cache[leaf][side to move] (or, for a
+ * root leaf, queues that board too), appends the 0/1 cells of every board that needs the trunk to
+ * `images` ([<= 2n][400] bf16, compact, *n_images = count) with image_dest[k] = cache row
+ * (state*2 + player) the trunk must write, and sets own_row[g] / opp_row[g] = cache rows the heads
+ * read (or -1).  *n_images must be zero on entry.
+ */
+int trl_encode_features_cached(const TrlGame* states, const int32_t* leaf_state, const int32_t* leaf_parent, int n,
+                               void* cache_bf16, void* images_bf16, int32_t* image_dest, int32_t* n_images,
+                               void* extras_bf16, int32_t* own_row, int32_t* opp_row, void* stream);
+
+/* trl_alphasame_trunk_rows with a device-side image count and scattered output rows:
+ * out_bf16[out_row[k]][400] = trunk(images[k]) for k < *n_images_dev (capacity max_images). */
+int trl_alphasame_trunk_rows_indexed(const void* images_bf16, const int32_t* n_images_dev, int max_images,
+                                     const int32_t* out_row, int n_blocks, const void* w_packed, const float* consts,
+                                     const void* stem_w, void* out_bf16, void* stream);
+
+/* trl_alphasame_heads reading its two feature rows through indices into a cache
+ * ([rows][400] bf16; own_row[g] < 0: leaf skipped). */
+int trl_alphasame_heads_indexed(const void* cache_bf16, const int32_t* own_row, const int32_t* opp_row,
+                                const void* extras_bf16, int n_leaves, const float* weights, int use_tanh,
+                                void* x_out_bf16, void* value_out_bf16, void* stream);
 
 /*
  * Tail of AlphaSame.forward between the trunk and the policy GEMM (architectures.py:128-142), fused:

@@ -11,7 +11,7 @@ from .state import GAME_DTYPE, PLAYER_DTYPE
 _SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtrl_b200.so")
 _lib = None
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_void_p, c_int, c_u64, c_u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32
 
@@ -41,6 +41,9 @@ SIGNATURES = {
     "trl_alphasame_trunk_rows_max_blocks": (c_int, []),
     "trl_alphasame_heads": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "trl_alphasame_heads_weight_floats": (c_int, []),
+    "trl_encode_features_cached": (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] * 8),
+    "trl_alphasame_trunk_rows_indexed": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "trl_alphasame_heads_indexed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "trl_encode_features": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
 }
 
@@ -100,4 +103,4 @@ class SearchBuffers(ctypes.Structure):
                                                "states", "first_child", "n_children", "fpu",
                                                "ctl", "games", "leaf_state", "legal", "n_legal",
                                                "samples", "sample_count", "ends", "end_count",
-                                               "next_game_id", "noise_override")]
+                                               "next_game_id", "noise_override", "leaf_parent")]

@@ -62,7 +62,85 @@ encode_features_kernel(const TrlGame* __restrict__ games, const int32_t* __restr
     if (lane == 0) extras[(size_t)i * kExtras + 104] = to_out<T>((float)turn);  // players[turn].color == turn
 }
 
+// Feature encoding for the trunk-feature cache (see include/trl.h): extras as above; the board
+// cells only of the boards whose trunk features are not known yet, as a compact image list.
+__global__ void __launch_bounds__(kWarps * 32)
+encode_features_cached_kernel(const TrlGame* __restrict__ states, const int32_t* __restrict__ leaf_state,
+                              const int32_t* __restrict__ leaf_parent, int n, __nv_bfloat16* __restrict__ cache,
+                              __nv_bfloat16* __restrict__ images, int32_t* __restrict__ image_dest,
+                              int32_t* __restrict__ n_images, __nv_bfloat16* __restrict__ extras,
+                              int32_t* __restrict__ own_row, int32_t* __restrict__ opp_row) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int si = leaf_state[i];
+    if (si < 0) {
+        if (lane == 0) { own_row[i] = -1; opp_row[i] = -1; }
+        return;
+    }
+    const int pi = leaf_parent[i];
+    const TrlGame& g = states[si];
+    const int turn = g.turn & 1;
+    const int n_new = (pi < 0) ? 2 : 1;               // root: both boards; else only the mover's (= opponent of the side to move)
+    int pos = 0;
+    if (lane == 0) pos = atomicAdd(n_images, n_new);
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const int pl = side == 0 ? turn : 1 - turn;
+        const TrlPlayer& p = g.players[pl];
+        const int row = si * 2 + pl;
+        if (side == 0 && pi >= 0) {
+            // the side to move did not move: its board is the parent's, so are its trunk features
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(cache + (size_t)(pi * 2 + pl) * kCells);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(cache + (size_t)row * kCells);
+            for (int c = lane; c < kCells / 2; c += 32) dst[c] = src[c];
+        } else {
+            const int k = pos + ((side == 1 && pi < 0) ? 1 : 0);
+            __nv_bfloat16* out = images + (size_t)k * kCells;
+            for (int c = lane; c < kCells; c += 32) {
+                const int r = c / TRL_COLS, col = c - r * TRL_COLS;
+                out[c] = __float2bfloat16((float)((p.rows[r] >> col) & 1u));
+            }
+            if (lane == 0) image_dest[k] = row;
+        }
+        __nv_bfloat16* ex = extras + (size_t)i * kExtras + side * 52;
+        for (int c = lane; c < 49; c += 32) {
+            const int slot = c / 7, mino = c - slot * 7;
+            int piece = TRL_NONE;
+            if (slot == 0) piece = p.piece;
+            else if (slot == 1) piece = p.held;
+            else if (slot - 2 < p.qlen) piece = p.queue[slot - 2];
+            ex[c] = __float2bfloat16(piece == mino ? 1.f : 0.f);
+        }
+        if (lane == 0) {
+            ex[49] = __float2bfloat16((float)p.b2b);
+            ex[50] = __float2bfloat16((float)p.combo);
+            ex[51] = __float2bfloat16((float)p.n_recv);
+        }
+    }
+    if (lane == 0) {
+        extras[(size_t)i * kExtras + 104] = __float2bfloat16((float)turn);
+        own_row[i] = si * 2 + turn;
+        opp_row[i] = si * 2 + (1 - turn);
+    }
+}
+
 }  // namespace
+
+extern "C" int trl_encode_features_cached(const TrlGame* states, const int32_t* leaf_state, const int32_t* leaf_parent,
+                                          int n, void* cache_bf16, void* images_bf16, int32_t* image_dest,
+                                          int32_t* n_images, void* extras_bf16, int32_t* own_row, int32_t* opp_row,
+                                          void* stream) {
+    if (n < 0 || !states || !leaf_state || !leaf_parent || !cache_bf16 || !images_bf16 || !image_dest || !n_images ||
+        !extras_bf16 || !own_row || !opp_row)
+        return TRL_E_ARG;
+    if (n == 0) return TRL_OK;
+    encode_features_cached_kernel<<<(n + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(
+        states, leaf_state, leaf_parent, n, (__nv_bfloat16*)cache_bf16, (__nv_bfloat16*)images_bf16, image_dest,
+        n_images, (__nv_bfloat16*)extras_bf16, own_row, opp_row);
+    return trl_check(cudaGetLastError());
+}
 
 extern "C" int trl_encode_features(const TrlGame* games, const int32_t* index, int n, void* grids,
                                    void* extras, int dtype, void* stream) {

@@ -23,7 +23,9 @@ constexpr int kOffWo = 0, kOffBo = kOffWo + kFeat * 16, kOffWv = kOffBo + 16, kO
               kOffW2 = kOffBv + 16, kOffB2 = kOffW2 + 16, kWFloats = kOffB2 + 4;
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-alphasame_heads_kernel(const __nv_bfloat16* __restrict__ feats,    // [2G][400]: own grids then opponent grids
+alphasame_heads_kernel(const __nv_bfloat16* __restrict__ feats,    // [2G][400]: own grids then opponent grids (or a cache)
+                       const int32_t* __restrict__ own_row,        // optional: feature rows of leaf g (< 0: skip)
+                       const int32_t* __restrict__ opp_row,
                        const __nv_bfloat16* __restrict__ extras,   // [G][105]
                        int G, const float* __restrict__ weights, int use_tanh,
                        __nv_bfloat16* __restrict__ x_out,          // [G][528]
@@ -39,8 +41,10 @@ alphasame_heads_kernel(const __nv_bfloat16* __restrict__ feats,    // [2G][400]:
     const int o = lane & 15, h = lane >> 4;
     for (int g = blockIdx.x * kWarpsPerBlock + warp; g < G; g += gridDim.x * kWarpsPerBlock) {
         // ---- stage: own features, side inputs, opponent features ----
-        const __nv_bfloat162* fa = reinterpret_cast<const __nv_bfloat162*>(feats + (size_t)g * kFeat);
-        const __nv_bfloat162* fb = reinterpret_cast<const __nv_bfloat162*>(feats + (size_t)(G + g) * kFeat);
+        const int ra = own_row ? own_row[g] : g, rb = own_row ? opp_row[g] : G + g;
+        if (ra < 0) continue;   // warp-uniform
+        const __nv_bfloat162* fa = reinterpret_cast<const __nv_bfloat162*>(feats + (size_t)ra * kFeat);
+        const __nv_bfloat162* fb = reinterpret_cast<const __nv_bfloat162*>(feats + (size_t)rb * kFeat);
         for (int i = lane; i < kFeat / 2; i += 32) {
             const float2 a = __bfloat1622float2(fa[i]), b = __bfloat1622float2(fb[i]);
             xs[2 * i] = a.x; xs[2 * i + 1] = a.y;
@@ -80,8 +84,9 @@ alphasame_heads_kernel(const __nv_bfloat16* __restrict__ feats,    // [2G][400]:
 
 extern "C" int trl_alphasame_heads_weight_floats(void) { return kWFloats; }
 
-extern "C" int trl_alphasame_heads(const void* feats_bf16, const void* extras_bf16, int n_leaves, const float* weights,
-                                   int use_tanh, void* x_out_bf16, void* value_out_bf16, void* stream) {
+static int launch_heads(const void* feats_bf16, const int32_t* own_row, const int32_t* opp_row, const void* extras_bf16,
+                        int n_leaves, const float* weights, int use_tanh, void* x_out_bf16, void* value_out_bf16,
+                        void* stream) {
     if (n_leaves < 0 || !feats_bf16 || !extras_bf16 || !weights || !x_out_bf16 || !value_out_bf16) return TRL_E_ARG;
     if (n_leaves == 0) return TRL_OK;
     const int smem = (kWFloats + kWarpsPerBlock * (kPad + kFeat)) * 4;
@@ -97,7 +102,19 @@ extern "C" int trl_alphasame_heads(const void* feats_bf16, const void* extras_bf
     int blocks = (n_leaves + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > 2 * sms) blocks = 2 * sms;
     alphasame_heads_kernel<<<blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)feats_bf16, (const __nv_bfloat16*)extras_bf16, n_leaves, weights, use_tanh,
+        (const __nv_bfloat16*)feats_bf16, own_row, opp_row, (const __nv_bfloat16*)extras_bf16, n_leaves, weights, use_tanh,
         (__nv_bfloat16*)x_out_bf16, (__nv_bfloat16*)value_out_bf16);
     return trl_check(cudaGetLastError());
+}
+
+extern "C" int trl_alphasame_heads(const void* feats_bf16, const void* extras_bf16, int n_leaves, const float* weights,
+                                   int use_tanh, void* x_out_bf16, void* value_out_bf16, void* stream) {
+    return launch_heads(feats_bf16, nullptr, nullptr, extras_bf16, n_leaves, weights, use_tanh, x_out_bf16, value_out_bf16, stream);
+}
+
+extern "C" int trl_alphasame_heads_indexed(const void* cache_bf16, const int32_t* own_row, const int32_t* opp_row,
+                                           const void* extras_bf16, int n_leaves, const float* weights, int use_tanh,
+                                           void* x_out_bf16, void* value_out_bf16, void* stream) {
+    if (!own_row || !opp_row) return TRL_E_ARG;
+    return launch_heads(cache_bf16, own_row, opp_row, extras_bf16, n_leaves, weights, use_tanh, x_out_bf16, value_out_bf16, stream);
 }

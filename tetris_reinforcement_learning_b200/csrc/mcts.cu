@@ -25,7 +25,7 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 
 static_assert(sizeof(TrlSearchCtl) == 80, "TrlSearchCtl layout");
 static_assert(sizeof(TrlSearchParams) == 152, "TrlSearchParams layout");
-static_assert(sizeof(TrlSearchBuffers) == 200, "TrlSearchBuffers layout");
+static_assert(sizeof(TrlSearchBuffers) == 208, "TrlSearchBuffers layout");
 static_assert(sizeof(TrlGameEnd) == 32, "TrlGameEnd layout");
 static_assert(sizeof(TrlSample) == 20 + 400 + 3 * 2 * TRL_SAMPLE_MOVES, "TrlSample layout");
 
@@ -105,7 +105,7 @@ search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
     if (g >= B.n_games) return;
     TrlSearchCtl* ctl = &B.ctl[g];
     if (!ctl->active) {
-        if (lane == 0) { B.leaf_state[g] = -1; ctl->leaf_kind = 3; }
+        if (lane == 0) { B.leaf_state[g] = -1; ctl->leaf_kind = 3; if (B.leaf_parent) B.leaf_parent[g] = -1; }
         return;
     }
     const size_t nb = (size_t)g * B.node_cap, sb = (size_t)g * B.state_cap;
@@ -171,8 +171,10 @@ search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
 
     // ---- materialise the leaf (ai.py:398-403) ----
     int s = B.slot[nb + node];
+    int parent_state = -1;
     if (node != 0) {
         const int ps = B.slot[nb + B.parent[nb + node]];
+        parent_state = (int)(sb + ps);
         if (s < 0) s = ctl->n_states;  // first visit: new state slot (uniform across lanes)
         copy_game(sg, reinterpret_cast<const uint32_t*>(&B.states[sb + ps]), lane);
         __syncwarp();
@@ -206,6 +208,7 @@ search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
         ctl->leaf = node; ctl->leaf_kind = kind; ctl->leaf_value = lv;
         if (depth > ctl->max_depth) ctl->max_depth = depth;
         B.leaf_state[g] = (kind == 2) ? -1 : (int)(sb + s);
+        if (B.leaf_parent) B.leaf_parent[g] = (kind == 2) ? -1 : parent_state;
     }
 }
 

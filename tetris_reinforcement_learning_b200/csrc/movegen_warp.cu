@@ -9,7 +9,8 @@
 //   * a call (board, current piece, hold-or-next piece) is two warps, one per piece type; a block
 //     of 8 warps owns 4 calls.  All search state lives in shared memory:
 //       vv[rot][row]  low 16 bits = validity row, high 16 bits = visited row     (4 x 46 words)
-//       fu[rot][row]  low 16 bits = flagged,      high 16 bits = used-last-kick  (T only)
+//       fu[rot][row]  T: low 16 bits = flagged, high 16 bits = used-last-kick; other pieces: low 16
+//                     bits = "already queued" (de-duplicates queue entries; order is irrelevant for them)
 //       fifo[1024]    the exploration queue, entries (mx, my, rot, roc, ulk) as in movegen.cu
 //   * the queue is consumed 32 entries at a time: every lane tests one entry (stuck? visited?),
 //     a ballot finds the first entry that starts a flood fill, the entries before it only
@@ -196,10 +197,20 @@ __device__ void search_piece_warp(PieceState& S, const uint16_t* rows, int type,
                     const uint32_t tv = kx >= 0 ? ((tw & 0xFFFFu) >> kx) : ((tw & 0xFFFFu) << -kx);
                     const uint32_t cand = rem & tv & 0x3FFFu;       // first valid kick of these sources
                     rem &= ~cand;
+                    if (!__any_sync(0xffffffffu, rem | cand)) break; // every edge cell of the batch has found its kick
                     if (ty < 2 || !cand) continue;                   // origin y < 0: direction abandoned (:463-464)
                     const uint32_t tvis = kx >= 0 ? ((tw >> 16) >> kx) : ((tw >> 16) << -kx);
                     const uint32_t tfree = kx >= 0 ? ((tn & 0xFFFFu) >> kx) : ((tn & 0xFFFFu) << -kx);
-                    const uint32_t pu = cand & ~tvis, im = cand & tvis & ~tfree;
+                    uint32_t pu = cand & ~tvis;
+                    const uint32_t im = cand & tvis & ~tfree;
+                    if (!is_T) {
+                        // Only T depends on the order and multiplicity of queue entries (its flagged
+                        // emissions).  For the other pieces a target that is already queued need not be
+                        // queued again: fu's low half doubles as the "pending" plane.
+                        const uint32_t pend = in ? S.fu[nrot][ty] : 0u;
+                        pu &= ~(kx >= 0 ? ((pend & 0xFFFFu) >> kx) : ((pend & 0xFFFFu) << -kx));
+                        if (pu) atomicOr(&S.fu[nrot][ty], kx >= 0 ? (pu << kx) : (pu >> -kx));
+                    }
                     Pu[kd] |= pu;
                     Im[kd] |= im;
                     const uint32_t s = pu | im;
@@ -365,10 +376,10 @@ movegen_warp_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restri
     if (i < n && !C.skip) {
         const int c = C.cur, a = C.alt;
         uint32_t st = 0;
-        const int tab = 0;
-        (void)tab;
-        if (which == 0 && c != TRL_NONE) search_piece_warp(ps[warp], C.rows, c, false, C.mask, st, &s_kpack[c == P_I ? 1 : 0]);
-        if (which == 1 && a != TRL_NONE && a != c) search_piece_warp(ps[warp], C.rows, a, true, C.mask, st, &s_kpack[a == P_I ? 1 : 0]);
+        // warp 0 of the call: the current piece; warp 1: the hold-or-next piece (de-duplicated, :103-105)
+        const int type = which ? a : c;
+        if (type != TRL_NONE && !(which && a == c))
+            search_piece_warp(ps[warp], C.rows, type, which != 0, C.mask, st, &s_kpack[type == P_I ? 1 : 0]);
         st = __reduce_or_sync(0xffffffffu, st);
         if (st && lane == 0) atomicOr(&C.status, st);
     }

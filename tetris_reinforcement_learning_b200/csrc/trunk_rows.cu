@@ -188,6 +188,8 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
                             const uint4* __restrict__ stem_w,     // [5][2][20][8][8] bf16
                             __nv_bfloat16* __restrict__ out,      // [n_images][400]
                             int* __restrict__ next_group,         // work counter (zeroed before launch)
+                            const int* __restrict__ n_images_dev, // optional: device-side image count (<= n_images)
+                            const int* __restrict__ out_row,      // optional: output row of image k (default k)
                             long long* __restrict__ trace) {      // optional [pseudo-layer][column][4] clock stamps (CTA 0, first group)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_tmem_base;
@@ -201,6 +203,7 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
     const uint32_t bar_i = smem_u32(smem + kOffBar);   // I   : board cells of the group staged
     const uint32_t bar_m = bar_i + 8;                  // M[c]: MMAs of input column c complete
     const uint32_t bar_o = bar_m + 80;                 // O[p]: operand columns 2p, 2p+1 written
+    if (n_images_dev) n_images = min(n_images, *n_images_dev);
     const int n_groups = (n_images + kImgs - 1) / kImgs;
 
     // ---- one-time setup ----
@@ -295,6 +298,7 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
         } else {
             // ============ input staging, epilogues ============
             const bool inside = (sy < 40 && sj < kImgs && g * kImgs + sj < n_images);
+            const int orow = !inside ? 0 : (out_row ? out_row[g * kImgs + sj] : g * kImgs + sj);
             if (set == 0) {
                 // board cells of this slot's row as one K=16 operand row: k = x + 2 (zero halo columns)
                 uint32_t cells[8];
@@ -361,7 +365,7 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
                         float acc = 0.f;
 #pragma unroll
                         for (int c = 0; c < 16; ++c) acc = fmaf(fc[32 + c], fmaxf(fmaf(ka[c], d[c], kb[c]), 0.f), acc);
-                        out[(size_t)(g * kImgs + sj) * 400 + sy * 10 + x] = __float2bfloat16(fmaxf(fmaf(fc[48], acc, fc[49]), 0.f));
+                        out[(size_t)orow * 400 + sy * 10 + x] = __float2bfloat16(fmaxf(fmaf(fc[48], acc, fc[49]), 0.f));
                     }
                     if (tr && h == 0) trace[(pl * 10 + 2 * set) * 4 + 2] = clock64();
                 }
@@ -422,6 +426,31 @@ extern "C" int trl_alphasame_trunk_rows(const void* grids_bf16, int n_images, in
     if (rc) return rc;
     alphasame_trunk_rows_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)grids_bf16, n_images, n_blocks, (const uint4*)w_packed, consts, (const uint4*)stem_w,
-        (__nv_bfloat16*)out_bf16, counter, g_trace);
+        (__nv_bfloat16*)out_bf16, counter, nullptr, nullptr, g_trace);
+    return trl_check(cudaGetLastError());
+}
+
+extern "C" int trl_alphasame_trunk_rows_indexed(const void* images_bf16, const int32_t* n_images_dev, int max_images,
+                                                const int32_t* out_row, int n_blocks, const void* w_packed,
+                                                const float* consts, const void* stem_w, void* out_bf16, void* stream) {
+    if (max_images < 0 || n_blocks < 1 || n_blocks > kMaxBlocks || !images_bf16 || !n_images_dev || !out_row || !w_packed ||
+        !consts || !stem_w || !out_bf16)
+        return TRL_E_ARG;
+    if (max_images == 0) return TRL_OK;
+    const int smem = smem_bytes(n_blocks);
+    int rc = trl_check(cudaFuncSetAttribute(alphasame_trunk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (rc) return rc;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_groups = (max_images + kImgs - 1) / kImgs;
+    const int grid = sms < n_groups ? sms : n_groups;
+    int* counter = (int*)trl_workspace(TRL_WS_TRUNK_COUNTER, 256);
+    if (!counter) return TRL_E_NOMEM;
+    rc = trl_check(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
+    if (rc) return rc;
+    alphasame_trunk_rows_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)images_bf16, max_images, n_blocks, (const uint4*)w_packed, consts, (const uint4*)stem_w,
+        (__nv_bfloat16*)out_bf16, counter, n_images_dev, out_row, g_trace);
     return trl_check(cudaGetLastError());
 }

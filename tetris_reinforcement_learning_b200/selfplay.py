@@ -92,7 +92,7 @@ class SelfPlayEngine:
 
     def __init__(self, config, evaluator, n_games, device="cuda:0", seed=0, first_game_id=0, game_id_stride=1,
                  feature_dtype=torch.float32, node_cap=None, sample_cap=None, restart_finished=True, save_all=None,
-                 max_rounds=None, use_cuda_graph=True, overlap_movegen=True):
+                 max_rounds=None, use_cuda_graph=True, overlap_movegen=True, reuse_trunk_features=True):
         if config.ruleset != "s2":
             raise NotImplementedError("only ruleset 's2' is implemented on the device path")
         if config.move_algorithm != "convolutional":
@@ -106,6 +106,8 @@ class SelfPlayEngine:
         self.feature_dtype = feature_dtype
         self.use_cuda_graph = use_cuda_graph
         self.overlap_movegen = overlap_movegen
+        # exact trunk-feature reuse (trunk.CachedTrunkEvaluator) when the evaluator offers it
+        self.cached_eval = getattr(evaluator, "cached", None) if (reuse_trunk_features and feature_dtype == torch.bfloat16) else None
         iters_max = max(self.params.max_iter, self.params.iters_long if (config.training and config.use_playout_cap_randomization) else 0)
         self.state_cap = iters_max + 2
         self.node_cap = int(node_cap) if node_cap else max(1024, iters_max * 96)
@@ -124,7 +126,7 @@ class SelfPlayEngine:
             "leaf_state": z(G, torch.int32), "legal": z(G * self.moves_cap, torch.int16), "n_legal": z(G, torch.int16),
             "samples": z(self.sample_cap * SAMPLE_DTYPE.itemsize, torch.uint8), "sample_count": z(1, torch.int32),
             "ends": z(self.end_cap * GAME_END_DTYPE.itemsize, torch.uint8), "end_count": z(1, torch.int32),
-            "next_game_id": z(1, torch.int32),
+            "next_game_id": z(1, torch.int32), "leaf_parent": z(G, torch.int32),
         }
         fdt = feature_dtype
         self.grids = torch.zeros((2 * G, 1, 40, 10), dtype=fdt, device=dev)
@@ -136,6 +138,7 @@ class SelfPlayEngine:
         for name, ten in self.t.items():
             setattr(b, name, ten.data_ptr())
         b.noise_override = None
+        b.leaf_parent = self.t["leaf_parent"].data_ptr()
         self.buf = b
         assert self.lib.trl_sizeof_search_ctl() == CTL_DTYPE.itemsize and self.lib.trl_sizeof_sample() == SAMPLE_DTYPE.itemsize
         self._graph = None
@@ -191,11 +194,15 @@ class SelfPlayEngine:
             _native.check(lib.trl_search_movegen(bp, self._side.cuda_stream), "trl_search_movegen")
         else:
             _native.check(lib.trl_search_movegen(bp, st), "trl_search_movegen")
-        dt = 0 if self.feature_dtype == torch.float32 else 1
-        _native.check(lib.trl_encode_features(self.t["states"].data_ptr(), self.t["leaf_state"].data_ptr(), self.G,
-                                              self.grids.data_ptr(), self.extras.data_ptr(), dt, st), "trl_encode_features")
-        with torch.no_grad():
-            values, logits = self.evaluator(self.grids, self.extras)
+        if self.cached_eval is not None:
+            with torch.no_grad():
+                values, logits = self.cached_eval(self.t["states"], self.t["leaf_state"], self.t["leaf_parent"], self.extras)
+        else:
+            dt = 0 if self.feature_dtype == torch.float32 else 1
+            _native.check(lib.trl_encode_features(self.t["states"].data_ptr(), self.t["leaf_state"].data_ptr(), self.G,
+                                                  self.grids.data_ptr(), self.extras.data_ptr(), dt, st), "trl_encode_features")
+            with torch.no_grad():
+                values, logits = self.evaluator(self.grids, self.extras)
         values = values.reshape(-1)
         if values.dtype != logits.dtype:
             values = values.to(logits.dtype)

@@ -168,4 +168,53 @@ def make_fused_evaluator(net, dtype=torch.bfloat16, layout=None, fused_heads=Tru
             return value, torch.nn.functional.linear(x, w_pol, b_pol)
 
     evaluate.packed = packed
+    if fused_heads and packed["layout"] == "rows":
+        evaluate.cached = CachedTrunkEvaluator(packed, w_heads, use_tanh, w_pol, b_pol, k_pad)
     return evaluate
+
+
+class CachedTrunkEvaluator:
+    """Network evaluation for SelfPlayEngine with exact trunk-feature reuse (include/trl.h,
+    trl_encode_features_cached): per simulation only the board that the last move changed goes
+    through the trunk; the features of the other board are the parent state's.  Outputs are
+    bit-identical to the plain fused evaluator (same kernels, same per-image arithmetic)."""
+
+    def __init__(self, packed, w_heads, use_tanh, w_pol, b_pol, k_pad):
+        self.packed, self.w_heads, self.use_tanh = packed, w_heads, use_tanh
+        self.w_pol, self.b_pol, self.k_pad = w_pol, b_pol, k_pad
+        self.buffers = {}
+
+    def _bufs(self, n_states, n_leaves, device):
+        key = (n_states, n_leaves, str(device))
+        if key not in self.buffers:
+            z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)  # noqa: E731
+            self.buffers = {key: {
+                "cache": z((n_states * 2, 400), torch.bfloat16), "images": z((2 * n_leaves, 400), torch.bfloat16),
+                "dest": z(2 * n_leaves, torch.int32), "count": z(1, torch.int32),
+                "own": z(n_leaves, torch.int32), "opp": z(n_leaves, torch.int32),
+                "x": z((n_leaves, self.k_pad), torch.bfloat16), "value": z(n_leaves, torch.bfloat16)}}
+        return self.buffers[key]
+
+    def __call__(self, states, leaf_state, leaf_parent, extras):
+        """states uint8 [n_states*400], leaf_state / leaf_parent int32 [G], extras bf16 [G,105] (written here)
+        -> (values bf16 [G], logits bf16 [G, 11584])."""
+        lib = _native.lib()
+        dev = extras.device
+        G = leaf_state.numel()
+        b = self._bufs(states.numel() // 400, G, dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        b["count"].zero_()
+        _native.check(lib.trl_encode_features_cached(
+            states.data_ptr(), leaf_state.data_ptr(), leaf_parent.data_ptr(), G, b["cache"].data_ptr(),
+            b["images"].data_ptr(), b["dest"].data_ptr(), b["count"].data_ptr(), extras.data_ptr(),
+            b["own"].data_ptr(), b["opp"].data_ptr(), st), "trl_encode_features_cached")
+        p = self.packed
+        _native.check(lib.trl_alphasame_trunk_rows_indexed(
+            b["images"].data_ptr(), b["count"].data_ptr(), 2 * G, b["dest"].data_ptr(), p["n_blocks"],
+            p["w_packed"].data_ptr(), p["consts"].data_ptr(), p["stem_w"].data_ptr(), b["cache"].data_ptr(), st),
+            "trl_alphasame_trunk_rows_indexed")
+        _native.check(lib.trl_alphasame_heads_indexed(
+            b["cache"].data_ptr(), b["own"].data_ptr(), b["opp"].data_ptr(), extras.data_ptr(), G,
+            self.w_heads.data_ptr(), self.use_tanh, b["x"].data_ptr(), b["value"].data_ptr(), st),
+            "trl_alphasame_heads_indexed")
+        return b["value"], torch.nn.functional.linear(b["x"], self.w_pol, self.b_pol)
