@@ -135,21 +135,35 @@ def run_selfplay(args, rank, world, local_rank):
         return SelfPlayEngine(cfg, ev, n_games, device=dev, seed=20261018, first_game_id=sh["first_game_id"],
                               game_id_stride=sh["game_id_stride"], feature_dtype=torch.bfloat16, **kw)
 
+    def timed(eng):
+        eng.step(12)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.step(args.selfplay_steps)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return e0.elapsed_time(e1)
+
     eng = engine(160)
-    eng.step(12)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    eng.step(args.selfplay_steps)
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
+    reuse = eng.cached_eval is not None
+    ms = timed(eng)
     samples, _ = eng.drain()
     ctl = eng.get_ctl()
+    launches_per_step = 8 if reuse else 7   # select, movegen, (count reset,) encode, trunk, heads, policy GEMM, expand
+    ms_both = None
+    if reuse and not args.no_game_length:
+        # the same step with BOTH boards of every leaf through the trunk (the reference's amount of work)
+        del eng
+        torch.cuda.empty_cache()
+        eng2 = engine(160, reuse_trunk_features=False)
+        ms_both = timed(eng2)
+        del eng2
+        torch.cuda.empty_cache()
     # mean game length in plies, from complete games of a short-search run with the same net
     n_fast = min(G, 256)
     fast = engine(8, n_games=n_fast, max_rounds=1000, restart_finished=False)
@@ -161,25 +175,35 @@ def run_selfplay(args, rank, world, local_rank):
         if len(plies) >= n_fast:
             break
     mean_plies = float(np.mean(plies)) if plies else float("nan")
-    stats = torch.tensor([ms, float(G * args.selfplay_steps), float(len(samples))], dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms, float(G * args.selfplay_steps), float(len(samples)), ms_both or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms, sims, nsamples = float(mx[0]), float(sm[1]), float(sm[2])
+        ms, sims, nsamples, ms_both = float(mx[0]), float(sm[1]), float(sm[2]), (float(mx[3]) or None)
     else:
         sims, nsamples = float(stats[1]), float(stats[2])
     sims_per_s = sims / (ms * 1e-3)
     flops_per_eval = 86.5e6  # AlphaSame(10,16), both grids
+    flops_done = (86.5e6 - 37.2e6) if reuse else 86.5e6   # with reuse one board per leaf goes through the trunk
     return {
+        "_launches": launches_per_step * args.selfplay_steps,
         "mcts_sims_per_sec": {
             "value": sims_per_s, "unit": "sims/s", "games_per_gpu": G, "n_gpus": world, "steps": args.selfplay_steps,
             "ms_per_step": ms / args.selfplay_steps, "max_iter": 160, "net": "AlphaSame(blocks=10, filters=16) bf16, " + ("PyTorch/cuDNN" if args.net_path == "pytorch" else
-                                                               "fused tcgen05 trunk + PyTorch heads") + ", CUDA graph",
+                                                               "row-Toeplitz tcgen05 trunk + fused heads kernel + cuBLAS policy GEMM") + ", CUDA graph",
+            "trunk_feature_reuse": reuse,
+            "trunk_feature_reuse_note": "exact: a move changes only the mover's board, so per simulation one board goes through the "
+                                        "trunk and the other board's features are the parent state's (bit-identical searches, "
+                                        "tests/test_gpu_trunk.py::test_trunk_feature_reuse_is_exact)",
+            "value_both_boards_through_trunk": (sims / (ms_both * 1e-3)) if ms_both else None,
+            "ms_per_step_both_boards": (ms_both / args.selfplay_steps) if ms_both else None,
             "searches_finished": nsamples, "status_nonzero": int((ctl["status"] != 0).sum()),
-            "roofline": {"bound": "tensor", "achieved": sims_per_s / world * flops_per_eval / 1e12,
+            "roofline": {"bound": "tensor", "achieved": sims_per_s / world * flops_done / 1e12,
                          "peak": load_tensor_peak(), "unit": "TFLOP/s",
-                         "frac": sims_per_s / world * flops_per_eval / 1e12 / load_tensor_peak(),
-                         "note": "the step is bound by the policy/value net (one evaluation per simulation)"},
+                         "frac": sims_per_s / world * flops_done / 1e12 / load_tensor_peak(),
+                         "flops_per_simulation_executed": flops_done, "flops_per_simulation_reference": flops_per_eval,
+                         "note": "executed FLOPs (with reuse: one trunk pass + heads per simulation); the trunk is bound by the "
+                                 "128 B/clk shared-memory operand fetch of N=48 MMAs, not by tensor math (DESIGN.md)"},
         },
         "selfplay_games_per_hour": {
             "value": sims_per_s / (160.0 * mean_plies) * 3600.0 if mean_plies == mean_plies else None,
@@ -302,20 +326,41 @@ def run_ours(args, rank, world, local_rank):
     h2d = n * (80 + 2)
     d2h = n * (MASK_WORDS * 4 + 2 + 4)
 
+    # the same call returning the placements as ascending move lists (np.argwhere order, what
+    # get_move_list consumes, ai.py:1016-1024) instead of bit-packed masks: 14x fewer bytes over PCIe
+    LIST_CAP = 256
+    del h_mask
+    h_moves = torch.empty((n, LIST_CAP), dtype=torch.int16).pin_memory()
+    h_n2 = torch.empty(n, dtype=torch.int16).pin_memory()
+
+    def e2e_list_step():
+        rc = L.trl_movegen_host(h_boards.data_ptr(), h_cur.data_ptr(), h_alt.data_ptr(), n, None,
+                                h_moves.data_ptr(), LIST_CAP, h_n2.data_ptr(), h_st.data_ptr())
+        _native.check(rc, "trl_movegen_host")
+
+    e2e_list_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_list_step()
+    torch.cuda.synchronize()
+    e2e_list_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_list_ok = bool(np.array_equal(h_n2.numpy(), d_n.cpu().numpy())) and not bool((h_st.numpy() != 0).any())
+    del h_moves
+
     # free the sweep's buffers before the self-play leg
-    del d_mask, h_mask
+    del d_mask
     torch.cuda.empty_cache()
     also = None
     if not args.no_selfplay:
         also = run_selfplay(args, rank, world, local_rank)
-        also["_launches"] = 0
 
     # ---- reduce over ranks: max time, summed work ----
-    stats = torch.tensor([total_ms, e2e_s, float(placements), float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
+    stats = torch.tensor([total_ms, e2e_s, float(placements), float(np.mean(kernel_ms)), e2e_list_s], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        total_ms, e2e_s, kern_ms = float(mx[0]), float(mx[1]), float(mx[3])
+        total_ms, e2e_s, kern_ms, e2e_list_s = float(mx[0]), float(mx[1]), float(mx[3]), float(mx[4])
         placements_all = float(sm[2])
     else:
         kern_ms, placements_all = float(np.mean(kernel_ms)), float(placements)
@@ -335,12 +380,15 @@ def run_ours(args, rank, world, local_rank):
                    "placements_per_step_per_gpu": placements, "l2": "inputs+outputs (>10 GB/step) exceed the 126 MB L2",
                    "status_nonzero": bad_status},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "movegen_thread_kernel",
+                     "traffic": None, "peak_source": peak_src, "kernel": "movegen_warp_kernel",
                      "algorithmic_bytes_per_call": ALGO_BYTES_PER_CALL, "kernel_ms": kern_ms,
                      "note": "integer-issue bound, not HBM bound (SURVEY §8d): see profiles/ for issue utilisation"},
         "e2e": {"value": placements_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "matches_device_run": e2e_ok,
-                "api": "trl_movegen_host (pinned host buffers, bit-packed masks returned to the host)"},
+                "api": "trl_movegen_host (pinned host buffers, bit-packed (27,39,11) masks returned to the host: PCIe bound)",
+                "as_move_lists": {"value": placements_all / e2e_list_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                                  "d2h_bytes_per_step": n * (LIST_CAP * 2 + 2 + 4), "matches_device_run": e2e_list_ok,
+                                  "api": "same call returning ascending uint16 move lists (np.argwhere order) + counts"}},
         "gpu_launches": args.steps,
         "clocks": clocks,
     }

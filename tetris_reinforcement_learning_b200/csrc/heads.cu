@@ -17,7 +17,7 @@
 namespace {
 
 constexpr int kFeat = 400, kSide = 52, kOpp = 16, kIn = 521, kPad = 528;
-constexpr int kWarpsPerBlock = 8;
+constexpr int kWarpsPerBlock = 16;   // one block per SM: the 59 KB of weights are staged once per block
 // packed weights (fp32): Wo_t[400][16], bo[16], Wv_t[528][16], bv[16], w2[16], b2
 constexpr int kOffWo = 0, kOffBo = kOffWo + kFeat * 16, kOffWv = kOffBo + 16, kOffBv = kOffWv + kPad * 16,
               kOffW2 = kOffBv + 16, kOffB2 = kOffW2 + 16, kWFloats = kOffB2 + 4;
@@ -100,7 +100,7 @@ static int launch_heads(const void* feats_bf16, const int32_t* own_row, const in
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int blocks = (n_leaves + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (blocks > 2 * sms) blocks = 2 * sms;
+    if (blocks > sms) blocks = sms;
     alphasame_heads_kernel<<<blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)feats_bf16, own_row, opp_row, (const __nv_bfloat16*)extras_bf16, n_leaves, weights, use_tanh,
         (__nv_bfloat16*)x_out_bf16, (__nv_bfloat16*)value_out_bf16);

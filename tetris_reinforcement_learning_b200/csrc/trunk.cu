@@ -312,7 +312,7 @@ extern "C" int trl_alphasame_trunk(const void* grids_bf16, int n_images, int n_b
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = sms * kCtasPerSm;  // resident CTAs per SM (TMEM / register bound), persistent over images
     if (grid > n_images) grid = n_images;
-    int* counter = (int*)trl_workspace(TRL_WS_TRUNK_COUNTER, 256);
+    int* counter = (int*)trl_workspace(TRL_WS_TRUNK_COUNTER_TAPS, 256);
     if (!counter) return TRL_E_NOMEM;
     int rc = trl_check(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
     if (rc) return rc;

@@ -398,6 +398,17 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
 
 extern "C" int trl_alphasame_trunk_rows_max_blocks(void) { return kMaxBlocks; }
 
+// Work counter of one launch.  Launches on different streams (two engines pipelined against each
+// other) must not share a counter, so every launch takes the next of 64 slots.
+static int* next_counter() {
+    static int slot = 0;
+    int* base = (int*)trl_workspace(TRL_WS_TRUNK_COUNTER, 64 * 64);
+    if (!base) return nullptr;
+    int* c = base + 16 * slot;
+    slot = (slot + 1) & 63;
+    return c;
+}
+
 // Profiling aid (tools/trunk_trace.py): device buffer of 2*n_blocks*10*4 int64 clock stamps written
 // by CTA 0 for its first group; nullptr (default) disables tracing.
 static long long* g_trace = nullptr;
@@ -420,7 +431,7 @@ extern "C" int trl_alphasame_trunk_rows(const void* grids_bf16, int n_images, in
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_groups = (n_images + kImgs - 1) / kImgs;
     int grid = sms < n_groups ? sms : n_groups;   // one persistent CTA per SM (it owns all 512 TMEM columns)
-    int* counter = (int*)trl_workspace(TRL_WS_TRUNK_COUNTER, 256);
+    int* counter = next_counter();
     if (!counter) return TRL_E_NOMEM;
     int rc = trl_check(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
     if (rc) return rc;
@@ -445,7 +456,7 @@ extern "C" int trl_alphasame_trunk_rows_indexed(const void* images_bf16, const i
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_groups = (max_images + kImgs - 1) / kImgs;
     const int grid = sms < n_groups ? sms : n_groups;
-    int* counter = (int*)trl_workspace(TRL_WS_TRUNK_COUNTER, 256);
+    int* counter = next_counter();
     if (!counter) return TRL_E_NOMEM;
     rc = trl_check(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
     if (rc) return rc;

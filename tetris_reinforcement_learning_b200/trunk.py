@@ -184,15 +184,15 @@ class CachedTrunkEvaluator:
         self.w_pol, self.b_pol, self.k_pad = w_pol, b_pol, k_pad
         self.buffers = {}
 
-    def _bufs(self, n_states, n_leaves, device):
-        key = (n_states, n_leaves, str(device))
+    def _bufs(self, states_ptr, n_states, n_leaves, device):
+        key = (states_ptr, n_states, n_leaves, str(device))   # one cache per engine (per states array)
         if key not in self.buffers:
             z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)  # noqa: E731
-            self.buffers = {key: {
+            self.buffers[key] = ({
                 "cache": z((n_states * 2, 400), torch.bfloat16), "images": z((2 * n_leaves, 400), torch.bfloat16),
                 "dest": z(2 * n_leaves, torch.int32), "count": z(1, torch.int32),
                 "own": z(n_leaves, torch.int32), "opp": z(n_leaves, torch.int32),
-                "x": z((n_leaves, self.k_pad), torch.bfloat16), "value": z(n_leaves, torch.bfloat16)}}
+                "x": z((n_leaves, self.k_pad), torch.bfloat16), "value": z(n_leaves, torch.bfloat16)})
         return self.buffers[key]
 
     def __call__(self, states, leaf_state, leaf_parent, extras):
@@ -201,7 +201,7 @@ class CachedTrunkEvaluator:
         lib = _native.lib()
         dev = extras.device
         G = leaf_state.numel()
-        b = self._bufs(states.numel() // 400, G, dev)
+        b = self._bufs(states.data_ptr(), states.numel() // 400, G, dev)
         st = torch.cuda.current_stream(dev).cuda_stream
         b["count"].zero_()
         _native.check(lib.trl_encode_features_cached(
