@@ -11,7 +11,7 @@
 //       vv[rot][row]  low 16 bits = validity row, high 16 bits = visited row     (4 x 46 words)
 //       fu[rot][row]  T: low 16 bits = flagged, high 16 bits = used-last-kick; other pieces: low 16
 //                     bits = "already queued" (de-duplicates queue entries; order is irrelevant for them)
-//       fifo[1024]    the exploration queue, entries (mx, my, rot, roc, ulk) as in movegen.cu
+//       fifo[768]     the exploration queue (ring), entries (mx, my, rot, roc, ulk) as in movegen.cu
 //   * the queue is consumed 32 entries at a time: every lane tests one entry (stuck? visited?),
 //     a ballot finds the first entry that starts a flood fill, the entries before it only
 //     produce their "arrived by a kick and stuck" emission (move_generation.py:384-394);
@@ -35,7 +35,8 @@
 
 namespace {
 
-constexpr int kFifoCap = 1024;            // live entries; adversarial cave boards peak < 500
+constexpr int kFifoCap = 768;             // live entries; adversarial cave boards peak < 500.
+                                          // 768 keeps a block at 30 KB of shared memory: 7 blocks = 56 warps per SM
 constexpr int kCallsPerBlock = 4;
 constexpr int kWarps = 2 * kCallsPerBlock;
 constexpr int kVRows = TRL_MAP_H + 2;     // rows 44, 45 stay 0: "below the map" is never valid
@@ -120,7 +121,7 @@ __device__ void search_piece_warp(PieceState& S, const uint16_t* rows, int type,
     while (head != tail) {
         // ---- consume up to 32 queue entries: (A) emissions, find the first entry that fills ----
         const int n = min(32u, tail - head);
-        const uint32_t e = (lane < n) ? S.fifo[(head + lane) & (kFifoCap - 1)] : 0u;
+        const uint32_t e = (lane < n) ? S.fifo[(head + lane) % kFifoCap] : 0u;
         const int mx = e & 15, my = (e >> 4) & 63, rot = (e >> 10) & 3;
         const uint32_t bit = 1u << mx;
         const uint32_t w = S.vv[rot][my];
@@ -251,7 +252,7 @@ __device__ void search_piece_warp(PieceState& S, const uint16_t* rows, int type,
                             if (room) {
                                 const int kx = (int)(((*kpack)[frot][kd][0] >> (4 * ki)) & 15u) - 2;
                                 const int ky = (int)(((*kpack)[frot][kd][1] >> (4 * ki)) & 15u) - 2;
-                                S.fifo[off & (kFifoCap - 1)] = (uint16_t)fifo_pack(ex + kx, ky_row - ky, (frot + kd + 1) & 3, 1, nulk);
+                                S.fifo[off % kFifoCap] = (uint16_t)fifo_pack(ex + kx, ky_row - ky, (frot + kd + 1) & 3, 1, nulk);
                                 ++off;
                             }
                         } else if (nulk) has_t = true;

@@ -56,15 +56,16 @@ constexpr int kStemWBytes = 5 * kStemWDyBytes;   // 25600
 constexpr int kWDyBytes = 48 * 16 * 2;           // 1536: B matrix of one vertical tap
 constexpr int kWLayerBytes = 3 * kWDyBytes;      // 4608
 constexpr int kTmemCols = 512;
-constexpr int kColX = 0, kColD = 160;
-constexpr int kMaxBlocks = 16;                   // resident weights: 32 x 4608 B
+constexpr int kColX = 0, kColD = 320;            // X of lane 0 / lane 1 at columns 0 / 160, shared D1 at 320
+constexpr int kMaxBlocks = 16;                   // resident weights: 32 x 4608 B (one lane); two lanes up to 11 blocks
+constexpr int kBarsPerLane = 16;                 // I, M[10], O[5]
+constexpr int kSmemLimit = 232448 - 1024;
 
-constexpr int kOffStemIn = kActBytes;
-constexpr int kOffStemW = kOffStemIn + kStemInBytes;
-constexpr int kOffBar = kOffStemW + kStemWBytes;          // I, M[10], O[5]
-constexpr int kOffConst = kOffBar + 22 * 8;
-__host__ __device__ inline int off_w(int n_blocks) { return kOffConst + ((n_blocks * 48 + 50 + 3) / 4) * 16; }
-__host__ __device__ inline int smem_bytes(int n_blocks) { return off_w(n_blocks) + 2 * n_blocks * kWLayerBytes; }
+// shared-memory bytes for n_lanes image groups in flight
+__host__ __device__ inline int smem_bytes(int n_blocks, int n_lanes) {
+    return n_lanes * (kActBytes + kStemInBytes) + kStemWBytes + 2 * kBarsPerLane * 8 +
+           ((n_blocks * 48 + 50 + 3) / 4) * 16 + 2 * n_blocks * kWLayerBytes;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -182,7 +183,7 @@ __device__ __forceinline__ void load16(const float* p, float (&r)[16]) {
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_images, int n_blocks,
+alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_images, int n_blocks, int n_lanes,
                             const uint4* __restrict__ w_packed,   // [2*n_blocks][3][2][6][8][8] bf16
                             const float* __restrict__ consts,     // [n_blocks*48 + 50]
                             const uint4* __restrict__ stem_w,     // [5][2][20][8][8] bf16
@@ -190,32 +191,36 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
                             int* __restrict__ next_group,         // work counter (zeroed before launch)
                             const int* __restrict__ n_images_dev, // optional: device-side image count (<= n_images)
                             const int* __restrict__ out_row,      // optional: output row of image k (default k)
-                            long long* __restrict__ trace) {      // optional [pseudo-layer][column][4] clock stamps (CTA 0, first group)
+                            long long* __restrict__ trace) {      // optional [pseudo-layer][column][4] clock stamps (CTA 0, first group, lane 0)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_group;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
     const int n_layers = 2 * n_blocks;
-    uint8_t* act = smem;
-    uint8_t* stem_in = smem + kOffStemIn;
-    float* s_const = reinterpret_cast<float*>(smem + kOffConst);
-    const uint32_t bar_i = smem_u32(smem + kOffBar);   // I   : board cells of the group staged
-    const uint32_t bar_m = bar_i + 8;                  // M[c]: MMAs of input column c complete
-    const uint32_t bar_o = bar_m + 80;                 // O[p]: operand columns 2p, 2p+1 written
+    // shared memory: per lane [operand buffer | stem input], then stem weights, barriers, constants, weights
+    const int lane_bytes = kActBytes + kStemInBytes;
+    const int off_stem_w = n_lanes * lane_bytes, off_bar = off_stem_w + kStemWBytes, off_const = off_bar + 2 * kBarsPerLane * 8;
+    const int off_w = off_const + ((n_blocks * 48 + 50 + 3) / 4) * 16;
+    float* s_const = reinterpret_cast<float*>(smem + off_const);
+    // per lane: I (cells staged), M[10] (MMAs of input column c complete), O[5] (operand columns 2p, 2p+1 written)
+    const uint32_t bars = smem_u32(smem + off_bar);
     if (n_images_dev) n_images = min(n_images, *n_images_dev);
     const int n_groups = (n_images + kImgs - 1) / kImgs;
 
     // ---- one-time setup ----
-    for (int i = tid; i < (kActBytes + kStemInBytes) / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < kStemWBytes / 16; i += kThreads) reinterpret_cast<uint4*>(smem + kOffStemW)[i] = stem_w[i];
+    for (int i = tid; i < n_lanes * lane_bytes / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < kStemWBytes / 16; i += kThreads) reinterpret_cast<uint4*>(smem + off_stem_w)[i] = stem_w[i];
     for (int i = tid; i < n_layers * (kWLayerBytes / 16); i += kThreads)
-        reinterpret_cast<uint4*>(smem + off_w(n_blocks))[i] = w_packed[i];
+        reinterpret_cast<uint4*>(smem + off_w)[i] = w_packed[i];
     for (int i = tid; i < n_blocks * 48 + 50; i += kThreads) s_const[i] = consts[i];
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" :: "r"(bar_i));
-        for (int c = 0; c < 10; ++c) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_m + 8 * c));
-        for (int c = 0; c < 5; ++c) asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" :: "r"(bar_o + 8 * c));
+        for (int ln = 0; ln < 2; ++ln) {
+            const uint32_t b = bars + ln * kBarsPerLane * 8;
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" :: "r"(b));
+            for (int c = 0; c < 10; ++c) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(b + 8 + 8 * c));
+            for (int c = 0; c < 5; ++c) asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" :: "r"(b + 88 + 8 * c));
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kEpiWarps) {
@@ -241,144 +246,167 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
 
-    uint32_t ph_i = 0, ph = 0;   // running mbarrier parities (every barrier completes once per pseudo-layer)
+    // running mbarrier parities per lane (every barrier of a lane completes once per pseudo-layer of that lane)
+    uint32_t ph_i[2] = {0, 0}, ph[2] = {0, 0};
     int group_iter = 0;
     while (true) {
-        if (tid == 0) s_group = atomicAdd(next_group, 1);
+        if (tid == 0) s_group = atomicAdd(next_group, n_lanes);
         __syncthreads();
-        const int g = s_group;
-        if (g >= n_groups) break;
+        const int g0 = s_group;
+        if (g0 >= n_groups) break;
+        // lane ln works on group g0 + ln; the two lanes alternate layer by layer on the tensor pipe, so the
+        // epilogue of one lane's layer overlaps the MMAs of the other lane's layer
+        const bool act1 = (n_lanes > 1) && (g0 + 1 < n_groups);
         const bool first_group = (group_iter++ == 0);
 
         if (warp == kEpiWarps) {
             // ============ MMA issuer (warp-uniform; elect.sync inside umma / umma_commit) ============
-            const uint64_t ad = umma_desc(smem_u32(act), kPlaneBytes, 128u);
-            const uint64_t bd = umma_desc(smem_u32(smem + off_w(n_blocks)), 768u, 128u);
-            const uint32_t a_lo = (uint32_t)ad, a_hi = (uint32_t)(ad >> 32), b_hi = (uint32_t)(bd >> 32);
+            const uint64_t bd = umma_desc(smem_u32(smem + off_w), 768u, 128u);
+            const uint32_t b_hi = (uint32_t)(bd >> 32);
             uint32_t b_lo = (uint32_t)bd;
-            {   // stem: X = conv5x5(cells) as 5 MMAs M=128 N=160 K=16 (K = 14 board columns incl. halo)
-                const uint64_t sa = umma_desc(smem_u32(stem_in), kPlaneBytes, 128u);
-                const uint64_t sb = umma_desc(smem_u32(smem + kOffStemW), 20u * 128u, 128u);
-                mbar_wait(bar_i, ph_i);
-                ph_i ^= 1u;
+            const uint64_t sb = umma_desc(smem_u32(smem + off_stem_w), 20u * 128u, 128u);
+#pragma unroll
+            for (int ln = 0; ln < 2; ++ln) {
+                if (ln == 1 && !act1) break;
+                // stem: X = conv5x5(cells) as 5 MMAs M=128 N=160 K=16 (K = 14 board columns incl. halo)
+                const uint32_t lb = bars + ln * kBarsPerLane * 8;
+                const uint64_t sa = umma_desc(smem_u32(smem + ln * lane_bytes + kActBytes), kPlaneBytes, 128u);
+                mbar_wait(lb, ph_i[ln]);
+                ph_i[ln] ^= 1u;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (trace && blockIdx.x == 0 && first_group && lane == 0) trace[0] = clock64();
+                if (trace && blockIdx.x == 0 && first_group && lane == 0 && ln == 0) trace[0] = clock64();
 #pragma unroll
                 for (int dy = 0; dy < 5; ++dy)
-                    umma(tmem_base + kColX, (uint32_t)sa + (uint32_t)dy, (uint32_t)(sa >> 32),
+                    umma(tmem_base + (uint32_t)(kColX + 160 * ln), (uint32_t)sa + (uint32_t)dy, (uint32_t)(sa >> 32),
                          (uint32_t)sb + (uint32_t)(dy * (kStemWDyBytes / 16)), (uint32_t)(sb >> 32), idesc(160), dy > 0 ? 1u : 0u);
 #pragma unroll
-                for (int c = 0; c < 10; ++c) umma_commit(bar_m + 8 * c);
+                for (int c = 0; c < 10; ++c) umma_commit(lb + 8 + 8 * c);
             }
             for (int layer = 0; layer < n_layers; ++layer, b_lo += kWLayerBytes / 16) {
-                const uint32_t dst = tmem_base + ((layer & 1) ? kColX : kColD);
+                const bool first_conv = !(layer & 1);
 #pragma unroll
-                for (int c = 0; c < 10; ++c) {
-                    if (!(c & 1)) {
-                        mbar_wait(bar_o + 8 * (c >> 1), ph);
+                for (int ln = 0; ln < 2; ++ln) {
+                    if (ln == 1 && !act1) break;
+                    const uint32_t lb = bars + ln * kBarsPerLane * 8;
+                    const uint64_t ad = umma_desc(smem_u32(smem + ln * lane_bytes), kPlaneBytes, 128u);
+                    const uint32_t a_lo = (uint32_t)ad, a_hi = (uint32_t)(ad >> 32);
+                    const uint32_t dst = tmem_base + (first_conv ? kColD : (uint32_t)(kColX + 160 * ln));
+#pragma unroll
+                    for (int c = 0; c < 10; ++c) {
+                        if (!(c & 1)) mbar_wait(lb + 88 + 8 * (c >> 1), ph[ln]);
+                        // D1 is shared by the lanes: lane 1's first convolution follows lane 0's, so its MMAs on
+                        // columns c-1..c+1 wait until lane 0's epilogue has drained (and re-zeroed) them, i.e. until
+                        // lane 0 has published the operand pair holding column c+1 for ITS next layer
+                        if (first_conv && ln == 1) mbar_wait(bars + 88 + 8 * ((c < 9 ? c + 1 : 9) >> 1), ph[0]);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    }
-                    if (trace && blockIdx.x == 0 && first_group && lane == 0) trace[((layer + 1) * 10 + c) * 4] = clock64();
+                        if (trace && blockIdx.x == 0 && first_group && lane == 0 && ln == 0) trace[((layer + 1) * 10 + c) * 4] = clock64();
 #pragma unroll
-                    for (int dy = 0; dy < 3; ++dy) {
-                        const uint32_t a = a_lo + (uint32_t)(c * (kColBytes / 16) + dy);   // column c, rows shifted by dy
-                        const uint32_t b = b_lo + (uint32_t)(dy * (kWDyBytes / 16));
-                        if (c == 0)        // x_out = 0, 1 (skip the x_out = -1 rows of B)
-                            umma(dst, a, a_hi, b + 16u, b_hi, idesc(32), 1u);
-                        else if (c == 9)   // x_out = 8, 9
-                            umma(dst + 128u, a, a_hi, b, b_hi, idesc(32), 1u);
-                        else
-                            umma(dst + (uint32_t)(16 * (c - 1)), a, a_hi, b, b_hi, idesc(48), 1u);
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const uint32_t a = a_lo + (uint32_t)(c * (kColBytes / 16) + dy);   // column c, rows shifted by dy
+                            const uint32_t b = b_lo + (uint32_t)(dy * (kWDyBytes / 16));
+                            if (c == 0)        // x_out = 0, 1 (skip the x_out = -1 rows of B)
+                                umma(dst, a, a_hi, b + 16u, b_hi, idesc(32), 1u);
+                            else if (c == 9)   // x_out = 8, 9
+                                umma(dst + 128u, a, a_hi, b, b_hi, idesc(32), 1u);
+                            else
+                                umma(dst + (uint32_t)(16 * (c - 1)), a, a_hi, b, b_hi, idesc(48), 1u);
+                        }
+                        umma_commit(lb + 8 + 8 * c);
                     }
-                    umma_commit(bar_m + 8 * c);
+                    ph[ln] ^= 1u;
                 }
-                ph ^= 1u;
             }
             __syncwarp();
         } else {
             // ============ input staging, epilogues ============
-            const bool inside = (sy < 40 && sj < kImgs && g * kImgs + sj < n_images);
-            const int orow = !inside ? 0 : (out_row ? out_row[g * kImgs + sj] : g * kImgs + sj);
-            if (set == 0) {
-                // board cells of this slot's row as one K=16 operand row: k = x + 2 (zero halo columns)
+            bool inside[2];
+#pragma unroll
+            for (int ln = 0; ln < 2; ++ln)
+                inside[ln] = (ln == 0 || act1) && sy < 40 && sj < kImgs && (g0 + ln) * kImgs + sj < n_images;
+            if (set < 2 && (set == 0 || act1)) {
+                // set `ln` stages lane ln: board cells of this slot's row as one K=16 operand row, k = x + 2
+                const int ln = set;
                 uint32_t cells[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) cells[q] = 0u;
-                if (inside) {
-                    const uint32_t* src = reinterpret_cast<const uint32_t*>(grids + ((size_t)(g * kImgs + sj) * 400 + sy * 10));
+                if (inside[ln]) {
+                    const uint32_t* src = reinterpret_cast<const uint32_t*>(grids + ((size_t)((g0 + ln) * kImgs + sj) * 400 + sy * 10));
 #pragma unroll
                     for (int q = 0; q < 5; ++q) cells[q + 1] = src[q];   // 10 bf16 cells = 5 words, k = 2..11
                 }
-                uint8_t* p = stem_in + (slot + 2) * 16;
+                uint8_t* p = smem + ln * lane_bytes + kActBytes + (slot + 2) * 16;
                 *reinterpret_cast<uint4*>(p) = make_uint4(cells[0], cells[1], cells[2], cells[3]);
                 *reinterpret_cast<uint4*>(p + kPlaneBytes) = make_uint4(cells[4], cells[5], cells[6], cells[7]);
-                publish_column(bar_i);
+                publish_column(bars + ln * kBarsPerLane * 8);
             }
 
-            // pseudo-layer 0 = stem, then the 2 * n_blocks convolutions, column by column behind the tensor pipe
+            // pseudo-layer 0 = stem, then the 2 * n_blocks convolutions, column pair by column pair behind the tensor pipe
             for (int pl = 0; pl <= n_layers; ++pl) {
                 const int layer = pl - 1;
                 const bool first_conv = (pl > 0) && !(layer & 1);
                 const bool last = (layer == n_layers - 1);
-                // next operand = relu(ka * acc + kb) per channel, with the halo mask folded into the
-                // constants (halo slots and missing images get ka = kb = 0 -> exact zeros)
-                float ka[16], kb[16];
-                if (first_conv) {
-                    load16(s_const + (layer >> 1) * 48 + 32, kb);              // bn2 bias (scale folded into the weights)
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) ka[c] = 1.f;
-                } else if (!last) {
-                    const float* nb = s_const + (pl == 0 ? 0 : (layer >> 1) + 1) * 48;
-                    load16(nb, ka);                                            // next block's bn1 scale, bias
-                    load16(nb + 16, kb);
-                } else {
-                    const float* fc = s_const + n_blocks * 48;
-                    load16(fc, ka);
-                    load16(fc + 16, kb);
-                }
-                if (!inside) {
+                for (int ln = 0; ln < 2; ++ln) {
+                    if (ln == 1 && !act1) break;
+                    const uint32_t lb = bars + ln * kBarsPerLane * 8;
+                    uint8_t* act = smem + ln * lane_bytes;
+                    // next operand = relu(ka * acc + kb) per channel, with the halo mask folded into the
+                    // constants (halo slots and missing images get ka = kb = 0 -> exact zeros)
+                    float ka[16], kb[16];
+                    if (first_conv) {
+                        load16(s_const + (layer >> 1) * 48 + 32, kb);              // bn2 bias (scale folded into the weights)
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) { ka[c] = 0.f; kb[c] = 0.f; }
-                }
-                // columns 2p-1..2p+2 of this layer are final.  Only the set's first warp polls the mbarrier;
-                // the other three sleep on a hardware barrier.
-                if ((warp & 3) == 0) mbar_wait(bar_m + 8 * (set < 4 ? 2 * set + 2 : 9), ph);
-                asm volatile("bar.sync %0, 128;" :: "r"(1 + set) : "memory");
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const bool tr = trace && blockIdx.x == 0 && first_group && (tid & 127) == 0;
-                if (tr) trace[(pl * 10 + 2 * set) * 4 + 1] = clock64();
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int x = 2 * set + h;
-                    float d[16], v[16];
-                    const uint32_t ta = tmem_lane + (uint32_t)((first_conv ? kColD : kColX) + 16 * x);
-                    tmem_ld16(ta, d);
-                    if (first_conv) tmem_st16_zero(ta);      // D1 is accumulate-only: leave it zeroed
-                    if (!last) {
-                        // first conv: U = relu(conv1'(T) + c2);  else T = relu(bn1_next(X)), X = stem / X + conv2(U)
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) v[c] = fmaf(ka[c], d[c], kb[c]);
-                        store_operand_relu(act, x, slot, v);
-                    } else if (inside) {
-                        // head of the trunk: BN-ReLU, 1x1 conv to one channel, BN-ReLU, flatten
+                        for (int c = 0; c < 16; ++c) ka[c] = 1.f;
+                    } else if (!last) {
+                        const float* nb = s_const + (pl == 0 ? 0 : (layer >> 1) + 1) * 48;
+                        load16(nb, ka);                                            // next block's bn1 scale, bias
+                        load16(nb + 16, kb);
+                    } else {
                         const float* fc = s_const + n_blocks * 48;
-                        float acc = 0.f;
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) acc = fmaf(fc[32 + c], fmaxf(fmaf(ka[c], d[c], kb[c]), 0.f), acc);
-                        out[(size_t)orow * 400 + sy * 10 + x] = __float2bfloat16(fmaxf(fmaf(fc[48], acc, fc[49]), 0.f));
+                        load16(fc, ka);
+                        load16(fc + 16, kb);
                     }
-                    if (tr && h == 0) trace[(pl * 10 + 2 * set) * 4 + 2] = clock64();
+                    if (!inside[ln]) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) { ka[c] = 0.f; kb[c] = 0.f; }
+                    }
+                    // columns 2p-1..2p+2 of this layer are final.  Only the set's first warp polls the mbarrier;
+                    // the other three sleep on a hardware barrier.
+                    if ((warp & 3) == 0) mbar_wait(lb + 8 + 8 * (set < 4 ? 2 * set + 2 : 9), ph[ln]);
+                    asm volatile("bar.sync %0, 128;" :: "r"(1 + set) : "memory");
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const bool tr = trace && blockIdx.x == 0 && first_group && (tid & 127) == 0 && ln == 0;
+                    if (tr) trace[(pl * 10 + 2 * set) * 4 + 1] = clock64();
+                    const int orow = !inside[ln] ? 0 : (out_row ? out_row[(g0 + ln) * kImgs + sj] : (g0 + ln) * kImgs + sj);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int x = 2 * set + h;
+                        float d[16], v[16];
+                        const uint32_t ta = tmem_lane + (uint32_t)((first_conv ? kColD : kColX + 160 * ln) + 16 * x);
+                        tmem_ld16(ta, d);
+                        if (first_conv) tmem_st16_zero(ta);      // D1 is accumulate-only: leave it zeroed
+                        if (!last) {
+                            // first conv: U = relu(conv1'(T) + c2);  else T = relu(bn1_next(X)), X = stem / X + conv2(U)
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) v[c] = fmaf(ka[c], d[c], kb[c]);
+                            store_operand_relu(act, x, slot, v);
+                        } else if (inside[ln]) {
+                            // head of the trunk: BN-ReLU, 1x1 conv to one channel, BN-ReLU, flatten
+                            const float* fc = s_const + n_blocks * 48;
+                            float acc = 0.f;
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) acc = fmaf(fc[32 + c], fmaxf(fmaf(ka[c], d[c], kb[c]), 0.f), acc);
+                            out[(size_t)orow * 400 + sy * 10 + x] = __float2bfloat16(fmaxf(fmaf(fc[48], acc, fc[49]), 0.f));
+                        }
+                        if (tr && h == 0) trace[(pl * 10 + 2 * set) * 4 + 2] = clock64();
+                    }
+                    if (!last) {
+                        if (first_conv) tmem_wait_st();
+                        publish_column(lb + 88 + 8 * set);
+                        if (tr) trace[(pl * 10 + 2 * set) * 4 + 3] = clock64();
+                    }
+                    ph[ln] ^= 1u;
                 }
-                if (!last) {
-                    if (tr) trace[(pl * 10 + 2 * set + 1) * 4 + 1] = clock64();
-                    if (first_conv) tmem_wait_st();
-                    if (tr) trace[(pl * 10 + 2 * set + 1) * 4 + 2] = clock64();
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    if (tr) trace[(pl * 10 + 2 * set + 1) * 4 + 3] = clock64();
-                    publish_column(bar_o + 8 * set);
-                    if (tr) trace[(pl * 10 + 2 * set) * 4 + 3] = clock64();
-                }
-                ph ^= 1u;
             }
             // the next group's stem overwrites X in TMEM: order this group's TMEM reads before it
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -397,6 +425,14 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
 }  // namespace
 
 extern "C" int trl_alphasame_trunk_rows_max_blocks(void) { return kMaxBlocks; }
+
+// Two image groups in flight per CTA when the resident weights leave room for two operand buffers.
+static int g_force_lanes = 0;
+extern "C" void trl_debug_trunk_rows_lanes(int n_lanes) { g_force_lanes = n_lanes; }
+static int lanes_for(int n_blocks) {
+    const int fit = smem_bytes(n_blocks, 2) <= kSmemLimit ? 2 : 1;
+    return (g_force_lanes == 1 || g_force_lanes == 2) ? (g_force_lanes < fit ? g_force_lanes : fit) : fit;
+}
 
 // Work counter of one launch.  Launches on different streams (two engines pipelined against each
 // other) must not share a counter, so every launch takes the next of 64 slots.
@@ -419,24 +455,21 @@ extern "C" int trl_alphasame_trunk_rows(const void* grids_bf16, int n_images, in
     if (n_images < 0 || n_blocks < 1 || n_blocks > kMaxBlocks || !grids_bf16 || !w_packed || !consts || !stem_w || !out_bf16)
         return TRL_E_ARG;
     if (n_images == 0) return TRL_OK;
-    const int smem = smem_bytes(n_blocks);
-    static int configured = 0;
-    if (configured < smem) {
-        int rc = trl_check(cudaFuncSetAttribute(alphasame_trunk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        if (rc) return rc;
-        configured = smem;
-    }
+    const int n_lanes = lanes_for(n_blocks);
+    const int smem = smem_bytes(n_blocks, n_lanes);
+    int rc0 = trl_check(cudaFuncSetAttribute(alphasame_trunk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (rc0) return rc0;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int n_groups = (n_images + kImgs - 1) / kImgs;
-    int grid = sms < n_groups ? sms : n_groups;   // one persistent CTA per SM (it owns all 512 TMEM columns)
+    const int n_units = ((n_images + kImgs - 1) / kImgs + n_lanes - 1) / n_lanes;
+    int grid = sms < n_units ? sms : n_units;   // one persistent CTA per SM (it owns all 512 TMEM columns)
     int* counter = next_counter();
     if (!counter) return TRL_E_NOMEM;
     int rc = trl_check(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
     if (rc) return rc;
     alphasame_trunk_rows_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)grids_bf16, n_images, n_blocks, (const uint4*)w_packed, consts, (const uint4*)stem_w,
+        (const __nv_bfloat16*)grids_bf16, n_images, n_blocks, n_lanes, (const uint4*)w_packed, consts, (const uint4*)stem_w,
         (__nv_bfloat16*)out_bf16, counter, nullptr, nullptr, g_trace);
     return trl_check(cudaGetLastError());
 }
@@ -448,20 +481,21 @@ extern "C" int trl_alphasame_trunk_rows_indexed(const void* images_bf16, const i
         !consts || !stem_w || !out_bf16)
         return TRL_E_ARG;
     if (max_images == 0) return TRL_OK;
-    const int smem = smem_bytes(n_blocks);
+    const int n_lanes = lanes_for(n_blocks);
+    const int smem = smem_bytes(n_blocks, n_lanes);
     int rc = trl_check(cudaFuncSetAttribute(alphasame_trunk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (rc) return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int n_groups = (max_images + kImgs - 1) / kImgs;
-    const int grid = sms < n_groups ? sms : n_groups;
+    const int n_units = ((max_images + kImgs - 1) / kImgs + n_lanes - 1) / n_lanes;
+    const int grid = sms < n_units ? sms : n_units;
     int* counter = next_counter();
     if (!counter) return TRL_E_NOMEM;
     rc = trl_check(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
     if (rc) return rc;
     alphasame_trunk_rows_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)images_bf16, max_images, n_blocks, (const uint4*)w_packed, consts, (const uint4*)stem_w,
+        (const __nv_bfloat16*)images_bf16, max_images, n_blocks, n_lanes, (const uint4*)w_packed, consts, (const uint4*)stem_w,
         (__nv_bfloat16*)out_bf16, counter, n_images_dev, out_row, g_trace);
     return trl_check(cudaGetLastError());
 }

@@ -185,18 +185,29 @@ class SelfPlayEngine:
         lib, st = self.lib, main.cuda_stream
         bp, pp = ctypes.byref(self.buf), ctypes.byref(self.params)
         _native.check(lib.trl_search_select(bp, pp, st), "trl_search_select")
-        # the leaves' legal placements only feed `expand`: enumerate them on a forked stream,
-        # concurrently with feature encoding and the network (joined before expand)
-        if self.overlap_movegen:
+        # the leaves' legal placements only feed `expand`: enumerate them on a forked stream, concurrently
+        # with the network (joined before expand).  overlap_movegen = "trunk": next to feature encoding and
+        # the trunk; "heads": next to the heads kernel and the policy GEMM (the trunk is bound by shared-
+        # memory bandwidth, which the enumeration also lives on); False: serially before the network.
+        def fork_movegen():
             if self._side is None:
                 self._side = torch.cuda.Stream(self.device)
             self._side.wait_stream(main)
             _native.check(lib.trl_search_movegen(bp, self._side.cuda_stream), "trl_search_movegen")
-        else:
+
+        mode = self.overlap_movegen
+        if mode is True:
+            mode = "trunk"
+        if mode == "heads" and self.cached_eval is None:
+            mode = "trunk"
+        if not mode:
             _native.check(lib.trl_search_movegen(bp, st), "trl_search_movegen")
+        elif mode == "trunk":
+            fork_movegen()
         if self.cached_eval is not None:
             with torch.no_grad():
-                values, logits = self.cached_eval(self.t["states"], self.t["leaf_state"], self.t["leaf_parent"], self.extras)
+                values, logits = self.cached_eval(self.t["states"], self.t["leaf_state"], self.t["leaf_parent"], self.extras,
+                                                  after_trunk=fork_movegen if mode == "heads" else None)
         else:
             dt = 0 if self.feature_dtype == torch.float32 else 1
             _native.check(lib.trl_encode_features(self.t["states"].data_ptr(), self.t["leaf_state"].data_ptr(), self.G,

@@ -195,7 +195,7 @@ class CachedTrunkEvaluator:
                 "x": z((n_leaves, self.k_pad), torch.bfloat16), "value": z(n_leaves, torch.bfloat16)})
         return self.buffers[key]
 
-    def __call__(self, states, leaf_state, leaf_parent, extras):
+    def __call__(self, states, leaf_state, leaf_parent, extras, after_trunk=None):
         """states uint8 [n_states*400], leaf_state / leaf_parent int32 [G], extras bf16 [G,105] (written here)
         -> (values bf16 [G], logits bf16 [G, 11584])."""
         lib = _native.lib()
@@ -213,6 +213,8 @@ class CachedTrunkEvaluator:
             b["images"].data_ptr(), b["count"].data_ptr(), 2 * G, b["dest"].data_ptr(), p["n_blocks"],
             p["w_packed"].data_ptr(), p["consts"].data_ptr(), p["stem_w"].data_ptr(), b["cache"].data_ptr(), st),
             "trl_alphasame_trunk_rows_indexed")
+        if after_trunk is not None:
+            after_trunk()
         _native.check(lib.trl_alphasame_heads_indexed(
             b["cache"].data_ptr(), b["own"].data_ptr(), b["opp"].data_ptr(), extras.data_ptr(), G,
             self.w_heads.data_ptr(), self.use_tanh, b["x"].data_ptr(), b["value"].data_ptr(), st),

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--fused", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--overlap", default="trunk")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
@@ -64,7 +65,7 @@ def main():
     print(f"net forward (eager, {args.dtype}, batch {G}): {net_ms:.3f} ms  -> {G / net_ms * 1e3:.3e} evals/s, "
           f"{86.5e6 * G / net_ms / 1e9:.1f} TFLOP/s")
     for graph in (False, True):
-        eng = SelfPlayEngine(cfg, ev, G, seed=1, feature_dtype=dt, use_cuda_graph=graph, overlap_movegen=not args.no_overlap)
+        eng = SelfPlayEngine(cfg, ev, G, seed=1, feature_dtype=dt, use_cuda_graph=graph, overlap_movegen=False if args.no_overlap else args.overlap)
         eng.step(10)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
