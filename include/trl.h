@@ -349,6 +349,8 @@ int trl_alphasame_trunk(const void* grids_bf16, int n_images, int n_blocks, cons
  *          B[(j, oc), ic] = w[oc][ic][dy][2 - j] in K-major core-matrix order [k chunk][n group][n][k].
  * stem_w   [5 dy][2][20][8][8] bf16: the 5x5 stem as 5 MMAs (M=128 N=160 K=16): per kernel row the
  *          160 x 16 matrix B[(x_out, oc), k] = w[oc][dy][k - x_out] (k = input column + 2, else 0).
+ * consts   as above but a HOST pointer: the folded BatchNorm constants are passed to the kernel by
+ *          value (constant bank), so they cost no shared-memory bandwidth.
  * Other arguments as above.  n_blocks <= trl_alphasame_trunk_rows_max_blocks().
  */
 int trl_alphasame_trunk_rows(const void* grids_bf16, int n_images, int n_blocks, const void* w_packed,

@@ -182,10 +182,19 @@ __device__ __forceinline__ void load16(const float* p, float (&r)[16]) {
     }
 }
 
+// Folded BatchNorm constants travel as a by-value kernel parameter: they are warp-uniform, so they
+// come through the constant bank (LDC/ULDC) and cost no shared-memory bandwidth.
+struct TrunkConsts { float v[kMaxBlocks * 48 + 52]; };
+
+__device__ __forceinline__ void load16c(const float* p, float (&r)[16]) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) r[q] = p[q];
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_images, int n_blocks, int n_lanes,
                             const uint4* __restrict__ w_packed,   // [2*n_blocks][3][2][6][8][8] bf16
-                            const float* __restrict__ consts,     // [n_blocks*48 + 50]
+                            const __grid_constant__ TrunkConsts consts,   // [n_blocks*48 + 50]
                             const uint4* __restrict__ stem_w,     // [5][2][20][8][8] bf16
                             __nv_bfloat16* __restrict__ out,      // [n_images][400]
                             int* __restrict__ next_group,         // work counter (zeroed before launch)
@@ -202,7 +211,7 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
     const int lane_bytes = kActBytes + kStemInBytes;
     const int off_stem_w = n_lanes * lane_bytes, off_bar = off_stem_w + kStemWBytes, off_const = off_bar + 2 * kBarsPerLane * 8;
     const int off_w = off_const + ((n_blocks * 48 + 50 + 3) / 4) * 16;
-    float* s_const = reinterpret_cast<float*>(smem + off_const);
+    const float* s_const = consts.v;
     // per lane: I (cells staged), M[10] (MMAs of input column c complete), O[5] (operand columns 2p, 2p+1 written)
     const uint32_t bars = smem_u32(smem + off_bar);
     if (n_images_dev) n_images = min(n_images, *n_images_dev);
@@ -213,7 +222,6 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
     for (int i = tid; i < kStemWBytes / 16; i += kThreads) reinterpret_cast<uint4*>(smem + off_stem_w)[i] = stem_w[i];
     for (int i = tid; i < n_layers * (kWLayerBytes / 16); i += kThreads)
         reinterpret_cast<uint4*>(smem + off_w)[i] = w_packed[i];
-    for (int i = tid; i < n_blocks * 48 + 50; i += kThreads) s_const[i] = consts[i];
     if (tid == 0) {
         for (int ln = 0; ln < 2; ++ln) {
             const uint32_t b = bars + ln * kBarsPerLane * 8;
@@ -354,17 +362,17 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
                     // constants (halo slots and missing images get ka = kb = 0 -> exact zeros)
                     float ka[16], kb[16];
                     if (first_conv) {
-                        load16(s_const + (layer >> 1) * 48 + 32, kb);              // bn2 bias (scale folded into the weights)
+                        load16c(s_const + (layer >> 1) * 48 + 32, kb);             // bn2 bias (scale folded into the weights)
 #pragma unroll
                         for (int c = 0; c < 16; ++c) ka[c] = 1.f;
                     } else if (!last) {
                         const float* nb = s_const + (pl == 0 ? 0 : (layer >> 1) + 1) * 48;
-                        load16(nb, ka);                                            // next block's bn1 scale, bias
-                        load16(nb + 16, kb);
+                        load16c(nb, ka);                                           // next block's bn1 scale, bias
+                        load16c(nb + 16, kb);
                     } else {
                         const float* fc = s_const + n_blocks * 48;
-                        load16(fc, ka);
-                        load16(fc + 16, kb);
+                        load16c(fc, ka);
+                        load16c(fc + 16, kb);
                     }
                     if (!inside[ln]) {
 #pragma unroll
@@ -450,6 +458,12 @@ static int* next_counter() {
 static long long* g_trace = nullptr;
 extern "C" void trl_debug_trunk_rows_trace(void* device_buffer) { g_trace = (long long*)device_buffer; }
 
+static TrunkConsts host_consts(const float* consts_host, int n_blocks) {
+    TrunkConsts c;
+    for (int i = 0; i < kMaxBlocks * 48 + 52; ++i) c.v[i] = (i < n_blocks * 48 + 50) ? consts_host[i] : 0.f;
+    return c;
+}
+
 extern "C" int trl_alphasame_trunk_rows(const void* grids_bf16, int n_images, int n_blocks, const void* w_packed,
                                         const float* consts, const void* stem_w, void* out_bf16, void* stream) {
     if (n_images < 0 || n_blocks < 1 || n_blocks > kMaxBlocks || !grids_bf16 || !w_packed || !consts || !stem_w || !out_bf16)
@@ -469,7 +483,7 @@ extern "C" int trl_alphasame_trunk_rows(const void* grids_bf16, int n_images, in
     int rc = trl_check(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
     if (rc) return rc;
     alphasame_trunk_rows_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)grids_bf16, n_images, n_blocks, n_lanes, (const uint4*)w_packed, consts, (const uint4*)stem_w,
+        (const __nv_bfloat16*)grids_bf16, n_images, n_blocks, n_lanes, (const uint4*)w_packed, host_consts(consts, n_blocks), (const uint4*)stem_w,
         (__nv_bfloat16*)out_bf16, counter, nullptr, nullptr, g_trace);
     return trl_check(cudaGetLastError());
 }
@@ -495,7 +509,7 @@ extern "C" int trl_alphasame_trunk_rows_indexed(const void* images_bf16, const i
     rc = trl_check(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
     if (rc) return rc;
     alphasame_trunk_rows_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)images_bf16, max_images, n_blocks, n_lanes, (const uint4*)w_packed, consts, (const uint4*)stem_w,
+        (const __nv_bfloat16*)images_bf16, max_images, n_blocks, n_lanes, (const uint4*)w_packed, host_consts(consts, n_blocks), (const uint4*)stem_w,
         (__nv_bfloat16*)out_bf16, counter, n_images_dev, out_row, g_trace);
     return trl_check(cudaGetLastError());
 }

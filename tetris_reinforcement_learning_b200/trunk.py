@@ -75,6 +75,7 @@ def pack_alphasame_trunk(net, device=None, layout=None):
     return {"stem_w": stem_w.reshape(-1).to(device=device, dtype=torch.bfloat16).contiguous(),
             "w_packed": torch.stack(convs).reshape(len(convs), -1).to(device=device, dtype=torch.bfloat16).contiguous(),
             "consts": torch.cat([c.reshape(-1) for c in consts]).to(device).contiguous(),
+            "consts_host": torch.cat([c.reshape(-1) for c in consts]).float().cpu().contiguous(),
             "stem_lut": lut.to(device).contiguous(), "n_blocks": len(net.res_blocks), "layout": layout}
 
 
@@ -88,7 +89,8 @@ def trunk_forward(packed, grids, out=None):
     rows = packed.get("layout") == "rows"
     fn = _native.lib().trl_alphasame_trunk_rows if rows else _native.lib().trl_alphasame_trunk
     stem = packed["stem_w"] if rows else packed["stem_lut"]
-    rc = fn(grids.data_ptr(), n, packed["n_blocks"], packed["w_packed"].data_ptr(), packed["consts"].data_ptr(),
+    consts = packed["consts_host"] if rows else packed["consts"]   # rows kernel: by-value kernel parameter
+    rc = fn(grids.data_ptr(), n, packed["n_blocks"], packed["w_packed"].data_ptr(), consts.data_ptr(),
             stem.data_ptr(), out.data_ptr(), torch.cuda.current_stream(grids.device).cuda_stream)
     _native.check(rc, "trl_alphasame_trunk")
     return out
@@ -211,7 +213,7 @@ class CachedTrunkEvaluator:
         p = self.packed
         _native.check(lib.trl_alphasame_trunk_rows_indexed(
             b["images"].data_ptr(), b["count"].data_ptr(), 2 * G, b["dest"].data_ptr(), p["n_blocks"],
-            p["w_packed"].data_ptr(), p["consts"].data_ptr(), p["stem_w"].data_ptr(), b["cache"].data_ptr(), st),
+            p["w_packed"].data_ptr(), p["consts_host"].data_ptr(), p["stem_w"].data_ptr(), b["cache"].data_ptr(), st),
             "trl_alphasame_trunk_rows_indexed")
         if after_trunk is not None:
             after_trunk()
