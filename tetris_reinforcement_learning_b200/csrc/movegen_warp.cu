@@ -37,7 +37,7 @@ namespace {
 
 constexpr int kFifoCap = 768;             // live entries; adversarial cave boards peak < 500.
                                           // 768 keeps a block at 30 KB of shared memory: 7 blocks = 56 warps per SM
-constexpr int kCallsPerBlock = 4;
+constexpr int kCallsPerBlock = 8;   // 16 warps, 60 KB of shared memory, 3 blocks per SM (measured best of 1/2/4/8)
 constexpr int kWarps = 2 * kCallsPerBlock;
 constexpr int kVRows = TRL_MAP_H + 2;     // rows 44, 45 stay 0: "below the map" is never valid
 
@@ -178,6 +178,78 @@ __device__ void search_piece_warp(PieceState& S, const uint16_t* rows, int type,
             if (lane < nrows) {
                 const uint32_t vr = S.vv[frot][ky_row] & 0xFFFFu, nx = S.vv[frot][ky_row + 1] & 0xFFFFu;
                 edges = (myr & ~nx) | (myr & ~(vr << 1)) | (myr & ~(vr >> 1));
+            }
+            // ---- small fills (the common case: caves reached by a kick): lane = (edge cell, direction) ----
+            // The bit-parallel pass below costs ~500 instructions whatever the fill size; with at most 10
+            // edge cells every (cell, direction) pair gets its own lane and walks its kick list serially.
+            {
+                const int ecnt = __popc(edges);
+                int eincl = ecnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, eincl, d);
+                    if (lane >= d) eincl += t;
+                }
+                const int etotal = __shfl_sync(0xffffffffu, eincl, 31);
+                if (etotal == 0) continue;
+                if (etotal <= 10 && nrows <= 8) {
+                    const int eoff = eincl - ecnt;
+                    const int q = lane / 3, kd = lane - 3 * q;
+                    int erow = 0, eq = 0;
+                    uint32_t emask = 0;
+                    for (int r = 0; r < nrows; ++r) {
+                        const int o = __shfl_sync(0xffffffffu, eoff, r), c = __shfl_sync(0xffffffffu, ecnt, r);
+                        const uint32_t ed = __shfl_sync(0xffffffffu, edges, r);
+                        if (q >= o && q < o + c) { erow = r; emask = ed; eq = q - o; }
+                    }
+                    const bool ev = (q < etotal) && (kd < 3) && (lane < 30);
+                    for (int t = 0; t < eq; ++t) emask &= emask - 1;
+                    const int ex = __ffs(emask) - 1, fy0 = base + erow;
+                    const int nrot = (frot + kd + 1) & 3;
+                    int res = 0, tx = 0, ty = 0, nulk = 0;   // res: 1 = queue the target, 2 = flagged emission at once
+                    if (ev) {
+                        const uint32_t px = (*kpack)[frot][kd][0], py = (*kpack)[frot][kd][1];
+                        const int kn = c_kicks[tab][frot][kd].n;
+                        for (int ki = 0; ki < kn; ++ki) {
+                            tx = ex + (int)((px >> (4 * ki)) & 15u) - 2;
+                            ty = fy0 - ((int)((py >> (4 * ki)) & 15u) - 2);
+                            if ((unsigned)tx >= (unsigned)TRL_MAP_W || (unsigned)ty >= (unsigned)TRL_MAP_H) continue;
+                            const uint32_t tw = S.vv[nrot][ty];
+                            if (!((tw >> tx) & 1u)) continue;
+                            if (ty < 2) break;                                   // origin y < 0: direction abandoned
+                            if (!((tw >> (16 + tx)) & 1u)) res = 1;
+                            else if (!((S.vv[nrot][ty + 1] >> tx) & 1u)) res = 2;
+                            nulk = (is_T && kd != 1 && ki == kn - 1) ? 1 : 0;
+                            break;                                               // first successful kick wins
+                        }
+                        if (res == 1 && !is_T) {   // already queued? (order / multiplicity only matter for T)
+                            if (atomicOr(&S.fu[nrot][ty], 1u << tx) & (1u << tx)) res = 0;
+                        }
+                    }
+                    const uint32_t pm = __ballot_sync(0xffffffffu, res == 1);
+                    const int total = __popc(pm);
+                    if ((tail - head) + (uint32_t)total > (uint32_t)kFifoCap) status |= TRL_ST_QUEUE_OVERFLOW;
+                    else {
+                        if (res == 1)   // lane order = (row, column, direction) = the reference's queue order
+                            S.fifo[(tail + (uint32_t)__popc(pm & ((1u << lane) - 1u))) % kFifoCap] = (uint16_t)fifo_pack(tx, ty, nrot, 1, nulk);
+                        tail += (uint32_t)total;
+                    }
+                    if (is_T) {
+                        const uint32_t im = __ballot_sync(0xffffffffu, res == 2);
+                        if (im) {
+                            const uint32_t mt = __ballot_sync(0xffffffffu, res == 2 && nulk);
+                            if (mt == 0u || mt == im) {
+                                if (res == 2) flag_cell(&S.fu[nrot][ty], 1u << tx, nulk != 0);
+                            } else if (res == 2) {   // mixed flags: the last emission of a cell wins
+                                const uint32_t grp = __match_any_sync(im, (uint32_t)(tx | (ty << 4) | (nrot << 10)));
+                                if ((31 - __clz(grp)) == lane) flag_cell(&S.fu[nrot][ty], 1u << tx, nulk != 0);
+                                else atomicOr(&S.fu[nrot][ty], 1u << tx);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    continue;
+                }
             }
             uint32_t Pu[3] = {0, 0, 0}, Im[3] = {0, 0, 0};      // sources whose kick pushes / emits at once
             uint32_t k0[3] = {0, 0, 0}, k1[3] = {0, 0, 0}, k2[3] = {0, 0, 0};   // bit planes of the winning kick index
