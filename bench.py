@@ -326,17 +326,20 @@ def run_ours(args, rank, world, local_rank):
     h2d = n * (80 + 2)
     d2h = n * (MASK_WORDS * 4 + 2 + 4)
 
-    # the same call returning the placements as ascending move lists (np.argwhere order, what
-    # get_move_list consumes, ai.py:1016-1024) instead of bit-packed masks: 14x fewer bytes over PCIe
-    LIST_CAP = 256
+    # the same enumeration returned as COMPACT ascending move lists (np.argwhere order, what get_move_list
+    # consumes, ai.py:1016-1024): 2 B per placement + 14 B per call cross PCIe instead of 1448 B of mask
     del h_mask
-    h_moves = torch.empty((n, LIST_CAP), dtype=torch.int16).pin_memory()
+    cap = int(placements * 1.02) + 4096
+    h_moves = torch.empty(cap, dtype=torch.int16).pin_memory()
+    h_off = torch.empty(n, dtype=torch.int64).pin_memory()
     h_n2 = torch.empty(n, dtype=torch.int16).pin_memory()
+    import ctypes
+    tot = ctypes.c_uint64(0)
 
     def e2e_list_step():
-        rc = L.trl_movegen_host(h_boards.data_ptr(), h_cur.data_ptr(), h_alt.data_ptr(), n, None,
-                                h_moves.data_ptr(), LIST_CAP, h_n2.data_ptr(), h_st.data_ptr())
-        _native.check(rc, "trl_movegen_host")
+        rc = L.trl_movegen_host_compact(h_boards.data_ptr(), h_cur.data_ptr(), h_alt.data_ptr(), n, h_moves.data_ptr(), cap,
+                                        h_off.data_ptr(), h_n2.data_ptr(), h_st.data_ptr(), ctypes.addressof(tot))
+        _native.check(rc, "trl_movegen_host_compact")
 
     e2e_list_step()
     barrier()
@@ -345,7 +348,9 @@ def run_ours(args, rank, world, local_rank):
         e2e_list_step()
     torch.cuda.synchronize()
     e2e_list_s = (time.perf_counter() - t0) / e2e_steps
-    e2e_list_ok = bool(np.array_equal(h_n2.numpy(), d_n.cpu().numpy())) and not bool((h_st.numpy() != 0).any())
+    e2e_list_ok = bool(np.array_equal(h_n2.numpy(), d_n.cpu().numpy())) and int(tot.value) == placements \
+        and not bool((h_st.numpy() != 0).any())
+    d2h_list = placements * 2 + n * (8 + 2 + 4)
     del h_moves
 
     # free the sweep's buffers before the self-play leg
@@ -383,12 +388,14 @@ def run_ours(args, rank, world, local_rank):
                      "traffic": None, "peak_source": peak_src, "kernel": "movegen_warp_kernel",
                      "algorithmic_bytes_per_call": ALGO_BYTES_PER_CALL, "kernel_ms": kern_ms,
                      "note": "integer-issue bound, not HBM bound (SURVEY §8d): see profiles/ for issue utilisation"},
-        "e2e": {"value": placements_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "matches_device_run": e2e_ok,
-                "api": "trl_movegen_host (pinned host buffers, bit-packed (27,39,11) masks returned to the host: PCIe bound)",
-                "as_move_lists": {"value": placements_all / e2e_list_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                                  "d2h_bytes_per_step": n * (LIST_CAP * 2 + 2 + 4), "matches_device_run": e2e_list_ok,
-                                  "api": "same call returning ascending uint16 move lists (np.argwhere order) + counts"}},
+        "e2e": {"value": placements_all / e2e_list_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_list,
+                "steps": e2e_steps, "matches_device_run": e2e_list_ok,
+                "api": "trl_movegen_host_compact: pinned host buffers in, ascending uint16 move lists (np.argwhere order, "
+                       "ai.py:1016-1024) packed back to back + offsets/counts/status out; H2D + kernel + D2H inside the timed region",
+                "as_bit_packed_masks": {"value": placements_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                                        "d2h_bytes_per_step": d2h, "matches_device_run": e2e_ok,
+                                        "api": "trl_movegen_host: the same enumeration returned as bit-packed (27,39,11) masks "
+                                               "(1448 B per call): bound by PCIe / host memory, does not scale with the GPU count"}},
         "gpu_launches": args.steps,
         "clocks": clocks,
     }

@@ -151,6 +151,17 @@ int trl_movegen_host(const uint16_t* boards, const uint8_t* cur, const uint8_t* 
                      uint32_t* mask_bits, uint16_t* moves, int moves_cap, uint16_t* n_moves,
                      uint32_t* status);
 
+/*
+ * trl_movegen_host with COMPACT output: the ascending move lists (np.argwhere order, what
+ * get_move_list consumes, ai.py:1016-1024) of all calls packed back to back without padding.  Call i
+ * owns moves_compact[offsets[i] .. offsets[i] + n_moves[i]).  Only 2 B per placement + 14 B per call
+ * cross PCIe (the bit-packed mask is 1448 B per call).  capacity = length of moves_compact in
+ * elements (TRL_E_ARG if too small); *total_out = number of placements written.
+ */
+int trl_movegen_host_compact(const uint16_t* boards, const uint8_t* cur, const uint8_t* alt, int n,
+                             uint16_t* moves_compact, uint64_t capacity, uint64_t* offsets,
+                             uint16_t* n_moves, uint32_t* status, uint64_t* total_out);
+
 /* Kernel used by every trl_movegen* entry point: 0 = one thread per call (csrc/movegen.cu),
  * 1 = one warp per piece search (csrc/movegen_warp.cu), -1 = automatic (default).  Both produce
  * bit-identical outputs; the choice only trades latency against throughput. */

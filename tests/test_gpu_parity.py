@@ -80,6 +80,27 @@ def test_movegen_random_sweep_vs_oracle(mg, oracle, seed, caves):
         assert np.array_equal(res["moves"][j, :len(want)], want)
 
 
+def test_movegen_host_compact_lists(mg):
+    """Compact (CSR-style) output = the same placements as the bit-packed masks, for every call; several
+    staging chunks, ragged sizes, calls without pieces."""
+    boards, cur, alt = synth.movegen_workload(43000, seed=5, caves=True)   # 301 000 calls: 3 chunks of 2^17
+    cur = cur.copy(); alt = alt.copy()
+    cur[::97] = 255; alt[::97] = 255                                        # no piece at all
+    ref = mg.movegen_host(boards, cur, alt, want_mask=True, want_moves=False)
+    res = mg.movegen_host_compact(boards, cur, alt)
+    assert np.array_equal(res["n_moves"], ref["n_moves"]) and np.array_equal(res["status"], ref["status"])
+    assert res["total"] == int(ref["n_moves"].astype(np.int64).sum())
+    # every segment lies inside the buffer, segments do not overlap, lists are ascending and equal the mask
+    order = np.lexsort((res["n_moves"], res["offsets"]))   # empty lists share their offset with a neighbour
+    ends = res["offsets"][order] + res["n_moves"][order]
+    assert (ends[:-1] <= res["offsets"][order][1:]).all() and ends[-1] <= res["total"]
+    for i in list(range(0, 3000)) + list(range(131000, 132000)) + list(range(boards.shape[0] - 2000, boards.shape[0])):
+        seg = res["moves"][int(res["offsets"][i]): int(res["offsets"][i]) + int(res["n_moves"][i])]
+        assert np.array_equal(seg, _moves_from_mask(ref["mask_bits"][i])), i
+    with pytest.raises(RuntimeError):
+        mg.movegen_host_compact(boards[:5000], cur[:5000], alt[:5000], capacity=100)   # caller buffer too small
+
+
 def test_movegen_edge_cases(mg, oracle):
     rows = np.zeros((6, 40), np.uint16)
     rows[1, :] = 0x3FF & ~1            # everything full except column 0: topped out

@@ -234,7 +234,9 @@ movegen_thread_kernel(const uint16_t* __restrict__ boards, const uint8_t* __rest
 // movegen_warp.cu
 int trl_launch_movegen_warp(const uint16_t* boards, const uint8_t* cur, const uint8_t* alt, const TrlGame* games,
                             const int32_t* index, int n, uint32_t* mask_bits, uint16_t* moves, int moves_cap,
-                            uint16_t* n_moves, uint32_t* status, cudaStream_t stream);
+                            uint16_t* n_moves, uint32_t* status, cudaStream_t stream, uint16_t* compact = nullptr,
+                            unsigned long long compact_cap = 0, unsigned long long* compact_total = nullptr,
+                            unsigned long long* offsets = nullptr);
 
 // Which kernel enumerates: 0 = one thread per call (movegen_thread_kernel), 1 = one warp per piece
 // search (movegen_warp_kernel), -1 = automatic.  Both are bit-exact; they differ in latency/throughput.
@@ -328,4 +330,79 @@ extern "C" int trl_movegen_host(const uint16_t* boards, const uint8_t* cur, cons
     int rc0 = trl_check(cudaStreamSynchronize(st[0]));
     int rc1 = trl_check(cudaStreamSynchronize(st[1]));
     return rc ? rc : (rc0 ? rc0 : rc1);
+}
+
+// Host entry point with COMPACT output: the ascending move lists of all calls packed back to back
+// (no padding), which is what crosses PCIe.  Call i owns moves_compact[offsets[i] .. offsets[i] +
+// n_moves[i]); segments are handed out by an atomic bump allocator per chunk, so their order inside a
+// chunk is arbitrary.  D2H traffic: 2 B per placement + 14 B per call instead of 1448 B of mask.
+extern "C" int trl_movegen_host_compact(const uint16_t* boards, const uint8_t* cur, const uint8_t* alt, int n,
+                                        uint16_t* moves_compact, uint64_t capacity, uint64_t* offsets,
+                                        uint16_t* n_moves, uint32_t* status, uint64_t* total_out) {
+    if (n < 0 || !boards || !cur || !alt || !moves_compact || !offsets || !n_moves || !total_out) return TRL_E_ARG;
+    *total_out = 0;
+    if (n == 0) return TRL_OK;
+    const int chunk = 1 << 17;
+    const size_t list_cap = (size_t)chunk * 160;   // per-chunk staging: 160 placements per call on average (x 2 B)
+    const size_t per = TRL_ROWS * 2 + 2 + 8 + 2 + 4;
+    const int cmax = n < chunk ? n : chunk;
+    const size_t half = ((per * (size_t)cmax + list_cap * 2 + 64) + 255) & ~(size_t)255;
+    char* ws = (char*)trl_workspace(TRL_WS_HOST_STAGE, 2 * half);
+    if (!ws) return TRL_E_NOMEM;
+    cudaStream_t st[2] = {trl_host_stream(0), trl_host_stream(1)};
+    if (!st[0] || !st[1]) return TRL_E_CUDA;
+    static unsigned long long* h_total = nullptr;   // pinned: the per-chunk totals come back through it
+    if (!h_total && trl_check(cudaMallocHost(&h_total, 2 * sizeof(unsigned long long))) != TRL_OK) return TRL_E_CUDA;
+    struct Pending { int off, m; unsigned long long* d_total; uint16_t* d_list; unsigned long long* d_offs;
+                     uint16_t* d_nm; uint32_t* d_status; bool live; } pend[2] = {};
+    uint64_t base = 0;
+    int rc = TRL_OK;
+    auto drain = [&](int h) -> int {   // chunk of half h: wait for its kernel + total, then fetch exactly `total` moves
+        Pending& p = pend[h];
+        if (!p.live) return TRL_OK;
+        p.live = false;
+        int r = trl_check(cudaStreamSynchronize(st[h]));
+        if (r) return r;
+        const unsigned long long total = h_total[h];
+        if (total > list_cap || base + total > capacity) return TRL_E_ARG;   // staging / caller buffer too small
+        r = trl_check(cudaMemcpyAsync(moves_compact + base, p.d_list, (size_t)total * 2, cudaMemcpyDeviceToHost, st[h]));
+        if (!r) r = trl_check(cudaMemcpyAsync(offsets + p.off, p.d_offs, (size_t)p.m * 8, cudaMemcpyDeviceToHost, st[h]));
+        if (!r) r = trl_check(cudaMemcpyAsync(n_moves + p.off, p.d_nm, (size_t)p.m * 2, cudaMemcpyDeviceToHost, st[h]));
+        if (!r && status) r = trl_check(cudaMemcpyAsync(status + p.off, p.d_status, (size_t)p.m * 4, cudaMemcpyDeviceToHost, st[h]));
+        if (!r) r = trl_check(cudaStreamSynchronize(st[h]));
+        if (r) return r;
+        for (int k = 0; k < p.m; ++k) offsets[p.off + k] += base;   // chunk-local -> global
+        base += total;
+        return TRL_OK;
+    };
+    int c = 0;
+    for (int off = 0; off < n && !rc; off += chunk, ++c) {
+        const int h = c & 1;
+        rc = drain(h);   // this half's previous chunk
+        if (rc) break;
+        const int m = (n - off < chunk) ? n - off : chunk;
+        char* p = ws + (size_t)h * half;
+        unsigned long long* d_total = (unsigned long long*)p; p += 64;
+        unsigned long long* d_offs = (unsigned long long*)p; p += (size_t)m * 8;
+        uint32_t* d_status = (uint32_t*)p; p += (size_t)m * 4;
+        uint16_t* d_boards = (uint16_t*)p; p += (size_t)m * TRL_ROWS * 2;
+        uint16_t* d_nm = (uint16_t*)p; p += (size_t)m * 2;
+        uint16_t* d_list = (uint16_t*)p; p += list_cap * 2;
+        uint8_t* d_cur = (uint8_t*)p; p += m;
+        uint8_t* d_alt = (uint8_t*)p; p += m;
+        cudaStream_t s = st[h];
+        rc = trl_check(cudaMemsetAsync(d_total, 0, 8, s));
+        if (!rc) rc = trl_check(cudaMemcpyAsync(d_boards, boards + (size_t)off * TRL_ROWS, (size_t)m * TRL_ROWS * 2, cudaMemcpyHostToDevice, s));
+        if (!rc) rc = trl_check(cudaMemcpyAsync(d_cur, cur + off, m, cudaMemcpyHostToDevice, s));
+        if (!rc) rc = trl_check(cudaMemcpyAsync(d_alt, alt + off, m, cudaMemcpyHostToDevice, s));
+        if (!rc) rc = trl_launch_movegen_warp(d_boards, d_cur, d_alt, nullptr, nullptr, m, nullptr, nullptr, 0, d_nm, d_status, s,
+                                              d_list, list_cap, d_total, d_offs);
+        if (!rc) rc = trl_check(cudaMemcpyAsync(&h_total[h], d_total, 8, cudaMemcpyDeviceToHost, s));
+        if (!rc) pend[h] = {off, m, d_total, d_list, d_offs, d_nm, d_status, true};
+    }
+    // drain in submission order so that `base` grows in chunk order
+    if (!rc) rc = drain(c & 1);
+    if (!rc) rc = drain((c + 1) & 1);
+    *total_out = base;
+    return rc;
 }

@@ -396,7 +396,12 @@ movegen_warp_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restri
                     const uint8_t* __restrict__ alt, const TrlGame* __restrict__ games,
                     const int32_t* __restrict__ index, int n, uint32_t* __restrict__ mask_bits,
                     uint16_t* __restrict__ moves, int moves_cap, uint16_t* __restrict__ n_moves,
-                    uint32_t* __restrict__ status) {
+                    uint32_t* __restrict__ status,
+                    // compact output (optional): the lists of all calls packed without padding; call i owns
+                    // compact[offsets[i] .. offsets[i] + n_moves[i]) (segments are handed out with an atomic
+                    // bump allocator, so their order in the buffer is arbitrary; each list is ascending)
+                    uint16_t* __restrict__ compact, unsigned long long compact_cap,
+                    unsigned long long* __restrict__ compact_total, unsigned long long* __restrict__ offsets) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     PieceState* ps = reinterpret_cast<PieceState*>(smem_raw);
     CallState* cs = reinterpret_cast<CallState*>(smem_raw + sizeof(PieceState) * kWarps);
@@ -464,6 +469,7 @@ movegen_warp_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restri
             if (lane == 0) {
                 if (n_moves) n_moves[i] = 0;
                 if (status) status[i] = 0;
+                if (compact) offsets[i] = 0;
             }
             return;
         }
@@ -487,6 +493,27 @@ movegen_warp_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restri
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         uint32_t st = C.status;
+        if (compact) {
+            unsigned long long off = 0;
+            if (lane == 0) off = atomicAdd(compact_total, (unsigned long long)total);
+            off = __shfl_sync(0xffffffffu, off, 0);
+            if (off + (unsigned long long)total > compact_cap) st |= TRL_ST_MOVES_TRUNC;
+            else {
+                uint16_t* mv = compact + off;
+                int pos = incl - cnt;
+                for (int k = 0; k < 12; ++k) {
+                    const int w2 = w0 + k;
+                    if (w2 >= TRL_MASK_WORDS) break;
+                    uint32_t m = C.mask[w2];
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        mv[pos++] = (uint16_t)(w2 * 32 + b);
+                    }
+                }
+            }
+            if (lane == 0) offsets[i] = off;
+        }
         if (moves) {
             uint16_t* mv = moves + (size_t)i * moves_cap;
             int pos = incl - cnt;
@@ -515,7 +542,9 @@ movegen_warp_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restri
 // Launch the warp-cooperative kernel (same argument contract as movegen.cu's launch_movegen).
 int trl_launch_movegen_warp(const uint16_t* boards, const uint8_t* cur, const uint8_t* alt, const TrlGame* games,
                             const int32_t* index, int n, uint32_t* mask_bits, uint16_t* moves, int moves_cap,
-                            uint16_t* n_moves, uint32_t* status, cudaStream_t stream) {
+                            uint16_t* n_moves, uint32_t* status, cudaStream_t stream, uint16_t* compact,
+                            unsigned long long compact_cap, unsigned long long* compact_total,
+                            unsigned long long* offsets) {
     const size_t smem = sizeof(PieceState) * kWarps + sizeof(CallState) * kCallsPerBlock;
     static bool configured = false;
     if (!configured) {
@@ -525,6 +554,7 @@ int trl_launch_movegen_warp(const uint16_t* boards, const uint8_t* cur, const ui
     }
     const int blocks = (n + kCallsPerBlock - 1) / kCallsPerBlock;
     movegen_warp_kernel<<<blocks, kWarps * 32, smem, stream>>>(boards, cur, alt, games, index, n, mask_bits, moves,
-                                                              moves_cap, n_moves, status);
+                                                              moves_cap, n_moves, status, compact, compact_cap,
+                                                              compact_total, offsets);
     return trl_check(cudaGetLastError());
 }

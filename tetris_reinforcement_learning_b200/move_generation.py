@@ -41,6 +41,41 @@ def movegen_host(boards, cur, alt, want_mask=True, want_moves=False, moves_cap=D
     return {"mask_bits": mask, "moves": moves, "n_moves": n_moves, "status": status}
 
 
+def movegen_host_compact(boards, cur, alt, capacity=None, out=None):
+    """Batched movegen on HOST buffers with compact output (trl_movegen_host_compact): the ascending
+    move lists of all calls packed back to back.
+
+    -> dict(moves uint16[total], offsets uint64[n], n_moves uint16[n], status uint32[n], total int);
+    call i owns moves[offsets[i] : offsets[i] + n_moves[i]].  `out` may carry preallocated (pinned)
+    numpy arrays under the same keys (moves sized `capacity`)."""
+    import ctypes
+    boards = np.ascontiguousarray(boards, dtype=np.uint16)
+    cur = np.ascontiguousarray(cur, dtype=np.uint8)
+    alt = np.ascontiguousarray(alt, dtype=np.uint8)
+    n = boards.shape[0]
+    if boards.shape != (n, ROWS) or cur.shape != (n,) or alt.shape != (n,):
+        raise ValueError("expected boards[n,40], cur[n], alt[n]")
+    out = out or {}
+    capacity = int(capacity if capacity is not None else (out["moves"].size if "moves" in out else max(1024, 160 * n)))
+    moves = out.get("moves", None)
+    if moves is None:
+        moves = np.empty(capacity, dtype=np.uint16)
+    offsets = out.get("offsets", None)
+    if offsets is None:
+        offsets = np.empty(n, dtype=np.uint64)
+    n_moves = out.get("n_moves", None)
+    if n_moves is None:
+        n_moves = np.empty(n, dtype=np.uint16)
+    status = out.get("status", None)
+    if status is None:
+        status = np.empty(n, dtype=np.uint32)
+    total = ctypes.c_uint64(0)
+    rc = _native.lib().trl_movegen_host_compact(_ptr(boards), _ptr(cur), _ptr(alt), n, _ptr(moves), capacity,
+                                                _ptr(offsets), _ptr(n_moves), _ptr(status), ctypes.addressof(total))
+    _native.check(rc, "trl_movegen_host_compact")
+    return {"moves": moves, "offsets": offsets, "n_moves": n_moves, "status": status, "total": int(total.value)}
+
+
 def movegen_device(boards, cur, alt, mask_bits=None, moves=None, n_moves=None, status=None):
     """Batched movegen on torch CUDA tensors, stream-ordered on the current stream.
 
