@@ -164,22 +164,39 @@ def run_selfplay(args, rank, world, local_rank):
         ms_both = timed(eng2)
         del eng2
         torch.cuda.empty_cache()
-    # mean game length in plies, from complete games of a short-search run with the same net
-    n_fast = min(G, 256)
-    fast = engine(8, n_games=n_fast, max_rounds=1000, restart_finished=False)
-    plies = []
-    for _ in range(0 if args.no_game_length else 200):
-        fast.step(64)
-        _, ends = fast.drain()
-        plies.extend(int(e["plies"]) for e in ends)
-        if len(plies) >= n_fast:
-            break
-    mean_plies = float(np.mean(plies)) if plies else float("nan")
-    stats = torch.tensor([ms, float(G * args.selfplay_steps), float(len(samples)), ms_both or 0.0], dtype=torch.float64, device=dev)
+    # self-play games/hour, MEASURED: the same engine keeps playing complete games at MAX_ITER=160 (finished
+    # games restart in place); after one mean game length of warm-up, count the games that END inside a timed
+    # window of about two mean game lengths.  (The mean game length itself comes from the ends seen.)
+    games_done, game_ms, mean_plies, plies = 0, 0.0, float("nan"), []
+    if not args.no_game_length:
+        eng = engine(160)
+        warm_steps = int(args.game_warm_steps)
+        eng.step(warm_steps)
+        _, ends0 = eng.drain()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.step(int(args.game_steps))
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        game_ms = e0.elapsed_time(e1)
+        _, ends = eng.drain()
+        games_done = len(ends)
+        plies = [int(e["plies"]) for e in ends]
+        mean_plies = float(np.mean(plies)) if plies else float("nan")
+        del eng
+        torch.cuda.empty_cache()
+    stats = torch.tensor([ms, float(G * args.selfplay_steps), float(len(samples)), ms_both or 0.0, game_ms, float(games_done)],
+                         dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms, sims, nsamples, ms_both = float(mx[0]), float(sm[1]), float(sm[2]), (float(mx[3]) or None)
+        game_ms, games_done = float(mx[4]), float(sm[5])
     else:
         sims, nsamples = float(stats[1]), float(stats[2])
     sims_per_s = sims / (ms * 1e-3)
@@ -206,9 +223,12 @@ def run_selfplay(args, rank, world, local_rank):
                                  "128 B/clk shared-memory operand fetch of N=48 MMAs, not by tensor math (DESIGN.md)"},
         },
         "selfplay_games_per_hour": {
-            "value": sims_per_s / (160.0 * mean_plies) * 3600.0 if mean_plies == mean_plies else None,
-            "unit": "games/h", "derived": True, "mean_plies_per_game": mean_plies, "games_measured": len(plies),
-            "how": "sims/s / (MAX_ITER x mean plies per game); plies from complete games of a MAX_ITER=8 run of the same net",
+            "value": (games_done / (game_ms * 1e-3) * 3600.0) if game_ms > 0 else None,
+            "unit": "games/h", "measured": True, "games_finished_in_window": games_done,
+            "window_ms": game_ms, "window_steps": int(args.game_steps), "warmup_steps": int(args.game_warm_steps),
+            "mean_plies_per_game": mean_plies,
+            "how": "complete self-play games (MAX_ITER=160 simulations per move, Gamma root noise, temperature move choice, "
+                   "finished games restart in place) that ended inside the timed window, all GPUs",
         },
     }
 
@@ -422,7 +442,9 @@ def main():
     ap.add_argument("--no-selfplay", action="store_true", help="skip the sims/s + games/h leg")
     ap.add_argument("--games", type=int, default=4096, help="concurrent self-play games per GPU")
     ap.add_argument("--selfplay-steps", type=int, default=320)
-    ap.add_argument("--no-game-length", action="store_true", help="skip the game-length run (profiling)")
+    ap.add_argument("--no-game-length", action="store_true", help="skip the games/h run and the no-reuse run (profiling)")
+    ap.add_argument("--game-warm-steps", type=int, default=9000, help="steps before the games/h window (about one game length)")
+    ap.add_argument("--game-steps", type=int, default=18000, help="steps of the games/h window (about two game lengths)")
     ap.add_argument("--net-path", default="fused", choices=["fused", "pytorch"])
     ap.add_argument("--forced", action="store_true", help="forced playouts + policy-target pruning (config 4)")
     args = ap.parse_args()
