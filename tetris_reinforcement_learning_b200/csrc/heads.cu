@@ -17,10 +17,14 @@
 namespace {
 
 constexpr int kFeat = 400, kSide = 52, kOpp = 16, kIn = 521, kPad = 528;
-constexpr int kWarpsPerBlock = 16;   // one block per SM: the 59 KB of weights are staged once per block
+constexpr int kWarpsPerBlock = 8;    // x 4 leaves x 3.7 KB of staged inputs + 59 KB of weights per block
 // packed weights (fp32): Wo_t[400][16], bo[16], Wv_t[528][16], bv[16], w2[16], b2
 constexpr int kOffWo = 0, kOffBo = kOffWo + kFeat * 16, kOffWv = kOffBo + 16, kOffBv = kOffWv + kPad * 16,
               kOffW2 = kOffBv + 16, kOffB2 = kOffW2 + 16, kWFloats = kOffB2 + 4;
+
+// kLeaves leaves per warp pass: the weight row of a k is loaded once and used for all of them
+// (the kernel is bound by shared-memory loads: per k one weight word + one 16-byte vector of leaf inputs).
+constexpr int kLeaves = 4;
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 alphasame_heads_kernel(const __nv_bfloat16* __restrict__ feats,    // [2G][400]: own grids then opponent grids (or a cache)
@@ -32,50 +36,128 @@ alphasame_heads_kernel(const __nv_bfloat16* __restrict__ feats,    // [2G][400]:
                        __nv_bfloat16* __restrict__ value_out) {    // [G]
     extern __shared__ __align__(16) float sm[];
     float* w = sm;
-    float* xs_all = sm + kWFloats;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < kWFloats; i += blockDim.x) w[i] = weights[i];
+    {   // weights -> shared memory: 16-byte loads, several in flight per thread (a scalar copy loop is
+        // latency bound: 59 dependent L2 round trips per thread)
+        const float4* src = reinterpret_cast<const float4*>(weights);
+        float4* dst = reinterpret_cast<float4*>(w);
+        constexpr int kVec = kWFloats / 4;
+        static_assert(kWFloats % 4 == 0, "weights are copied as float4");
+#pragma unroll 8
+        for (int i = tid; i < kVec; i += kWarpsPerBlock * 32) dst[i] = src[i];
+    }
     __syncthreads();
-    float* xs = xs_all + warp * (kPad + kFeat);
-    float* fo = xs + kPad;
+    // per warp: xs[k][leaf] (528 x 4) and fo[k][leaf] (400 x 4), leaf-interleaved so one LDS.128 feeds 4 FMAs
+    float4* xs = reinterpret_cast<float4*>(sm + kWFloats) + warp * (kPad + kFeat);
+    float4* fo = xs + kPad;
+    float* xs_f = reinterpret_cast<float*>(xs);
+    float* fo_f = reinterpret_cast<float*>(fo);
     const int o = lane & 15, h = lane >> 4;
-    for (int g = blockIdx.x * kWarpsPerBlock + warp; g < G; g += gridDim.x * kWarpsPerBlock) {
-        // ---- stage: own features, side inputs, opponent features ----
-        const int ra = own_row ? own_row[g] : g, rb = own_row ? opp_row[g] : G + g;
-        if (ra < 0) continue;   // warp-uniform
-        const __nv_bfloat162* fa = reinterpret_cast<const __nv_bfloat162*>(feats + (size_t)ra * kFeat);
-        const __nv_bfloat162* fb = reinterpret_cast<const __nv_bfloat162*>(feats + (size_t)rb * kFeat);
-        for (int i = lane; i < kFeat / 2; i += 32) {
-            const float2 a = __bfloat1622float2(fa[i]), b = __bfloat1622float2(fb[i]);
-            xs[2 * i] = a.x; xs[2 * i + 1] = a.y;
-            fo[2 * i] = b.x; fo[2 * i + 1] = b.y;
+    const int n_quads = (G + kLeaves - 1) / kLeaves;
+    for (int q = blockIdx.x * kWarpsPerBlock + warp; q < n_quads; q += gridDim.x * kWarpsPerBlock) {
+        int ra[kLeaves], rb[kLeaves];
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < kLeaves; ++j) {
+            const int g = q * kLeaves + j;
+            ra[j] = (g < G) ? (own_row ? own_row[g] : g) : -1;
+            rb[j] = (g < G) ? (own_row ? opp_row[g] : G + g) : -1;
+            any = any || ra[j] >= 0;
         }
-        const __nv_bfloat16* ex = extras + (size_t)g * (2 * kSide + 1);
-        for (int i = lane; i < 2 * kSide + 1; i += 32)
-            xs[kFeat + i + (i >= kSide ? kOpp : 0)] = __bfloat162float(ex[i]);
-        if (lane < kPad - kIn) xs[kIn + lane] = 0.f;
+        if (!any) continue;   // warp-uniform
+        // ---- stage: own features, side inputs, opponent features (zeros for skipped leaves) ----
+        // all global loads of the pass are issued before the first use (the pass is latency bound otherwise)
+        constexpr int kFI = (kFeat / 2 + 31) / 32;            // 7 bf16x2 words per lane and feature row
+        constexpr int kEI = (2 * kSide + 1 + 31) / 32;        // 4 side inputs per lane
+        uint32_t ua[kLeaves][kFI], ub[kLeaves][kFI];
+        uint16_t ue[kLeaves][kEI];
+#pragma unroll
+        for (int j = 0; j < kLeaves; ++j) {
+            const uint32_t* fa = reinterpret_cast<const uint32_t*>(feats + (size_t)(ra[j] < 0 ? 0 : ra[j]) * kFeat);
+            const uint32_t* fb = reinterpret_cast<const uint32_t*>(feats + (size_t)(ra[j] < 0 ? 0 : rb[j]) * kFeat);
+            const uint16_t* ex = reinterpret_cast<const uint16_t*>(extras + (size_t)(ra[j] < 0 ? 0 : q * kLeaves + j) * (2 * kSide + 1));
+#pragma unroll
+            for (int t = 0; t < kFI; ++t) {
+                const int i = lane + 32 * t;
+                const bool ok = ra[j] >= 0 && i < kFeat / 2;
+                ua[j][t] = ok ? fa[i] : 0u;
+                ub[j][t] = ok ? fb[i] : 0u;
+            }
+#pragma unroll
+            for (int t = 0; t < kEI; ++t) {
+                const int i = lane + 32 * t;
+                ue[j][t] = (ra[j] >= 0 && i < 2 * kSide + 1) ? ex[i] : (uint16_t)0;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kLeaves; ++j) {
+#pragma unroll
+            for (int t = 0; t < kFI; ++t) {
+                const int i = lane + 32 * t;
+                if (i < kFeat / 2) {
+                    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ua[j][t]));
+                    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ub[j][t]));
+                    xs_f[(2 * i) * kLeaves + j] = a.x; xs_f[(2 * i + 1) * kLeaves + j] = a.y;
+                    fo_f[(2 * i) * kLeaves + j] = b.x; fo_f[(2 * i + 1) * kLeaves + j] = b.y;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < kEI; ++t) {
+                const int i = lane + 32 * t;
+                if (i < 2 * kSide + 1)
+                    xs_f[(kFeat + i + (i >= kSide ? kOpp : 0)) * kLeaves + j] = __bfloat162float(__ushort_as_bfloat16(ue[j][t]));
+            }
+            if (lane < kOpp) xs_f[(kFeat + kSide + lane) * kLeaves + j] = 0.f;
+            if (lane < kPad - kIn) xs_f[(kIn + lane) * kLeaves + j] = 0.f;
+        }
         __syncwarp();
-        // ---- osidedense: 16 outputs x 400, lanes = (k parity, output) ----
-        float acc = 0.f;
+        // ---- osidedense: 16 outputs x 400 for 4 leaves, lanes = (k parity, output) ----
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-        for (int k = h; k < kFeat; k += 2) acc = fmaf(fo[k], w[kOffWo + k * 16 + o], acc);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-        const float o16 = fmaxf(acc + w[kOffBo + o], 0.f);
-        if (h == 0) xs[kFeat + kSide + o] = __bfloat162float(__float2bfloat16(o16));   // rounded like the module's bf16 output
+        for (int k = h; k < kFeat; k += 2) {
+            const float wk = w[kOffWo + k * 16 + o];
+            const float4 f = fo[k];
+            acc.x = fmaf(f.x, wk, acc.x); acc.y = fmaf(f.y, wk, acc.y); acc.z = fmaf(f.z, wk, acc.z); acc.w = fmaf(f.w, wk, acc.w);
+        }
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+        if (h == 0) {   // rounded like the module's bf16 output
+            const float bo = w[kOffBo + o];
+            xs[kFeat + kSide + o] = make_float4(__bfloat162float(__float2bfloat16(fmaxf(acc.x + bo, 0.f))),
+                                                __bfloat162float(__float2bfloat16(fmaxf(acc.y + bo, 0.f))),
+                                                __bfloat162float(__float2bfloat16(fmaxf(acc.z + bo, 0.f))),
+                                                __bfloat162float(__float2bfloat16(fmaxf(acc.w + bo, 0.f))));
+        }
         __syncwarp();
         // ---- x out (bf16, 528 wide) ----
-        __nv_bfloat162* xo = reinterpret_cast<__nv_bfloat162*>(x_out + (size_t)g * kPad);
-        for (int i = lane; i < kPad / 2; i += 32) xo[i] = __floats2bfloat162_rn(xs[2 * i], xs[2 * i + 1]);
-        // ---- value head ----
-        acc = 0.f;
-#pragma unroll 4
-        for (int k = h; k < kPad; k += 2) acc = fmaf(xs[k], w[kOffWv + k * 16 + o], acc);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-        float v = fmaxf(acc + w[kOffBv + o], 0.f) * w[kOffW2 + o];
 #pragma unroll
-        for (int d = 8; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        v += w[kOffB2];
-        if (lane == 0) value_out[g] = __float2bfloat16(use_tanh ? tanhf(v) : 1.f / (1.f + __expf(-v)));
+        for (int j = 0; j < kLeaves; ++j) {
+            if (ra[j] < 0) continue;
+            __nv_bfloat162* xo = reinterpret_cast<__nv_bfloat162*>(x_out + (size_t)(q * kLeaves + j) * kPad);
+            for (int i = lane; i < kPad / 2; i += 32)
+                xo[i] = __floats2bfloat162_rn(xs_f[(2 * i) * kLeaves + j], xs_f[(2 * i + 1) * kLeaves + j]);
+        }
+        // ---- value head ----
+        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int k = h; k < kPad; k += 2) {
+            const float wk = w[kOffWv + k * 16 + o];
+            const float4 f = xs[k];
+            acc.x = fmaf(f.x, wk, acc.x); acc.y = fmaf(f.y, wk, acc.y); acc.z = fmaf(f.z, wk, acc.z); acc.w = fmaf(f.w, wk, acc.w);
+        }
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+        const float bv = w[kOffBv + o], w2 = w[kOffW2 + o];
+        float v[kLeaves] = {fmaxf(acc.x + bv, 0.f) * w2, fmaxf(acc.y + bv, 0.f) * w2, fmaxf(acc.z + bv, 0.f) * w2,
+                            fmaxf(acc.w + bv, 0.f) * w2};
+#pragma unroll
+        for (int j = 0; j < kLeaves; ++j) {
+#pragma unroll
+            for (int d = 8; d >= 1; d >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], d);
+            v[j] += w[kOffB2];
+            if (lane == 0 && ra[j] >= 0)
+                value_out[q * kLeaves + j] = __float2bfloat16(use_tanh ? tanhf(v[j]) : 1.f / (1.f + __expf(-v[j])));
+        }
         __syncwarp();
     }
 }
@@ -89,7 +171,7 @@ static int launch_heads(const void* feats_bf16, const int32_t* own_row, const in
                         void* stream) {
     if (n_leaves < 0 || !feats_bf16 || !extras_bf16 || !weights || !x_out_bf16 || !value_out_bf16) return TRL_E_ARG;
     if (n_leaves == 0) return TRL_OK;
-    const int smem = (kWFloats + kWarpsPerBlock * (kPad + kFeat)) * 4;
+    const int smem = (kWFloats + kWarpsPerBlock * kLeaves * (kPad + kFeat)) * 4;
     static bool configured = false;
     if (!configured) {
         int rc = trl_check(cudaFuncSetAttribute(alphasame_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -99,7 +181,7 @@ static int launch_heads(const void* feats_bf16, const int32_t* own_row, const in
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int blocks = (n_leaves + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    int blocks = ((n_leaves + kLeaves - 1) / kLeaves + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > sms) blocks = sms;
     alphasame_heads_kernel<<<blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)feats_bf16, own_row, opp_row, (const __nv_bfloat16*)extras_bf16, n_leaves, weights, use_tanh,
