@@ -45,6 +45,8 @@ extern "C" {
 #define TRL_POLICY_SIZE 11583    /* 27*39*11, const.py:122-123 */
 #define TRL_MASK_WORDS 362       /* ceil(11583/32) */
 #define TRL_NONE 255
+#define TRL_RULESET_S2 0
+#define TRL_RULESET_S1 1
 #define TRL_QUEUE_CAP 16
 #define TRL_RECV_CAP 80
 
@@ -88,7 +90,9 @@ typedef struct TrlPlayer {
 typedef struct TrlGame {
     TrlPlayer players[2];            /* 0                                                 */
     uint8_t  turn;                   /* 384 index of the side to move                     */
-    uint8_t  pad_;
+    uint8_t  ruleset;                /* 385 0 = TETR.IO season 2 ('s2', default), 1 = season 1 ('s1'):
+                                            attack table (stats.py:49-86 / 88-129) and the s2-only
+                                            all-spin rule (player.py:145-151)                     */
     uint16_t bag_ctr;                /* 386 number of 7-bag refills dealt so far          */
     uint32_t rounds;                 /* 388 len(history.states) (game.py:86-87)           */
     uint32_t rng_ctr;                /* 392 counter for the next garbage-column draw      */

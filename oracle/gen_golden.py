@@ -16,6 +16,7 @@ Files
                       outputs[n,4] i16 (attack, combo', b2b', level')
   env_golden.npz      before[n] / after[n] packed TrlGame bytes, moves[n] u16, add_bag[n] u8,
                       seed; `after` is the reference's state after Game.make_move
+  attack_golden_s1.npz, env_golden_s1.npz   the same for ruleset 's1' 
 """
 import os
 import sys
@@ -64,7 +65,7 @@ def gen_movegen(n_boards=220):
     print("movegen_golden:", len(boards), "calls,", int(np.unpackbits(masks.view(np.uint8)).sum()), "placements")
 
 
-def gen_attack():
+def gen_attack(ruleset="s2"):
     m = rh.modules()
     ins, outs = [], []
     for rows in range(0, 5):
@@ -74,20 +75,20 @@ def gen_attack():
                     for combo in range(0, 14):
                         for b2b in list(range(-1, 7)) + [23, 24, 66, 67, 1369, 1370]:
                             for lvl in (0, 1, 2, 3, 8):
-                                s = m.stats.Stats("s2")
+                                s = m.stats.Stats(ruleset)
                                 s.combo, s.b2b, s.b2b_level = combo, b2b, lvl
                                 a = s.get_attack(rows, bool(tspin), bool(mini), bool(pc), "T")
                                 ins.append((rows, tspin, mini, pc, combo, b2b, lvl))
                                 outs.append((a, s.combo, s.b2b, s.b2b_level))
-    np.savez_compressed(os.path.join(OUT, "attack_golden.npz"),
-                        inputs=np.array(ins, np.int16), outputs=np.array(outs, np.int16))
-    print("attack_golden:", len(ins), "cases")
+    name = "attack_golden.npz" if ruleset == "s2" else f"attack_golden_{ruleset}.npz"
+    np.savez_compressed(os.path.join(OUT, name), inputs=np.array(ins, np.int16), outputs=np.array(outs, np.int16))
+    print(name, len(ins), "cases")
 
 
-def gen_env(n_games=260, plies=40):
+def gen_env(n_games=260, plies=40, ruleset="s2"):
     rng = np.random.default_rng(SEED)
     tape = rh.install_tape(SEED)
-    games = random_midgame(rng, n_games, SEED)
+    games = random_midgame(rng, n_games, SEED, ruleset)
     before, after, moves, bags = [], [], [], []
     stats = dict(clears=0, pcs=0, attacks=0, recv=0, tops=0, holds=0, spins=0)
     for i in range(n_games):
@@ -114,7 +115,7 @@ def gen_env(n_games=260, plies=40):
             before.append(rec.copy())
             new_rng, new_bag = rh.step(ref, mv, add_bag, tape, gid, pre_rng, pre_bag)
             nxt = np.zeros(1, dtype=GAME_DTYPE)
-            pack_game(ref, game_id=gid, rng_ctr=new_rng, bag_ctr=new_bag, out=nxt[0])
+            pack_game(ref, game_id=gid, rng_ctr=new_rng, bag_ctr=new_bag, out=nxt[0])   # ruleset from ref.ruleset
             # rounds = len(history.states): grows when player 1 places with add_history (game.py:86-87)
             nxt[0]["rounds"] = rounds + (1 if (add_bag and turn_before == 1) else 0)
             after.append(nxt.copy()); moves.append(mv); bags.append(int(add_bag))
@@ -125,11 +126,12 @@ def gen_env(n_games=260, plies=40):
             stats["spins"] += int(bool(out["flags"] & 3))
             rec = nxt  # continue from the REFERENCE's state
     before = np.concatenate(before); after = np.concatenate(after)
-    np.savez_compressed(os.path.join(OUT, "env_golden.npz"),
+    name = "env_golden.npz" if ruleset == "s2" else f"env_golden_{ruleset}.npz"
+    np.savez_compressed(os.path.join(OUT, name),
                         before=before.view(np.uint8).reshape(len(before), -1),
                         after=after.view(np.uint8).reshape(len(after), -1),
                         moves=np.array(moves, np.uint16), add_bag=np.array(bags, np.uint8), seed=SEED)
-    print("env_golden:", len(moves), "transitions", stats)
+    print(name, len(moves), "transitions", stats)
 
 
 def gen_mcts(n_searches=24, iters=48):
@@ -168,7 +170,7 @@ if __name__ == "__main__":
     if not rh.available():
         sys.exit("reference checkout not available")
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["movegen", "attack", "env", "mcts"]
+    which = sys.argv[1:] or ["movegen", "attack", "env", "mcts", "s1"]
     if "movegen" in which:
         gen_movegen()
     if "attack" in which:
@@ -177,3 +179,6 @@ if __name__ == "__main__":
         gen_env()
     if "mcts" in which:
         gen_mcts()
+    if "s1" in which:   # ruleset s1: attack table (stats.py:49-86) and env transitions without the all-spin rule
+        gen_attack("s1")
+        gen_env(n_games=140, plies=40, ruleset="s1")

@@ -40,6 +40,8 @@ def lib():
         L.trl_oracle_movegen_batch.argtypes = [u16p, u8p, u8p, ctypes.c_int, u32p, u16p, u32p, ctypes.c_int]
         L.trl_oracle_get_attack_s2.restype = ctypes.c_int
         L.trl_oracle_get_attack_s2.argtypes = [ctypes.c_int] * 4 + [ip, ip, ip]
+        L.trl_oracle_get_attack_s1.restype = ctypes.c_int
+        L.trl_oracle_get_attack_s1.argtypes = [ctypes.c_int] * 4 + [ip, ip, ip]
         L.trl_oracle_env_step_batch.restype = None
         L.trl_oracle_env_step_batch.argtypes = [ctypes.c_void_p, u16p, ctypes.c_int, ctypes.c_void_p,
                                                 ctypes.c_int, ctypes.c_uint64]
@@ -103,6 +105,14 @@ def get_attack_s2(rows_cleared, tspin, mini, all_clear, combo, b2b, b2b_level):
     return a, c.value, b.value, l.value
 
 
+def get_attack_s1(rows_cleared, tspin, mini, all_clear, combo, b2b, b2b_level):
+    """-> (attack, combo, b2b, b2b_level) after Stats.get_attack (ruleset s1)."""
+    c, b, l = ctypes.c_int(combo), ctypes.c_int(b2b), ctypes.c_int(b2b_level)
+    a = lib().trl_oracle_get_attack_s1(int(rows_cleared), int(bool(tspin)), int(bool(mini)),
+                                       int(bool(all_clear)), ctypes.byref(c), ctypes.byref(b), ctypes.byref(l))
+    return a, c.value, b.value, l.value
+
+
 def env_step(games, moves, add_bag, seed):
     """Steps GAME_DTYPE array `games` in place; returns STEPOUT_DTYPE array."""
     assert games.dtype == GAME_DTYPE and games.flags["C_CONTIGUOUS"]
@@ -113,9 +123,11 @@ def env_step(games, moves, add_bag, seed):
     return out
 
 
-def game_setup(n, first_game_id, seed):
+def game_setup(n, first_game_id, seed, ruleset="s2"):
+    from tetris_reinforcement_learning_b200.state import ruleset_id
     games = np.zeros(n, dtype=GAME_DTYPE)
     lib().trl_oracle_game_setup_batch(games.ctypes.data, n, int(first_game_id), int(seed))
+    games["ruleset"] = ruleset_id(ruleset)
     return games
 
 

@@ -60,9 +60,10 @@ def sweep_movegen(n_calls, seed):
     return bad
 
 
-def sweep_attack():
+def sweep_attack(ruleset="s2"):
     m = rh.modules()
     bad = n = 0
+    mine = oracle.get_attack_s1 if ruleset == "s1" else oracle.get_attack_s2
     for rows in range(0, 5):
         for tspin in (False, True):
             for mini in (False, True):
@@ -70,23 +71,23 @@ def sweep_attack():
                     for combo in range(0, 21):
                         for b2b in list(range(-1, 12)) + [23, 24, 66, 67, 184, 185, 503, 504, 1369, 1370]:
                             for lvl in range(0, 9):
-                                s = m.stats.Stats("s2")
+                                s = m.stats.Stats(ruleset)
                                 s.combo, s.b2b, s.b2b_level = combo, b2b, lvl
                                 a = s.get_attack(rows, tspin, mini, pc, "T")
-                                got = oracle.get_attack_s2(rows, tspin, mini, pc, combo, b2b, lvl)
+                                got = mine(rows, tspin, mini, pc, combo, b2b, lvl)
                                 n += 1
                                 if got != (a, s.combo, s.b2b, s.b2b_level):
                                     bad += 1
                                     if bad < 5:
                                         print("  ATTACK MISMATCH", rows, tspin, mini, pc, combo, b2b, lvl,
                                               (a, s.combo, s.b2b, s.b2b_level), got)
-    print(f"attack: {n} cases, mismatches {bad}")
+    print(f"attack ({ruleset}): {n} cases, mismatches {bad}")
     return bad
 
 
-def random_midgame(rng, n, seed):
+def random_midgame(rng, n, seed, ruleset="s2"):
     """Packed games with synthetic boards, pending garbage and non-trivial stats."""
-    games = oracle.game_setup(n, first_game_id=1000, seed=seed)
+    games = oracle.game_setup(n, first_game_id=1000, seed=seed, ruleset=ruleset)
     boards = synth.random_boards(2 * n, seed=int(rng.integers(1 << 30)), caves=True)
     for i in range(n):
         for pl in range(2):
@@ -119,7 +120,7 @@ def random_midgame(rng, n, seed):
                 p["held"] = int(rng.integers(0, 7))
             p["combo"] = int(rng.integers(0, 6)) if rng.random() < 0.5 else 0
             p["b2b"] = int(rng.integers(-1, 8))
-            p["b2b_level"] = int(rng.integers(0, 3))
+            p["b2b_level"] = int(rng.integers(0, 3)) if ruleset == "s2" else int(rng.integers(0, 5))
         games[i]["turn"] = int(rng.integers(0, 2))
     return games
 
@@ -137,10 +138,10 @@ def pick_move(rng, rec, legal, seed):
     return int(legal[int(rng.choice(top))])
 
 
-def sweep_env(n_games, plies, seed):
+def sweep_env(n_games, plies, seed, ruleset="s2"):
     rng = np.random.default_rng(seed)
     tape = rh.install_tape(seed)
-    games = random_midgame(rng, n_games, seed)
+    games = random_midgame(rng, n_games, seed, ruleset)
     bad = moves_played = clears = sends = recvs = tops = holds = spins = pcs = 0
     for i in range(n_games):
         rec = games[i:i + 1].copy()
@@ -185,7 +186,7 @@ def sweep_env(n_games, plies, seed):
                     if a["turn"] != b["turn"]:
                         print("    turn", a["turn"], b["turn"])
                 break
-    print(f"env: {moves_played} moves over {n_games} games; clears {clears}, all-clears {pcs}, attacks {sends}, "
+    print(f"env ({ruleset}): {moves_played} moves over {n_games} games; clears {clears}, all-clears {pcs}, attacks {sends}, "
           f"garbage receipts {recvs}, top-outs {tops}, holds {holds}, spin/mini flags {spins}; mismatches {bad}")
     return bad
 
@@ -202,8 +203,9 @@ def main():
         return 2
     t = time.time()
     bad = sweep_movegen(args.movegen, args.seed)
-    bad += sweep_attack()
-    bad += sweep_env(args.games, args.plies, args.seed)
+    for ruleset in ("s2", "s1"):
+        bad += sweep_attack(ruleset)
+        bad += sweep_env(args.games, args.plies, args.seed, ruleset)
     print(f"total mismatches {bad}  ({time.time() - t:.1f} s)")
     return 1 if bad else 0
 

@@ -191,10 +191,12 @@ def movegen_packed(rows, cur, alt, alt_is_held=True):
     return movegen(pl)
 
 
-def make_game(rec, ruleset="s2"):
-    """Reference Game from a GAME_DTYPE scalar."""
+def make_game(rec, ruleset=None):
+    """Reference Game from a GAME_DTYPE scalar (ruleset from the record unless given)."""
     from tetris_reinforcement_learning_b200.state import piece_name
     m = modules()
+    if ruleset is None:
+        ruleset = "s1" if int(rec["ruleset"]) == 1 else "s2"
     g = m.game.Game(ruleset)
     for i, pl in enumerate(g.players):
         pr = rec["players"][i]

@@ -15,6 +15,8 @@ int  trl_oracle_movegen(const uint16_t* rows, int cur, int alt, uint8_t* mask, u
                         int* n_push_out, int* n_emit_out);
 int  trl_oracle_get_attack_s2(int rows_cleared, int is_tspin, int is_mini, int is_all_clear,
                               int* combo, int* b2b, int* b2b_level);
+int  trl_oracle_get_attack_s1(int rows_cleared, int is_tspin, int is_mini, int is_all_clear,
+                              int* combo, int* b2b, int* b2b_level);
 void trl_oracle_game_setup(TrlGame* g, uint32_t game_id, uint64_t seed);
 void trl_oracle_env_step(TrlGame* g, int move, int add_bag, uint64_t seed, TrlStepOut* out);
 void trl_oracle_env_step_rng(TrlGame* g, int move, int add_bag, uint64_t seed, uint32_t stream,

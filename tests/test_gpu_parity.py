@@ -202,8 +202,9 @@ def test_movegen_full_size_properties(mg, oracle):
 # env step
 # ------------------------------------------------------------------------------------------
 
-def test_env_reference_transitions(env, golden_dir):
-    g = np.load(os.path.join(golden_dir, "env_golden.npz"))
+@pytest.mark.parametrize("ruleset", ["s2", "s1"])
+def test_env_reference_transitions(env, golden_dir, ruleset):
+    g = np.load(os.path.join(golden_dir, "env_golden.npz" if ruleset == "s2" else "env_golden_s1.npz"))
     before = g["before"].copy().view(GAME_DTYPE).reshape(-1)
     after = g["after"].copy().view(GAME_DTYPE).reshape(-1)
     seed = int(g["seed"])
@@ -222,13 +223,15 @@ def test_game_setup_vs_oracle(env, oracle):
     assert games_equal(got, want).all()
 
 
-def test_env_selfplay_vs_oracle(env, mg, oracle):
+@pytest.mark.parametrize("ruleset", ["s2", "s1"])
+def test_env_selfplay_vs_oracle(env, mg, oracle, ruleset):
     """Random legal self-play from setup, GPU movegen + GPU env step vs the oracle, every ply:
     boards, queues, holds, garbage lists, attack, b2b, combo, top-outs, bag refills."""
     seed, n = 4242, 512
     rng = np.random.default_rng(seed)
-    games = env.game_setup_host(n, 0, seed)
-    shadow = oracle.game_setup(n, 0, seed)
+    games = env.game_setup_host(n, 0, seed, ruleset=ruleset)
+    shadow = oracle.game_setup(n, 0, seed, ruleset=ruleset)
+    assert (games["ruleset"] == (1 if ruleset == "s1" else 0)).all()
     attacks = clears = 0
     for ply in range(120):
         pl = games["players"][np.arange(n), games["turn"]]

@@ -204,3 +204,21 @@ def test_engine_is_deterministic_and_matches_oracle_env():
             trunc[0]["players"][pl]["qlen"] = min(int(trunc[0]["players"][pl]["qlen"]), 5)
         assert games_equal(root, trunc).all(), f"search {int(s['search_no'])}: recorded root differs from the replay"
         oracle.env_step(shadow, np.array([s["chosen_move"]], np.uint16), True, 5)
+
+
+def test_engine_ruleset_s1_runs_and_survives_restarts():
+    """Config(ruleset='s1'): the engine plays complete games under the season-1 attack table; restarted
+    games keep the ruleset byte."""
+    import torch
+    from tetris_reinforcement_learning_b200 import architectures as arch
+    from tetris_reinforcement_learning_b200.config import Config
+    from tetris_reinforcement_learning_b200.selfplay import SelfPlayEngine, best_evaluator
+    torch.manual_seed(0)
+    net = arch.AlphaSame(arch.AlphaSameConfig()).to("cuda:0")
+    cfg = Config(visual=False, ruleset="s1", model="pytorch", model_config=arch.AlphaSameConfig(), MAX_ITER=6, training=True)
+    eng = SelfPlayEngine(cfg, best_evaluator(net), 64, seed=5, feature_dtype=torch.bfloat16, max_rounds=6, sample_cap=16384)
+    eng.step(600)
+    samples, ends = eng.drain()
+    assert len(ends) > 64 and len(samples) > 0
+    assert (eng.get_games()["ruleset"] == 1).all() and (samples["state"]["ruleset"] == 1).all()
+    assert (eng.get_ctl()["status"] == 0).all()

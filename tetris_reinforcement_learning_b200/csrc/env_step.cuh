@@ -116,6 +116,32 @@ __device__ __forceinline__ int trl_get_attack_s2(int n, bool tspin, bool mini, b
     return attack;
 }
 
+// Stats.get_attack for ruleset s1 (stats.py:49-86), same integer-arithmetic treatment: B2B only for
+// quads and T-spins, no surge, the full b2b level enters the formulas, +10 for any all-clear.
+__device__ __forceinline__ int trl_get_attack_s1(int n, bool tspin, bool mini, bool all_clear,
+                                                 int& combo, int& b2b, int& level) {
+    if (n == 0) { combo = 0; return 0; }
+    int attack = 0;
+    const bool is_b2b = tspin || n == 4;
+    b2b = is_b2b ? b2b + 1 : -1;
+    const int thr[9] = {-1, 1, 3, 8, 24, 67, 185, 504, 1370};
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+        if (b2b >= thr[i] && level < i) level = i;
+    const int q = 4 + combo;
+    if (n == 1) {
+        if (!tspin) attack += (2 + combo) >> 2;
+        else if (mini) attack += (b2b <= 0 && level <= 0) ? ((2 + combo) >> 2) : ((level * q) >> 2);
+        else attack += ((2 + level) * q) >> 2;
+    } else {
+        const int inner4 = (tspin ? 2 * n * (mini ? 1 : 4) : 4 * (1 << (n - 2))) + 4 * level * (is_b2b ? 1 : 0);
+        attack += (q * inner4) >> 4;
+    }
+    combo += 1;
+    if (all_clear) attack += 10;
+    return attack;
+}
+
 // One full Game.make_move on a game in shared memory.  Scalar: call from ONE lane.
 static __device__ __noinline__ TrlStepOut trl_env_step_scalar(TrlGame* g, int move, bool add_bag, uint64_t seed,
                                                        uint32_t stream, uint32_t* ctr) {
@@ -158,7 +184,8 @@ static __device__ __noinline__ TrlStepOut trl_env_step_scalar(TrlGame* g, int mo
         const bool front = ((fm >> rot) & 1u) && ((fm >> ((rot + 1) & 3)) & 1u);
         if (!front && !ulk) mini = true;
     }
-    if (!tspin) {  // s2 all-spin: immobile at its own (x, y) (player.py:145-151)
+    const bool s1 = g->ruleset == TRL_RULESET_S1;
+    if (!tspin && !s1) {  // s2 all-spin: immobile at its own (x, y) (player.py:145-151)
         const bool movable = trl_fits(p->rows, minos, x - 1, y) || trl_fits(p->rows, minos, x + 1, y) ||
                              trl_fits(p->rows, minos, x, y - 1) || trl_fits(p->rows, minos, x, y + 1);
         if (!movable) mini = true;
@@ -195,7 +222,8 @@ static __device__ __noinline__ TrlStepOut trl_env_step_scalar(TrlGame* g, int mo
     }
 
     int combo = p->combo, b2b = p->b2b, level = p->b2b_level;
-    const int attack = trl_get_attack_s2(n_cleared, tspin, mini, all_clear, combo, b2b, level);
+    const int attack = s1 ? trl_get_attack_s1(n_cleared, tspin, mini, all_clear, combo, b2b, level)
+                          : trl_get_attack_s2(n_cleared, tspin, mini, all_clear, combo, b2b, level);
     p->combo = (int16_t)combo; p->b2b = (int16_t)b2b; p->b2b_level = (uint8_t)level;
     p->pieces += 1;
 
@@ -242,10 +270,11 @@ static __device__ __noinline__ TrlStepOut trl_env_step_scalar(TrlGame* g, int mo
 }
 
 // Game() + Game.setup() (game.py:8-38).  Scalar.
-__device__ __forceinline__ void trl_game_setup_scalar(TrlGame* g, uint32_t game_id, uint64_t seed) {
+__device__ __forceinline__ void trl_game_setup_scalar(TrlGame* g, uint32_t game_id, uint64_t seed, uint8_t ruleset = TRL_RULESET_S2) {
     uint32_t* w = reinterpret_cast<uint32_t*>(g);
     for (int i = 0; i < (int)(sizeof(TrlGame) / 4); ++i) w[i] = 0;
     g->game_id = game_id;
+    g->ruleset = ruleset;
     for (int pl = 0; pl < 2; ++pl) {
         g->players[pl].b2b = -1;
         g->players[pl].piece = TRL_NONE;

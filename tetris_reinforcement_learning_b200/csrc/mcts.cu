@@ -358,7 +358,7 @@ __device__ void finish_search(const TrlSearchBuffers& B, const TrlSearchParams& 
             ctl->search_no = 0; ctl->lines_sent0 = 0; ctl->lines_cleared0 = 0;
             if (P.restart_finished) {
                 const uint32_t id = atomicAdd(B.next_game_id, P.game_id_stride);
-                trl_game_setup_scalar(rg, id, P.seed);
+                trl_game_setup_scalar(rg, id, P.seed, rg->ruleset);   // the restarted game keeps its ruleset
             } else {
                 ctl->active = 0;
             }

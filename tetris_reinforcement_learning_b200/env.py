@@ -6,14 +6,17 @@ the device).  No CPU implementation: without libtrl_b200.so these raise.
 import numpy as np
 
 from . import _native
-from .state import GAME_DTYPE, STEPOUT_DTYPE
+from .state import GAME_DTYPE, STEPOUT_DTYPE, ruleset_id
+
+_RULESET_BYTE = GAME_DTYPE.fields["ruleset"][1]   # offset of TrlGame.ruleset (385)
 
 
-def game_setup_host(n, first_game_id=0, seed=0, id_stride=1):
-    """n fresh games after Game.setup() (game.py:28-32) -> GAME_DTYPE[n]."""
+def game_setup_host(n, first_game_id=0, seed=0, id_stride=1, ruleset="s2"):
+    """n fresh games after Game(ruleset).setup() (game.py:8-32) -> GAME_DTYPE[n]."""
     games = np.zeros(n, dtype=GAME_DTYPE)
     rc = _native.lib().trl_game_setup_host(games.ctypes.data, n, int(first_game_id), int(id_stride), int(seed))
     _native.check(rc, "trl_game_setup_host")
+    games["ruleset"] = ruleset_id(ruleset)
     return games
 
 
@@ -35,12 +38,13 @@ def env_step_host(games, moves, add_bag=True, seed=0):
     return out
 
 
-def game_setup_device(games, first_game_id=0, seed=0, id_stride=1):
+def game_setup_device(games, first_game_id=0, seed=0, id_stride=1, ruleset="s2"):
     """games: uint8[n,400] CUDA tensor, filled in place on the current stream."""
     import torch
     rc = _native.lib().trl_game_setup(games.data_ptr(), games.shape[0], int(first_game_id), int(id_stride), int(seed),
                                       torch.cuda.current_stream().cuda_stream)
     _native.check(rc, "trl_game_setup")
+    games.view(games.shape[0], GAME_DTYPE.itemsize)[:, _RULESET_BYTE] = ruleset_id(ruleset)
 
 
 def env_step_device(games, moves, out=None, add_bag=True, seed=0):

@@ -93,8 +93,8 @@ class SelfPlayEngine:
     def __init__(self, config, evaluator, n_games, device="cuda:0", seed=0, first_game_id=0, game_id_stride=1,
                  feature_dtype=torch.float32, node_cap=None, sample_cap=None, restart_finished=True, save_all=None,
                  max_rounds=None, use_cuda_graph=True, overlap_movegen=True, reuse_trunk_features=True):
-        if config.ruleset != "s2":
-            raise NotImplementedError("only ruleset 's2' is implemented on the device path")
+        from .state import ruleset_id
+        self.ruleset = ruleset_id(config.ruleset)   # 's2' (default) or 's1': attack table + all-spin rule
         if config.move_algorithm != "convolutional":
             raise NotImplementedError("only move_algorithm='convolutional' is implemented on the device path")
         self.lib = _native.lib()
@@ -154,6 +154,7 @@ class SelfPlayEngine:
         rc = self.lib.trl_game_setup(games.data_ptr(), self.G, int(first_game_id), int(stride), self.seed,
                                      torch.cuda.current_stream(self.device).cuda_stream)
         _native.check(rc, "trl_game_setup")
+        games[:, GAME_DTYPE.fields["ruleset"][1]] = self.ruleset   # restarted games inherit it (mcts.cu)
         self.t["next_game_id"].fill_(int(first_game_id + self.G * stride))
         ctl = np.zeros(self.G, dtype=CTL_DTYPE)
         ctl["active"] = 1

@@ -22,7 +22,7 @@ PLAYER_DTYPE = np.dtype({
 })
 
 GAME_DTYPE = np.dtype({
-    "names": ["players", "turn", "pad_", "bag_ctr", "rounds", "rng_ctr", "game_id"],
+    "names": ["players", "turn", "ruleset", "bag_ctr", "rounds", "rng_ctr", "game_id"],
     "formats": [(PLAYER_DTYPE, (2,)), "u1", "u1", "<u2", "<u4", "<u4", "<u4"],
     "offsets": [0, 384, 385, 386, 388, 392, 396],
     "itemsize": 400,
@@ -36,6 +36,16 @@ STEPOUT_DTYPE = np.dtype({
 })
 
 _PIECE_ID = {m: i for i, m in enumerate(MINOS)}
+
+
+RULESETS = {"s2": 0, "s1": 1}   # TRL_RULESET_S2 / TRL_RULESET_S1 (include/trl.h)
+
+
+def ruleset_id(ruleset):
+    """'s2' / 's1' (Config.ruleset, ai.py:72) -> the byte stored in TrlGame.ruleset."""
+    if ruleset not in RULESETS:
+        raise ValueError(f"unknown ruleset {ruleset!r} (expected 's1' or 's2')")
+    return RULESETS[ruleset]
 
 
 def piece_id(piece_type):
@@ -111,6 +121,7 @@ def pack_game(game, game_id=0, rng_ctr=0, bag_ctr=0, out=None):
     for i in range(2):
         pack_player(game.players[i], out=rec["players"][i])
     rec["turn"] = game.turn
+    rec["ruleset"] = ruleset_id(getattr(game, "ruleset", "s2"))
     hist = getattr(game, "history", None)
     rec["rounds"] = len(hist.states) if hist is not None and hasattr(hist, "states") else 0
     rec["rng_ctr"] = rng_ctr
@@ -190,7 +201,6 @@ def canonical_games(games):
     p["queue"][qi[None, None, :] >= p["qlen"][..., None]] = 0
     p["recv"][ri[None, None, :] >= p["n_recv"][..., None]] = 0
     p["pad_"] = 0
-    g["pad_"] = 0
     return g
 
 
