@@ -24,6 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+NCU_DRAM_BYTES_PER_CALL = 1.0206e9 / 700000  # measured DRAM traffic of movegen_warp_kernel (profiles/r1_summary.md)
 ALGO_BYTES_PER_CALL = 80 + 4 + 1448  # board + (cur, alt, pad) in, bit-packed (27,39,11) mask out
 METRIC = "placements/sec (movegen)"
 UNIT = "placements/s"
@@ -405,7 +406,10 @@ def run_ours(args, rank, world, local_rank):
                    "placements_per_step_per_gpu": placements, "l2": "inputs+outputs (>10 GB/step) exceed the 126 MB L2",
                    "status_nonzero": bad_status},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "movegen_warp_kernel",
+                     "traffic": int(NCU_DRAM_BYTES_PER_CALL * n), "traffic_unit": "bytes per launch",
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum = 1.0206e9 B for a 700 000-call "
+                                       "launch (profiles/r1_summary.md), scaled to this launch's call count",
+                     "peak_source": peak_src, "kernel": "movegen_warp_kernel",
                      "algorithmic_bytes_per_call": ALGO_BYTES_PER_CALL, "kernel_ms": kern_ms,
                      "note": "integer-issue bound, not HBM bound (SURVEY §8d): see profiles/ for issue utilisation"},
         "e2e": {"value": placements_all / e2e_list_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_list,

@@ -1,0 +1,37 @@
+"""Small workload for compute-sanitizer (memcheck / racecheck / synccheck):
+    compute-sanitizer --tool memcheck python tools/sanitize_smoke.py [movegen|trunk|engine]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tetris_reinforcement_learning_b200 import architectures as arch, move_generation, synth, trunk  # noqa: E402
+from tetris_reinforcement_learning_b200.config import Config  # noqa: E402
+from tetris_reinforcement_learning_b200.selfplay import SelfPlayEngine  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+if what in ("movegen", "all"):
+    boards, cur, alt = synth.movegen_workload(40, seed=3, caves=True)
+    res = move_generation.movegen_host(boards, cur, alt, want_mask=True, want_moves=True)
+    res2 = move_generation.movegen_host_compact(boards, cur, alt)
+    print("movegen ok", int(res["n_moves"].sum()), res2["total"])
+if what in ("trunk", "all"):
+    torch.manual_seed(0)
+    net = arch.AlphaSame(arch.AlphaSameConfig(blocks=2)).to("cuda:0").eval()
+    packed = trunk.pack_alphasame_trunk(net)
+    g = (torch.rand((11, 1, 40, 10), device="cuda:0") < 0.3).to(torch.bfloat16)
+    out = trunk.trunk_forward(packed, g)
+    torch.cuda.synchronize()
+    print("trunk ok", float(out.float().abs().sum()))
+if what in ("engine", "all"):
+    torch.manual_seed(0)
+    mc = arch.AlphaSameConfig(blocks=2)
+    net = arch.AlphaSame(mc).to("cuda:0")
+    cfg = Config(visual=False, ruleset="s2", model="pytorch", model_config=mc, MAX_ITER=4, training=True)
+    eng = SelfPlayEngine(cfg, trunk.make_fused_evaluator(net), 16, seed=1, feature_dtype=torch.bfloat16, max_rounds=3,
+                         use_cuda_graph=False)
+    eng.step(40)
+    s, e = eng.drain()
+    print("engine ok", len(s), len(e), int(eng.get_ctl()["status"].max()))
