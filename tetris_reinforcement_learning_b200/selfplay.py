@@ -269,64 +269,6 @@ class SelfPlayEngine:
         return int(self.get_ctl()["sims"].sum())
 
 
-class PipelinedSelfPlay:
-    """`n_games` self-play games on one GPU as `ways` independent SelfPlayEngines whose steps are
-    captured side by side in ONE CUDA graph (one forked stream per engine): while the tensor cores
-    run the network of one engine, the integer kernels of the search (select, movegen, feature
-    encoding, expand) of the other engine fill the rest of the SMs.  Games stay independent, ids
-    interleave (engine k owns first_game_id + k*stride, + ways*stride, ...), so the set of games and
-    every game's random streams are the same as with a single engine."""
-
-    def __init__(self, config, evaluator, n_games, ways=2, device="cuda:0", seed=0, first_game_id=0, game_id_stride=1, **kw):
-        assert n_games % ways == 0
-        self.device = torch.device(device)
-        self.engines = [SelfPlayEngine(config, evaluator, n_games // ways, device=device, seed=seed,
-                                       first_game_id=first_game_id + k * game_id_stride,
-                                       game_id_stride=ways * game_id_stride, use_cuda_graph=False, **kw)
-                        for k in range(ways)]
-        self.G = n_games
-        self.streams = [torch.cuda.Stream(self.device) for _ in self.engines]
-        self._graph = None
-        self.steps_done = 0
-
-    def _step_all(self):
-        main = torch.cuda.current_stream(self.device)
-        for eng, st in zip(self.engines, self.streams):
-            st.wait_stream(main)
-            with torch.cuda.stream(st):
-                eng._step_eager()
-        for st in self.streams:
-            main.wait_stream(st)
-
-    def step(self, n=1):
-        if self._graph is None:
-            warm = torch.cuda.Stream(self.device)
-            warm.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(warm):
-                for _ in range(2):
-                    self._step_all()
-            torch.cuda.current_stream(self.device).wait_stream(warm)
-            self.steps_done += 2
-            n -= 2
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._step_all()
-            self._graph = g
-        for _ in range(max(n, 0)):
-            self._graph.replay()
-        self.steps_done += max(n, 0)
-
-    def drain(self):
-        parts = [e.drain() for e in self.engines]
-        return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
-
-    def get_ctl(self):
-        return np.concatenate([e.get_ctl() for e in self.engines])
-
-    def total_sims(self):
-        return sum(e.total_sims() for e in self.engines)
-
-
 def best_evaluator(net, dtype=torch.bfloat16):
     """The fastest evaluator for `net`: the fused tcgen05 trunk + PyTorch heads where the
     architecture allows it (AlphaSame, 16 filters), else the plain PyTorch path."""

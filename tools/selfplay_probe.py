@@ -79,17 +79,6 @@ def main():
         print(f"engine step (graph={graph}): {ms:.3f} ms device, {wall:.3f} ms wall -> {G / ms * 1e3:.3e} sims/s; "
               f"samples {len(samples)}, game ends {len(ends)}, status {int(ctl['status'].max())}, "
               f"max nodes {int(ctl['n_nodes'].max())}, max depth {int(ctl['max_depth'].max())}")
-    from tetris_reinforcement_learning_b200.selfplay import PipelinedSelfPlay
-    for ways in (2, 4):
-        eng = PipelinedSelfPlay(cfg, ev, G, ways=ways, seed=1, feature_dtype=dt)
-        eng.step(10)
-        torch.cuda.synchronize()
-        e0.record()
-        eng.step(args.steps)
-        e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
-        ctl = eng.get_ctl()
-        print(f"pipelined x{ways}: {ms:.3f} ms per step of {G} games -> {G / ms * 1e3:.3e} sims/s; status {int(ctl['status'].max())}")
     # parts, eager with events
     import ctypes
     from tetris_reinforcement_learning_b200 import _native
