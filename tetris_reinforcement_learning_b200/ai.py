@@ -262,6 +262,7 @@ def _engine_for(config, net, n_games, seed=None, **kw):
     else:
         import copy
         evaluator = best_evaluator(copy.deepcopy(net).to("cuda"), dtype)  # the caller's module is left untouched
+    kw.setdefault("device", torch.device("cuda", torch.cuda.current_device()))   # one process per GPU: the current device
     return SelfPlayEngine(config, evaluator, n_games, seed=seed, feature_dtype=dtype, **kw)
 
 
