@@ -151,6 +151,7 @@ def run_selfplay(args, rank, world, local_rank):
         return e0.elapsed_time(e1)
 
     eng = engine(160)
+    eng_flags = eng
     reuse = eng.cached_eval is not None
     ms = timed(eng)
     samples, _ = eng.drain()
@@ -161,7 +162,7 @@ def run_selfplay(args, rank, world, local_rank):
         # the same step with BOTH boards of every leaf through the trunk (the reference's amount of work)
         del eng
         torch.cuda.empty_cache()
-        eng2 = engine(160, reuse_trunk_features=False)
+        eng2 = engine(160, reuse_trunk_features=False, reuse_sibling_placements=False)
         ms_both = timed(eng2)
         del eng2
         torch.cuda.empty_cache()
@@ -209,12 +210,14 @@ def run_selfplay(args, rank, world, local_rank):
             "value": sims_per_s, "unit": "sims/s", "games_per_gpu": G, "n_gpus": world, "steps": args.selfplay_steps,
             "ms_per_step": ms / args.selfplay_steps, "max_iter": 160, "net": "AlphaSame(blocks=10, filters=16) bf16, " + ("PyTorch/cuDNN" if args.net_path == "pytorch" else
                                                                "row-Toeplitz tcgen05 trunk + fused heads kernel + cuBLAS policy GEMM") + ", CUDA graph",
-            "trunk_feature_reuse": reuse,
+            "trunk_feature_reuse": reuse, "sibling_placement_reuse": bool(getattr(eng_flags, "reuse_sibling_placements", False)),
             "trunk_feature_reuse_note": "exact: a move changes only the mover's board, so per simulation one board goes through the "
                                         "trunk and the other board's features are the parent state's (bit-identical searches, "
                                         "tests/test_gpu_trunk.py::test_trunk_feature_reuse_is_exact)",
-            "value_both_boards_through_trunk": (sims / (ms_both * 1e-3)) if ms_both else None,
-            "ms_per_step_both_boards": (ms_both / args.selfplay_steps) if ms_both else None,
+            "value_without_reuse": (sims / (ms_both * 1e-3)) if ms_both else None,
+            "ms_per_step_without_reuse": (ms_both / args.selfplay_steps) if ms_both else None,
+            "without_reuse_note": "both boards of every leaf through the trunk and legal placements enumerated for every leaf "
+                                  "(the amount of work the reference does per simulation)",
             "searches_finished": nsamples, "status_nonzero": int((ctl["status"] != 0).sum()),
             "roofline": {"bound": "tensor", "achieved": sims_per_s / world * flops_done / 1e12,
                          "peak": load_tensor_peak(), "unit": "TFLOP/s",

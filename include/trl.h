@@ -317,6 +317,14 @@ typedef struct TrlSearchBuffers {
     const double* noise_override;            /* [n_games * moves_cap] or NULL (tests)       */
     int32_t* leaf_parent;                    /* [n_games] state index of the leaf's parent, -1 = the leaf is
                                                 the root / nothing to evaluate (may be NULL)            */
+    /* Exact reuse of legal-placement lists between siblings (all three NULL = off).  A move changes
+     * neither the OTHER player's board nor its pieces (player.py:109-188, game.py:66-118), so every
+     * child of a state has the same side-to-move board / piece / hold and hence the same
+     * get_move_matrix: the list is enumerated for the first child that becomes a leaf and stored
+     * under the parent state. */
+    uint16_t* legal_cache;                   /* [n_games * state_cap * moves_cap]                        */
+    int32_t* legal_cache_n;                  /* [n_games * state_cap] number of cached moves, -1 = none  */
+    int32_t* movegen_index;                  /* [n_games] state to enumerate this step or -1 (cache hit)  */
 } TrlSearchBuffers;
 
 int trl_sizeof_search_ctl(void);
@@ -327,7 +335,8 @@ int trl_sizeof_sample(void);
  * (if leaf_parent != NULL) leaf_parent[g] = index of the state it was reached from, or -1. */
 int trl_search_select(const TrlSearchBuffers* buf, const TrlSearchParams* prm, void* stream);
 
-/* Legal placements for the selected leaves: trl_movegen_games on states[leaf_state[g]]. */
+/* Legal placements for the selected leaves: trl_movegen_games on states[leaf_state[g]] (with the
+ * sibling cache: only on states[movegen_index[g]], the leaves whose parent has no list yet). */
 int trl_search_movegen(const TrlSearchBuffers* buf, void* stream);
 
 /* Step part 2: expand the leaf with the network outputs (values [n_games], logits

@@ -69,6 +69,39 @@ def test_fused_evaluator_matches_module_and_runs_in_engine():
     assert len(samples) > 0 and len(ends) > 0 and (eng.get_ctl()["status"] == 0).all()
 
 
+def test_sibling_placement_reuse_is_exact():
+    """All children of a state share the side to move's board and pieces, so the engine enumerates the
+    legal placements once per PARENT and reuses the list for the siblings: searches must be bit-identical
+    to enumerating for every leaf."""
+    import copy
+    import torch
+    from tetris_reinforcement_learning_b200 import architectures as arch, trunk
+    from tetris_reinforcement_learning_b200.config import Config
+    from tetris_reinforcement_learning_b200.selfplay import SelfPlayEngine
+    net = _random_net(2, 9)
+    ev = trunk.make_fused_evaluator(copy.deepcopy(net))
+    cfg = Config(visual=False, ruleset="s2", model="pytorch", model_config=arch.AlphaSameConfig(blocks=2), MAX_ITER=24,
+                 training=True, use_forced_playouts_and_policy_target_pruning=True)
+    out = []
+    for reuse in (True, False):
+        eng = SelfPlayEngine(cfg, ev, 96, seed=4, feature_dtype=torch.bfloat16, max_rounds=5, sample_cap=16384,
+                             reuse_sibling_placements=reuse)
+        eng.step(700)
+        samples, ends = eng.drain()
+        hits = None
+        if reuse:
+            hits = int((eng.t["legal_cache_n"] >= 0).sum())
+        out.append((samples, ends, eng.get_ctl(), hits))
+    (s0, e0, c0, hits), (s1, e1, c1, _) = out
+    assert hits > 0 and len(s0) > 100 and len(s0) == len(s1) and len(e0) == len(e1) and len(e0) > 0
+    s0, s1 = (np.sort(s, order=["game_id", "search_no"]) for s in (s0, s1))
+    e0, e1 = (np.sort(e, order=["game_id"]) for e in (e0, e1))
+    for name in s0.dtype.names:
+        assert np.array_equal(s0[name], s1[name]), name
+    assert e0.tobytes() == e1.tobytes()
+    assert (c0["status"] == 0).all() and (c1["status"] == 0).all()
+
+
 def test_trunk_feature_reuse_is_exact():
     """The engine with trunk-feature reuse (only the board changed by the last move goes through the
     trunk) must produce bit-identical searches to the engine that evaluates both boards of every leaf."""

@@ -11,7 +11,7 @@ from .state import GAME_DTYPE, PLAYER_DTYPE
 _SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtrl_b200.so")
 _lib = None
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 c_void_p, c_int, c_u64, c_u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32
 
@@ -104,4 +104,5 @@ class SearchBuffers(ctypes.Structure):
                                                "states", "first_child", "n_children", "fpu",
                                                "ctl", "games", "leaf_state", "legal", "n_legal",
                                                "samples", "sample_count", "ends", "end_count",
-                                               "next_game_id", "noise_override", "leaf_parent")]
+                                               "next_game_id", "noise_override", "leaf_parent",
+                                               "legal_cache", "legal_cache_n", "movegen_index")]

@@ -25,7 +25,7 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 
 static_assert(sizeof(TrlSearchCtl) == 80, "TrlSearchCtl layout");
 static_assert(sizeof(TrlSearchParams) == 152, "TrlSearchParams layout");
-static_assert(sizeof(TrlSearchBuffers) == 208, "TrlSearchBuffers layout");
+static_assert(sizeof(TrlSearchBuffers) == 232, "TrlSearchBuffers layout");
 static_assert(sizeof(TrlGameEnd) == 32, "TrlGameEnd layout");
 static_assert(sizeof(TrlSample) == 20 + 400 + 3 * 2 * TRL_SAMPLE_MOVES, "TrlSample layout");
 
@@ -105,7 +105,11 @@ search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
     if (g >= B.n_games) return;
     TrlSearchCtl* ctl = &B.ctl[g];
     if (!ctl->active) {
-        if (lane == 0) { B.leaf_state[g] = -1; ctl->leaf_kind = 3; if (B.leaf_parent) B.leaf_parent[g] = -1; }
+        if (lane == 0) {
+            B.leaf_state[g] = -1; ctl->leaf_kind = 3;
+            if (B.leaf_parent) B.leaf_parent[g] = -1;
+            if (B.movegen_index) B.movegen_index[g] = -1;
+        }
         return;
     }
     const size_t nb = (size_t)g * B.node_cap, sb = (size_t)g * B.state_cap;
@@ -122,6 +126,7 @@ search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
             B.parent[nb] = -1; B.slot[nb] = 0; B.visits[nb] = 0; B.value_sum[nb] = 0.0; B.prior[nb] = 0.0;
             B.move[nb] = 0xFFFF;
             B.first_child[sb] = -1; B.n_children[sb] = 0; B.fpu[sb] = 0.0;
+            if (B.legal_cache_n) B.legal_cache_n[sb] = -1;
             ctl->n_nodes = 1; ctl->n_states = 1; ctl->garbage_ctr = 0; ctl->max_depth = 0;
             int iters = P.max_iter;
             uint32_t fast = 0;
@@ -183,6 +188,7 @@ search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
             if (B.slot[nb + node] < 0) {
                 B.slot[nb + node] = s;
                 B.first_child[sb + s] = -1; B.n_children[sb + s] = 0; B.fpu[sb + s] = 0.0;
+                if (B.legal_cache_n) B.legal_cache_n[sb + s] = -1;   // no child of this state has been enumerated yet
                 ctl->n_states = s + 1;
             }
         }
@@ -209,6 +215,11 @@ search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
         if (depth > ctl->max_depth) ctl->max_depth = depth;
         B.leaf_state[g] = (kind == 2) ? -1 : (int)(sb + s);
         if (B.leaf_parent) B.leaf_parent[g] = (kind == 2) ? -1 : parent_state;
+        if (B.movegen_index) {
+            // all children of a state share the side to move's board and pieces: enumerate once per parent
+            const bool hit = B.legal_cache_n && parent_state >= 0 && B.legal_cache_n[parent_state] >= 0;
+            B.movegen_index[g] = (kind == 2 || hit) ? -1 : (int)(sb + s);
+        }
     }
 }
 
@@ -389,7 +400,23 @@ search_expand_kernel(TrlSearchBuffers B, TrlSearchParams P, const void* __restri
         value = ctl->leaf_value;
     } else {
         value = (double)load_out(values, (size_t)g, dtype);
+        // legal placements: enumerated this step, or the list stored under the parent state by a sibling
+        const uint16_t* mv = B.legal + (size_t)g * B.moves_cap;
         int C = (kind == 0) ? (int)B.n_legal[g] : 0;
+        if (B.legal_cache_n && B.movegen_index && leaf != 0) {
+            const size_t pstate = sb + (size_t)B.slot[nb + B.parent[nb + leaf]];
+            const int cached = B.legal_cache_n[pstate];
+            uint16_t* slot_mv = B.legal_cache + pstate * (size_t)B.moves_cap;
+            if (cached >= 0) {
+                mv = slot_mv;
+                C = (kind == 0) ? cached : 0;
+            } else {
+                const int n_store = min((int)B.n_legal[g], B.moves_cap);
+                for (int c = lane; c < n_store; c += 32) slot_mv[c] = mv[c];
+                __syncwarp();
+                if (lane == 0) B.legal_cache_n[pstate] = n_store;
+            }
+        }
         if (C > B.moves_cap) C = B.moves_cap;
         if (C > 0 && ctl->n_nodes + C > B.node_cap) {  // arena full: the leaf stays childless
             C = 0;
@@ -398,7 +425,6 @@ search_expand_kernel(TrlSearchBuffers B, TrlSearchParams P, const void* __restri
         if (C > 0) {
             // priors over the legal moves (ai.py:411-443).  softmax over all 11583 logits followed
             // by renormalisation over the legal ones == softmax over the legal logits.
-            const uint16_t* mv = B.legal + (size_t)g * B.moves_cap;
             const size_t lb = (size_t)g * (size_t)logits_stride;
             double mx = -INFINITY;
             for (int c = lane; c < C; c += 32) mx = fmax(mx, (double)load_out(logits, lb + mv[c], dtype));
@@ -504,8 +530,8 @@ int trl_movegen_indexed(const TrlGame* games, const int32_t* index, int n, uint1
 
 extern "C" int trl_search_movegen(const TrlSearchBuffers* buf, void* stream) {
     if (!buffers_ok(buf)) return TRL_E_ARG;
-    return trl_movegen_indexed(buf->states, buf->leaf_state, buf->n_games, buf->legal, buf->moves_cap, buf->n_legal,
-                               (cudaStream_t)stream);
+    return trl_movegen_indexed(buf->states, buf->movegen_index ? buf->movegen_index : buf->leaf_state, buf->n_games,
+                               buf->legal, buf->moves_cap, buf->n_legal, (cudaStream_t)stream);
 }
 
 extern "C" int trl_search_expand(const TrlSearchBuffers* buf, const TrlSearchParams* prm, const void* values,

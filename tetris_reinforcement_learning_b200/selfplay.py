@@ -92,7 +92,8 @@ class SelfPlayEngine:
 
     def __init__(self, config, evaluator, n_games, device="cuda:0", seed=0, first_game_id=0, game_id_stride=1,
                  feature_dtype=torch.float32, node_cap=None, sample_cap=None, restart_finished=True, save_all=None,
-                 max_rounds=None, use_cuda_graph=True, overlap_movegen=True, reuse_trunk_features=True):
+                 max_rounds=None, use_cuda_graph=True, overlap_movegen=True, reuse_trunk_features=True,
+                 reuse_sibling_placements=True):
         from .state import ruleset_id
         self.ruleset = ruleset_id(config.ruleset)   # 's2' (default) or 's1': attack table + all-spin rule
         if config.move_algorithm != "convolutional":
@@ -128,6 +129,12 @@ class SelfPlayEngine:
             "ends": z(self.end_cap * GAME_END_DTYPE.itemsize, torch.uint8), "end_count": z(1, torch.int32),
             "next_game_id": z(1, torch.int32), "leaf_parent": z(G, torch.int32),
         }
+        # exact reuse of legal-placement lists between siblings (include/trl.h, TrlSearchBuffers.legal_cache)
+        self.reuse_sibling_placements = bool(reuse_sibling_placements)
+        if self.reuse_sibling_placements:
+            self.t["legal_cache"] = z(ns * self.moves_cap, torch.int16)
+            self.t["legal_cache_n"] = torch.full((ns,), -1, dtype=torch.int32, device=dev)
+            self.t["movegen_index"] = z(G, torch.int32)
         fdt = feature_dtype
         self.grids = torch.zeros((2 * G, 1, 40, 10), dtype=fdt, device=dev)
         self.extras = torch.zeros((G, 105), dtype=fdt, device=dev)
