@@ -401,8 +401,9 @@ int trl_encode_features_cached(const TrlGame* states, const int32_t* leaf_state,
                                void* extras_bf16, int32_t* own_row, int32_t* opp_row, void* stream);
 
 /* trl_alphasame_trunk_rows with a device-side image count and scattered output rows:
- * out_bf16[out_row[k]][400] = trunk(images[k]) for k < *n_images_dev (capacity max_images). */
-int trl_alphasame_trunk_rows_indexed(const void* images_bf16, const int32_t* n_images_dev, int max_images,
+ * out_bf16[out_row[k]][400] = trunk(images[k]) for k < *n_images_dev (capacity max_images).
+ * The kernel resets *n_images_dev to 0 when it has consumed it (no memset per step). */
+int trl_alphasame_trunk_rows_indexed(const void* images_bf16, int32_t* n_images_dev, int max_images,
                                      const int32_t* out_row, int n_blocks, const void* w_packed, const float* consts,
                                      const void* stem_w, void* out_bf16, void* stream);
 

@@ -25,6 +25,7 @@ void* trl_workspace(int slot, size_t bytes) {
     if (g_ws_ptr[slot]) { cudaFree(g_ws_ptr[slot]); g_ws_ptr[slot] = nullptr; g_ws_size[slot] = 0; }
     void* p = nullptr;
     if (trl_check(cudaMalloc(&p, bytes)) != TRL_OK) return nullptr;
+    if (trl_check(cudaMemset(p, 0, bytes)) != TRL_OK) { cudaFree(p); return nullptr; }   // counters start at zero
     g_ws_ptr[slot] = p;
     g_ws_size[slot] = bytes;
     return p;

@@ -197,8 +197,9 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
                             const __grid_constant__ TrunkConsts consts,   // [n_blocks*48 + 50]
                             const uint4* __restrict__ stem_w,     // [5][2][20][8][8] bf16
                             __nv_bfloat16* __restrict__ out,      // [n_images][400]
-                            int* __restrict__ next_group,         // work counter (zeroed before launch)
-                            const int* __restrict__ n_images_dev, // optional: device-side image count (<= n_images)
+                            int* __restrict__ next_group,         // [0] work counter, [1] finished CTAs; both zero on entry,
+                                                                  // re-zeroed by the last CTA (no memset node per launch)
+                            int* __restrict__ n_images_dev,       // optional: device-side image count (<= n_images); reset to 0 at the end
                             const int* __restrict__ out_row,      // optional: output row of image k (default k)
                             long long* __restrict__ trace) {      // optional [pseudo-layer][column][4] clock stamps (CTA 0, first group, lane 0)
     extern __shared__ __align__(128) uint8_t smem[];
@@ -428,6 +429,15 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
     if (warp == kEpiWarps) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(kTmemCols));
     }
+    if (tid == 0) {   // the last CTA to finish leaves the counters at zero for the next launch that uses this slot
+        __threadfence();
+        if (atomicAdd(next_group + 1, 1) == (int)gridDim.x - 1) {
+            next_group[0] = 0;
+            next_group[1] = 0;
+            if (n_images_dev) *n_images_dev = 0;   // consumed: the next step's feature encoder appends from zero
+            __threadfence();
+        }
+    }
 }
 
 }  // namespace
@@ -478,17 +488,15 @@ extern "C" int trl_alphasame_trunk_rows(const void* grids_bf16, int n_images, in
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_units = ((n_images + kImgs - 1) / kImgs + n_lanes - 1) / n_lanes;
     int grid = sms < n_units ? sms : n_units;   // one persistent CTA per SM (it owns all 512 TMEM columns)
-    int* counter = next_counter();
+    int* counter = next_counter();   // zero on entry: the previous launch on this slot reset it
     if (!counter) return TRL_E_NOMEM;
-    int rc = trl_check(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
-    if (rc) return rc;
     alphasame_trunk_rows_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)grids_bf16, n_images, n_blocks, n_lanes, (const uint4*)w_packed, host_consts(consts, n_blocks), (const uint4*)stem_w,
         (__nv_bfloat16*)out_bf16, counter, nullptr, nullptr, g_trace);
     return trl_check(cudaGetLastError());
 }
 
-extern "C" int trl_alphasame_trunk_rows_indexed(const void* images_bf16, const int32_t* n_images_dev, int max_images,
+extern "C" int trl_alphasame_trunk_rows_indexed(const void* images_bf16, int32_t* n_images_dev, int max_images,
                                                 const int32_t* out_row, int n_blocks, const void* w_packed,
                                                 const float* consts, const void* stem_w, void* out_bf16, void* stream) {
     if (max_images < 0 || n_blocks < 1 || n_blocks > kMaxBlocks || !images_bf16 || !n_images_dev || !out_row || !w_packed ||
@@ -504,10 +512,8 @@ extern "C" int trl_alphasame_trunk_rows_indexed(const void* images_bf16, const i
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_units = ((max_images + kImgs - 1) / kImgs + n_lanes - 1) / n_lanes;
     const int grid = sms < n_units ? sms : n_units;
-    int* counter = next_counter();
+    int* counter = next_counter();   // zero on entry: the previous launch on this slot reset it
     if (!counter) return TRL_E_NOMEM;
-    rc = trl_check(cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream));
-    if (rc) return rc;
     alphasame_trunk_rows_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)images_bf16, max_images, n_blocks, n_lanes, (const uint4*)w_packed, host_consts(consts, n_blocks), (const uint4*)stem_w,
         (__nv_bfloat16*)out_bf16, counter, n_images_dev, out_row, g_trace);

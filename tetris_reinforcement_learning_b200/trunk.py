@@ -204,8 +204,7 @@ class CachedTrunkEvaluator:
         dev = extras.device
         G = leaf_state.numel()
         b = self._bufs(states.data_ptr(), states.numel() // 400, G, dev)
-        st = torch.cuda.current_stream(dev).cuda_stream
-        b["count"].zero_()
+        st = torch.cuda.current_stream(dev).cuda_stream   # b["count"] is zero here: the trunk kernel resets it
         _native.check(lib.trl_encode_features_cached(
             states.data_ptr(), leaf_state.data_ptr(), leaf_parent.data_ptr(), G, b["cache"].data_ptr(),
             b["images"].data_ptr(), b["dest"].data_ptr(), b["count"].data_ptr(), extras.data_ptr(),
