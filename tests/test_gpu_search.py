@@ -174,13 +174,14 @@ def test_search_tree_invariants_and_selfplay_with_network():
     assert (ctl["status"] & ~np.uint32(0)).max() == 0
 
 
-def test_engine_is_deterministic_and_matches_oracle_env():
+@pytest.mark.parametrize("ruleset", ["s2", "s1"])
+def test_engine_is_deterministic_and_matches_oracle_env(ruleset):
     """Two engines with the same seed produce identical games; every recorded position replays
-    through the CPU oracle (positions + chosen moves form a legal trajectory)."""
+    through the CPU oracle (positions + chosen moves form a legal trajectory), under both rulesets."""
     import torch
     from oracle import oracle
     from tetris_reinforcement_learning_b200.selfplay import SelfPlayEngine
-    cfg = Config(visual=False, ruleset="s2", model="pytorch", MAX_ITER=8, training=True)
+    cfg = Config(visual=False, ruleset=ruleset, model="pytorch", MAX_ITER=8, training=True)
     outs = []
     for _ in range(2):
         eng = SelfPlayEngine(cfg, fake_evaluator_torch(torch.device("cuda:0")), 32, seed=5, save_all=True,
@@ -196,7 +197,7 @@ def test_engine_is_deterministic_and_matches_oracle_env():
     assert k1 == k2
     # replay game 0 through the oracle
     mine = sorted([s for s in s1 if int(s["game_id"]) == 0], key=lambda s: int(s["search_no"]))
-    shadow = oracle.game_setup(1, 0, 5)
+    shadow = oracle.game_setup(1, 0, 5, ruleset=ruleset)
     for s in mine:
         root = np.array([s["state"]], dtype=GAME_DTYPE)
         trunc = shadow.copy()
