@@ -147,6 +147,7 @@ class SelfPlayEngine:
         b.noise_override = None
         b.leaf_parent = self.t["leaf_parent"].data_ptr()
         self.buf = b
+        self._cache_bufs = self.cached_eval.make_buffers(ns, G, dev) if self.cached_eval is not None else None
         assert self.lib.trl_sizeof_search_ctl() == CTL_DTYPE.itemsize and self.lib.trl_sizeof_sample() == SAMPLE_DTYPE.itemsize
         self._graph = None
         self._side = None
@@ -214,7 +215,7 @@ class SelfPlayEngine:
             fork_movegen()
         if self.cached_eval is not None:
             with torch.no_grad():
-                values, logits = self.cached_eval(self.t["states"], self.t["leaf_state"], self.t["leaf_parent"], self.extras,
+                values, logits = self.cached_eval(self._cache_bufs, self.t["states"], self.t["leaf_state"], self.t["leaf_parent"], self.extras,
                                                   after_trunk=fork_movegen if mode == "heads" else None)
         else:
             dt = 0 if self.feature_dtype == torch.float32 else 1

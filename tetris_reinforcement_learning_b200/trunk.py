@@ -184,26 +184,22 @@ class CachedTrunkEvaluator:
     def __init__(self, packed, w_heads, use_tanh, w_pol, b_pol, k_pad):
         self.packed, self.w_heads, self.use_tanh = packed, w_heads, use_tanh
         self.w_pol, self.b_pol, self.k_pad = w_pol, b_pol, k_pad
-        self.buffers = {}
 
-    def _bufs(self, states_ptr, n_states, n_leaves, device):
-        key = (states_ptr, n_states, n_leaves, str(device))   # one cache per engine (per states array)
-        if key not in self.buffers:
-            z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)  # noqa: E731
-            self.buffers[key] = ({
-                "cache": z((n_states * 2, 400), torch.bfloat16), "images": z((2 * n_leaves, 400), torch.bfloat16),
+    def make_buffers(self, n_states, n_leaves, device):
+        """Per-ENGINE buffers (the engine owns them, so they are freed with it): the feature cache
+        [n_states * 2, 400] and the per-step staging of images, indices, head inputs and values."""
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)  # noqa: E731
+        return {"cache": z((n_states * 2, 400), torch.bfloat16), "images": z((2 * n_leaves, 400), torch.bfloat16),
                 "dest": z(2 * n_leaves, torch.int32), "count": z(1, torch.int32),
                 "own": z(n_leaves, torch.int32), "opp": z(n_leaves, torch.int32),
-                "x": z((n_leaves, self.k_pad), torch.bfloat16), "value": z(n_leaves, torch.bfloat16)})
-        return self.buffers[key]
+                "x": z((n_leaves, self.k_pad), torch.bfloat16), "value": z(n_leaves, torch.bfloat16)}
 
-    def __call__(self, states, leaf_state, leaf_parent, extras, after_trunk=None):
-        """states uint8 [n_states*400], leaf_state / leaf_parent int32 [G], extras bf16 [G,105] (written here)
-        -> (values bf16 [G], logits bf16 [G, 11584])."""
+    def __call__(self, b, states, leaf_state, leaf_parent, extras, after_trunk=None):
+        """b: make_buffers(); states uint8 [n_states*400], leaf_state / leaf_parent int32 [G], extras bf16
+        [G,105] (written here) -> (values bf16 [G], logits bf16 [G, 11584])."""
         lib = _native.lib()
         dev = extras.device
         G = leaf_state.numel()
-        b = self._bufs(states.data_ptr(), states.numel() // 400, G, dev)
         st = torch.cuda.current_stream(dev).cuda_stream   # b["count"] is zero here: the trunk kernel resets it
         _native.check(lib.trl_encode_features_cached(
             states.data_ptr(), leaf_state.data_ptr(), leaf_parent.data_ptr(), G, b["cache"].data_ptr(),
