@@ -54,6 +54,9 @@ GAME_END_DTYPE = np.dtype({
 def search_params_from_config(config, seed=0, restart_finished=True, game_id_stride=1, save_all=None, max_rounds=None):
     """Config (ai.py:97-137) -> TrlSearchParams."""
     from .const import MAX_MOVES
+    if getattr(config, "use_random_starting_moves", False):
+        # reference ai.py:1588-1608 (random opening plies sampled from the raw policy); default False
+        raise NotImplementedError("use_random_starting_moves=True is not implemented on the device path")
     p = _native.SearchParams()
     p.seed = int(seed)
     p.cpuct, p.dpuct, p.fpu_value = float(config.CPUCT), float(config.DPUCT), float(config.FpuValue)
