@@ -254,7 +254,8 @@ typedef struct TrlSearchParams {
     int32_t max_rounds;                /* MAX_MOVES = 1000 (const.py:12)                   */
     int32_t restart_finished;          /* != 0: a finished game is replaced by a fresh one */
     uint32_t game_id_stride;           /* new game id = previous id + stride (ranks interleave) */
-    int32_t pad_;
+    int32_t use_random_start;          /* use_random_starting_moves (ai.py:1588-1608)      */
+    double random_start_scale;         /* 0.04 * DIRICHLET_S: mean of the exponential number of opening plies */
 } TrlSearchParams;
 
 /* Per-game search control block. */
@@ -273,7 +274,8 @@ typedef struct TrlSearchCtl {
     uint64_t sims;                     /* simulations run in this slot                     */
     int32_t lines_sent0, lines_cleared0; /* player 0 totals of the running game (ai.py:1518-1529) */
     double leaf_value;                 /* value of a terminal leaf                         */
-    int32_t max_depth, pad_;
+    int32_t max_depth;
+    int32_t random_left;               /* random opening plies still to play in this game (ai.py:1604-1610) */
 } TrlSearchCtl;
 
 /* One finished search = one training position before augmentation (ai.py:1611-1666). */

@@ -223,3 +223,38 @@ def test_engine_ruleset_s1_runs_and_survives_restarts():
     assert len(ends) > 64 and len(samples) > 0
     assert (eng.get_games()["ruleset"] == 1).all() and (samples["state"]["ruleset"] == 1).all()
     assert (eng.get_ctl()["status"] == 0).all()
+
+
+def test_random_starting_moves(oracle):
+    """use_random_starting_moves (ai.py:1588-1608): every game opens with ceil(Exp(0.04 * DIRICHLET_S)) plies that
+    are one-iteration searches sampled from the raw policy and are not saved; the count per game follows the
+    Philox draw (purpose 6) exactly."""
+    import math
+    import torch
+    from tetris_reinforcement_learning_b200.selfplay import SelfPlayEngine
+    seed, G = 11, 256
+    cfg = Config(visual=False, ruleset="s2", model="pytorch", MAX_ITER=6, training=True, use_random_starting_moves=True,
+                 use_playout_cap_randomization=False)
+    eng = SelfPlayEngine(cfg, fake_evaluator_torch(torch.device("cuda:0")), G, seed=seed, save_all=True,
+                         restart_finished=False, max_rounds=4, use_cuda_graph=False, sample_cap=65536)
+    eng.step(120)
+    samples, _ = eng.drain()
+    assert (eng.get_ctl()["status"] == 0).all()
+    by_game = {}
+    for s in samples:
+        by_game.setdefault(int(s["game_id"]), []).append(s)
+    ks = []
+    for gid in range(G):
+        recs = sorted(by_game[gid], key=lambda r: int(r["search_no"]))
+        u = oracle.uniform(seed, gid, 0, 6, 0)
+        k = int(math.ceil(-1.0 * math.log(1.0 - u)))          # scale = 0.04 * DIRICHLET_S = 1.0
+        ks.append(k)
+        for r in recs:
+            opening = int(r["search_no"]) < k
+            assert int(r["iterations"]) == (1 if opening else cfg.MAX_ITER), (gid, int(r["search_no"]), k)
+            assert int(r["saved"]) == (0 if opening else 1)
+            C = int(r["n_children"])
+            assert int(r["chosen_move"]) in set(int(m) for m in r["moves"][:C])
+            if opening:
+                assert int(r["visits_pre"][:C].sum()) == 0        # the root was expanded, nothing else
+    assert 1.3 < np.mean(ks) < 1.9 and min(ks) >= 1               # E[ceil(Exp(1))] = 1 / (1 - 1/e) = 1.58

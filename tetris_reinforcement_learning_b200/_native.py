@@ -11,7 +11,7 @@ from .state import GAME_DTYPE, PLAYER_DTYPE
 _SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtrl_b200.so")
 _lib = None
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 c_void_p, c_int, c_u64, c_u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32
 
@@ -94,7 +94,8 @@ class SearchParams(ctypes.Structure):
                 ("use_playout_cap", ctypes.c_int32), ("use_noise", ctypes.c_int32), ("use_dirichlet_s", ctypes.c_int32),
                 ("use_forced", ctypes.c_int32), ("use_tanh", ctypes.c_int32), ("save_all", ctypes.c_int32),
                 ("max_rounds", ctypes.c_int32), ("restart_finished", ctypes.c_int32),
-                ("game_id_stride", ctypes.c_uint32), ("pad_", ctypes.c_int32)]
+                ("game_id_stride", ctypes.c_uint32), ("use_random_start", ctypes.c_int32),
+                ("random_start_scale", ctypes.c_double)]
 
 
 class SearchBuffers(ctypes.Structure):

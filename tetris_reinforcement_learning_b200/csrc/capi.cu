@@ -40,7 +40,7 @@ cudaStream_t trl_host_stream(int which) {
     return g_host_stream[which];
 }
 
-extern "C" int trl_abi_version(void) { return 6; }
+extern "C" int trl_abi_version(void) { return 7; }
 extern "C" const char* trl_last_error(void) { return g_err; }
 extern "C" int trl_sizeof_player(void) { return (int)sizeof(TrlPlayer); }
 extern "C" int trl_sizeof_game(void) { return (int)sizeof(TrlGame); }

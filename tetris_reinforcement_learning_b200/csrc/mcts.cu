@@ -24,7 +24,7 @@ constexpr int kGameWords = sizeof(TrlGame) / 4;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 static_assert(sizeof(TrlSearchCtl) == 80, "TrlSearchCtl layout");
-static_assert(sizeof(TrlSearchParams) == 152, "TrlSearchParams layout");
+static_assert(sizeof(TrlSearchParams) == 160, "TrlSearchParams layout");
 static_assert(sizeof(TrlSearchBuffers) == 232, "TrlSearchBuffers layout");
 static_assert(sizeof(TrlGameEnd) == 32, "TrlGameEnd layout");
 static_assert(sizeof(TrlSample) == 20 + 400 + 3 * 2 * TRL_SAMPLE_MOVES, "TrlSample layout");
@@ -130,7 +130,21 @@ search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
             ctl->n_nodes = 1; ctl->n_states = 1; ctl->garbage_ctr = 0; ctl->max_depth = 0;
             int iters = P.max_iter;
             uint32_t fast = 0;
-            if (P.training && P.use_playout_cap) {  // ai.py:323-330
+            if (ctl->search_no == 0) {
+                // play_game's random opening (ai.py:1588-1596): ceil(Exp(0.04 * DIRICHLET_S)) plies sampled from
+                // the raw policy; purpose 6 = the exponential draw (replaces np.random.exponential)
+                int k = 0;
+                if (P.use_random_start) {
+                    const double u = trl_uniform(P.seed, B.games[g].game_id, 0u, 6u, 0u);
+                    const double n = -P.random_start_scale * log(1.0 - u);
+                    k = n > 0.0 ? (int)ceil(n) : 0;
+                }
+                ctl->random_left = k;
+            }
+            if (ctl->random_left > 0) {   // fast_config (ai.py:1597-1601): one iteration, no coin, no noise, not saved
+                iters = 1;
+                fast = 1;
+            } else if (P.training && P.use_playout_cap) {  // ai.py:323-330
                 const double coin = trl_uniform(P.seed, B.games[g].game_id, ctl->search_no, 3u, 0u);
                 if (coin < P.playout_cap_chance) iters = P.iters_long;
                 else { iters = P.iters_short; fast = 1; }
@@ -256,7 +270,19 @@ __device__ void finish_search(const TrlSearchBuffers& B, const TrlSearchParams& 
         // random.choices' accumulate + bisect
         const double temp = P.training ? P.temperature : 0.0;
         if (lane == 0) {
-            if (temp == 0.0) {  // np.argmax: FIRST maximum
+            if (ctl->random_left > 0) {
+                // pick_random_move_by_policy (ai.py:999-1014): random.choices(moves, priors); purpose 7
+                double total = 0.0;
+                for (int c = 0; c < C; ++c) total += B.prior[nb + base + c];
+                const double x = trl_uniform(P.seed, B.games[g].game_id, ctl->search_no, 7u, 0u) * total;
+                double cum = 0.0;
+                chosen = C - 1;
+                for (int c = 0; c < C - 1; ++c) {
+                    cum += B.prior[nb + base + c];
+                    if (cum > x) { chosen = c; break; }
+                }
+                ctl->random_left -= 1;
+            } else if (temp == 0.0) {  // np.argmax: FIRST maximum
                 int bi = 0, bn = -1;
                 for (int c = 0; c < C; ++c) { const int n = B.visits[nb + base + c]; if (n > bn) { bn = n; bi = c; } }
                 chosen = bi;

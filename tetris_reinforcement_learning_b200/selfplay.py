@@ -27,7 +27,7 @@ SAMPLE_MOVES = 512
 CTL_DTYPE = np.dtype({
     "names": ["iter", "max_iter", "n_nodes", "n_states", "leaf", "leaf_kind", "search_no", "garbage_ctr", "status",
               "fast", "active", "games_finished", "sims", "lines_sent0", "lines_cleared0", "leaf_value",
-              "max_depth", "pad_"],
+              "max_depth", "random_left"],
     "formats": ["<i4", "<i4", "<i4", "<i4", "<i4", "<i4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u8",
                 "<i4", "<i4", "<f8", "<i4", "<i4"],
     "offsets": [0, 4, 8, 12, 16, 20, 24, 28, 32, 36, 40, 44, 48, 56, 60, 64, 72, 76],
@@ -54,9 +54,6 @@ GAME_END_DTYPE = np.dtype({
 def search_params_from_config(config, seed=0, restart_finished=True, game_id_stride=1, save_all=None, max_rounds=None):
     """Config (ai.py:97-137) -> TrlSearchParams."""
     from .const import MAX_MOVES
-    if getattr(config, "use_random_starting_moves", False):
-        # reference ai.py:1588-1608 (random opening plies sampled from the raw policy); default False
-        raise NotImplementedError("use_random_starting_moves=True is not implemented on the device path")
     p = _native.SearchParams()
     p.seed = int(seed)
     p.cpuct, p.dpuct, p.fpu_value = float(config.CPUCT), float(config.DPUCT), float(config.FpuValue)
@@ -82,6 +79,9 @@ def search_params_from_config(config, seed=0, restart_finished=True, game_id_str
     p.max_rounds = int(MAX_MOVES if max_rounds is None else max_rounds)
     p.restart_finished = int(bool(restart_finished))
     p.game_id_stride = int(game_id_stride)
+    # random opening plies sampled from the raw policy (ai.py:1588-1608); scale = 0.04 * DIRICHLET_S
+    p.use_random_start = int(bool(getattr(config, "use_random_starting_moves", False)))
+    p.random_start_scale = 0.04 * float(config.DIRICHLET_S)
     return p
 
 
