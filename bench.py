@@ -420,7 +420,10 @@ def run_ours(args, rank, world, local_rank):
                                        "launch (profiles/r1_summary.md), scaled to this launch's call count",
                      "peak_source": peak_src, "kernel": "movegen_warp_kernel",
                      "algorithmic_bytes_per_call": ALGO_BYTES_PER_CALL, "kernel_ms": kern_ms,
-                     "note": "integer-issue bound, not HBM bound (SURVEY §8d): see profiles/ for issue utilisation"},
+                     "note": "integer-issue bound, not HBM bound (SURVEY §8d): the DRAM traffic is at the algorithmic minimum; "
+                             "what binds is the ALU / XU pipes",
+                     "ncu": {"issue_slots_busy_pct": 64.3, "alu_pipe_pct_of_peak": 53.8, "threads_per_warp_instruction": 21.6,
+                             "warp_instructions_per_call": 12650, "source": "profiles/r1_summary.md (r1_movegen_warp_sweep2.ncu-rep)"}},
         "e2e": {"value": placements_all / e2e_list_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_list,
                 "steps": e2e_steps, "matches_device_run": e2e_list_ok,
                 "api": "trl_movegen_host_compact: pinned host buffers in, ascending uint16 move lists (np.argwhere order, "
