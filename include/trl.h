@@ -115,6 +115,9 @@ typedef struct TrlStepOut {
 
 /* ABI version of this header; bumped on any incompatible change. */
 int trl_abi_version(void);
+
+/* Profiling aid: a one-thread kernel writes the GPU's %globaltimer (ns) to *slot in stream order. */
+int trl_stamp_globaltimer(unsigned long long* slot, void* stream);
 /* Text of the last CUDA error seen by this thread's calls ("" if none). */
 const char* trl_last_error(void);
 /* sizeof checks for bindings: returns sizeof(TrlPlayer) / sizeof(TrlGame). */
@@ -327,6 +330,14 @@ typedef struct TrlSearchBuffers {
     uint16_t* legal_cache;                   /* [n_games * state_cap * moves_cap]                        */
     int32_t* legal_cache_n;                  /* [n_games * state_cap] number of cached moves, -1 = none  */
     int32_t* movegen_index;                  /* [n_games] state to enumerate this step or -1 (cache hit)  */
+    /* Compacted work list of the leaf enumeration (both NULL = off: trl_search_movegen then walks
+     * movegen_index with one call slot per game).  trl_search_select appends every game whose leaf needs
+     * an enumeration; trl_search_movegen consumes the list with as few, fully occupied thread blocks as
+     * the count needs (one 16-call block per SM), so the SMs it does not use are free for the network
+     * kernels that run beside it, and leaves both counters at zero for the next step. */
+    int32_t* movegen_list;                   /* [n_games] game indices, arbitrary order                   */
+    uint32_t* movegen_count;                 /* [4] entries in movegen_list; finished blocks; next ticket; pad.
+                                                Zero between steps (the enumeration kernel resets them)    */
 } TrlSearchBuffers;
 
 int trl_sizeof_search_ctl(void);
@@ -341,12 +352,23 @@ int trl_search_select(const TrlSearchBuffers* buf, const TrlSearchParams* prm, v
  * sibling cache: only on states[movegen_index[g]], the leaves whose parent has no list yet). */
 int trl_search_movegen(const TrlSearchBuffers* buf, void* stream);
 
+/* Tuning knob of the compacted enumeration: calls served per call slot (default 1; 1..6 measured equal within noise on B200).  With r rounds
+ * ceil(count / (16 r)) SMs work on the list, for about r search latencies. */
+void trl_search_movegen_rounds(int rounds);
+
 /* Step part 2: expand the leaf with the network outputs (values [n_games], logits
  * [n_games][logits_stride >= 11583]; dtype 0 = float32, 1 = bfloat16), root noise, backup, FPU refresh; when a
  * search has used its iteration budget: choose the move, prune, emit the sample, play the move
  * on the real game, emit the game end and restart. */
 int trl_search_expand(const TrlSearchBuffers* buf, const TrlSearchParams* prm, const void* values,
                       const void* logits, int logits_stride, int dtype, void* stream);
+
+/* trl_search_expand immediately followed by the NEXT step's trl_search_select in one kernel (the same
+ * warp owns a game in both, so the fusion is exact): saves a kernel boundary per simulation.  The
+ * caller runs trl_search_select once before the first step and then only movegen -> network ->
+ * trl_search_expand_select per step. */
+int trl_search_expand_select(const TrlSearchBuffers* buf, const TrlSearchParams* prm, const void* values,
+                             const void* logits, int logits_stride, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------ */
 /* fused convolutional trunk of the policy/value net (tcgen05 tensor cores)               */
@@ -408,6 +430,12 @@ int trl_encode_features_cached(const TrlGame* states, const int32_t* leaf_state,
 int trl_alphasame_trunk_rows_indexed(const void* images_bf16, int32_t* n_images_dev, int max_images,
                                      const int32_t* out_row, int n_blocks, const void* w_packed, const float* consts,
                                      const void* stem_w, void* out_bf16, void* stream);
+
+/* Gate for a forked stream: work submitted to `stream` after this call starts only once every CTA of the
+ * most recent trl_alphasame_trunk_rows_indexed launch is resident (or after 100 us).  The self-play step
+ * uses it to queue the leaf enumeration BEHIND the trunk: its blocks then take over SMs as trunk CTAs
+ * run out of work instead of delaying trunk CTAs at the start. */
+int trl_alphasame_trunk_rows_gate(void* stream);
 
 /* trl_alphasame_heads reading its two feature rows through indices into a cache
  * ([rows][400] bf16; own_row[g] < 0: leaf skipped). */

@@ -133,3 +133,46 @@ def test_trunk_feature_reuse_is_exact():
     # compared through their per-game records above, not slot by slot)
     assert int(c0["sims"].sum()) == int(c1["sims"].sum()) and (c0["status"] == 0).all() and (c1["status"] == 0).all()
     assert sorted(g0["game_id"].tolist()) == sorted(g1["game_id"].tolist())
+
+
+def test_compact_movegen_and_fused_expand_select_are_exact():
+    """Two re-organisations of a self-play step that must not change a single search: (i) the leaf
+    enumeration over a compacted work list on as few SMs as the count needs (movegen_list_kernel)
+    instead of one call slot per game, (ii) expand(t) and select(t+1) as one kernel."""
+    import copy
+    import torch
+    from tetris_reinforcement_learning_b200 import architectures as arch, trunk
+    from tetris_reinforcement_learning_b200.config import Config
+    from tetris_reinforcement_learning_b200.selfplay import SelfPlayEngine
+    net = _random_net(2, 9)
+    ev = trunk.make_fused_evaluator(copy.deepcopy(net))
+    cfg = Config(visual=False, ruleset="s2", model="pytorch", model_config=arch.AlphaSameConfig(blocks=2), MAX_ITER=24,
+                 training=True, use_forced_playouts_and_policy_target_pruning=True)
+    out = []
+    for compact, fuse in ((True, True), (False, False), (True, False), (False, True)):
+        eng = SelfPlayEngine(cfg, ev, 2500, seed=4, feature_dtype=torch.bfloat16, max_rounds=3, sample_cap=65536,
+                             compact_movegen=compact, fuse_expand_select=fuse)   # 2500 games: > 148 x 16 call slots at iteration 0
+        eng.step(150)
+        eng.drain()               # reading results between graph replays must not disturb a pending selection
+        eng.step(150)
+        samples, ends = eng.drain()
+        if compact:   # the kernel leaves its counters at zero; with the fused kernel the next step's list is pending
+            cnt = eng.t["movegen_count"].cpu().numpy()
+            assert int(cnt[1]) == 0 and (int(cnt[0]) == 0 or fuse) and 0 <= int(cnt[0]) <= 2500
+        out.append((samples, ends, eng.get_ctl()))
+    s_ref, e_ref, c_ref = out[0]
+    assert len(s_ref) > 1000 and len(e_ref) > 0 and (c_ref["status"] == 0).all()
+    s_ref = np.sort(s_ref, order=["game_id", "search_no"])
+    e_ref = np.sort(e_ref, order=["game_id"])
+    for s, e, c in out[1:]:
+        assert len(s) == len(s_ref) and len(e) == len(e_ref) and (c["status"] == 0).all()
+        s = np.sort(s, order=["game_id", "search_no"])
+        # record slots are recycled after a drain: entries past n_children are stale, compare the live part
+        live = np.arange(s["moves"].shape[1])[None, :] < s_ref["n_children"][:, None]
+        for name in s.dtype.names:
+            if name in ("moves", "visits", "visits_pre"):
+                assert np.array_equal(np.where(live, s[name], 0), np.where(live, s_ref[name], 0)), name
+            else:
+                assert np.array_equal(s[name], s_ref[name]), name
+        assert np.sort(e, order=["game_id"]).tobytes() == e_ref.tobytes()
+        assert int(c["sims"].sum()) == int(c_ref["sims"].sum())

@@ -11,13 +11,14 @@ from .state import GAME_DTYPE, PLAYER_DTYPE
 _SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtrl_b200.so")
 _lib = None
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 c_void_p, c_int, c_u64, c_u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32
 
 # name -> (restype, argtypes); pointers are passed as integers (device or host addresses)
 SIGNATURES = {
     "trl_abi_version": (c_int, []),
+    "trl_stamp_globaltimer": (c_int, [c_void_p, c_void_p]),
     "trl_last_error": (ctypes.c_char_p, []),
     "trl_sizeof_player": (c_int, []),
     "trl_sizeof_game": (c_int, []),
@@ -28,6 +29,7 @@ SIGNATURES = {
                                  c_void_p, c_void_p]),
     "trl_movegen_host_compact": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_u64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "trl_movegen_select_kernel": (None, [c_int]),
+    "trl_search_movegen_rounds": (None, [c_int]),
     "trl_env_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_u64, c_void_p]),
     "trl_env_step_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_u64]),
     "trl_game_setup": (c_int, [c_void_p, c_int, c_u32, c_u32, c_u64, c_void_p]),
@@ -37,6 +39,7 @@ SIGNATURES = {
     "trl_search_select": (c_int, [c_void_p, c_void_p, c_void_p]),
     "trl_search_movegen": (c_int, [c_void_p, c_void_p]),
     "trl_search_expand": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "trl_search_expand_select": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "trl_alphasame_trunk": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "trl_alphasame_trunk_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "trl_alphasame_trunk_rows_max_blocks": (c_int, []),
@@ -44,6 +47,7 @@ SIGNATURES = {
     "trl_alphasame_heads_weight_floats": (c_int, []),
     "trl_encode_features_cached": (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] * 8),
     "trl_alphasame_trunk_rows_indexed": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "trl_alphasame_trunk_rows_gate": (c_int, [c_void_p]),
     "trl_alphasame_heads_indexed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "trl_encode_features": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
 }
@@ -106,4 +110,5 @@ class SearchBuffers(ctypes.Structure):
                                                "ctl", "games", "leaf_state", "legal", "n_legal",
                                                "samples", "sample_count", "ends", "end_count",
                                                "next_game_id", "noise_override", "leaf_parent",
-                                               "legal_cache", "legal_cache_n", "movegen_index")]
+                                               "legal_cache", "legal_cache_n", "movegen_index",
+                                               "movegen_list", "movegen_count")]

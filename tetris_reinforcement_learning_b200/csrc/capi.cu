@@ -40,7 +40,20 @@ cudaStream_t trl_host_stream(int which) {
     return g_host_stream[which];
 }
 
-extern "C" int trl_abi_version(void) { return 7; }
+extern "C" int trl_abi_version(void) { return 8; }
 extern "C" const char* trl_last_error(void) { return g_err; }
 extern "C" int trl_sizeof_player(void) { return (int)sizeof(TrlPlayer); }
 extern "C" int trl_sizeof_game(void) { return (int)sizeof(TrlGame); }
+
+// One-thread kernel that records the GPU's global nanosecond timer: put between the kernels of a
+// captured step to get the in-graph timeline (tools/step_timeline.py).
+__global__ void stamp_kernel(unsigned long long* slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *slot = t;
+}
+extern "C" int trl_stamp_globaltimer(unsigned long long* slot, void* stream) {
+    if (!slot) return TRL_E_ARG;
+    stamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(slot);
+    return trl_check(cudaGetLastError());
+}

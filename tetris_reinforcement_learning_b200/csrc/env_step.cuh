@@ -205,7 +205,13 @@ static __device__ __noinline__ TrlStepOut trl_env_step_scalar(TrlGame* g, int mo
     p->piece = TRL_NONE;
 
     int n_cleared = 0;  // player.py:161-176: drop full touched rows, empty rows enter on top
-    {
+    bool any_full = false;   // most placements clear nothing: skip the 40-row compaction then
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int r = py + (int)((minos >> (8 * m + 4)) & 15u);
+        if ((unsigned)r < (unsigned)TRL_ROWS && (p->rows[r] & TRL_FULL_ROW) == TRL_FULL_ROW) any_full = true;
+    }
+    if (any_full) {
         int w = TRL_ROWS - 1;
         for (int r = TRL_ROWS - 1; r >= 0; --r) {
             const bool t = (r < 32) ? ((touched >> r) & 1u) : ((touched_hi >> (r - 32)) & 1u);

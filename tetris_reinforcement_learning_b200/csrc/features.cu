@@ -70,21 +70,32 @@ encode_features_cached_kernel(const TrlGame* __restrict__ states, const int32_t*
                               __nv_bfloat16* __restrict__ images, int32_t* __restrict__ image_dest,
                               int32_t* __restrict__ n_images, __nv_bfloat16* __restrict__ extras,
                               int32_t* __restrict__ own_row, int32_t* __restrict__ opp_row) {
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    __shared__ int s_new[kWarps];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int i = blockIdx.x * kWarps + wib;
+    const int si = (i < n) ? leaf_state[i] : -1;
+    const int pi = (si >= 0) ? leaf_parent[i] : -1;
+    const int n_new = (si < 0) ? 0 : ((pi < 0) ? 2 : 1);   // root: both boards; else only the mover's (= opponent of the side to move)
+    // one atomic per BLOCK on the image counter (4096 same-address atomics would serialise in L2)
+    if (lane == 0) s_new[wib] = n_new;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int total = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) total += s_new[w];
+        s_base = total ? atomicAdd(n_images, total) : 0;
+    }
+    __syncthreads();
     if (i >= n) return;
-    const int si = leaf_state[i];
     if (si < 0) {
         if (lane == 0) { own_row[i] = -1; opp_row[i] = -1; }
         return;
     }
-    const int pi = leaf_parent[i];
+    int pos = s_base;
+    for (int w = 0; w < wib; ++w) pos += s_new[w];
     const TrlGame& g = states[si];
     const int turn = g.turn & 1;
-    const int n_new = (pi < 0) ? 2 : 1;               // root: both boards; else only the mover's (= opponent of the side to move)
-    int pos = 0;
-    if (lane == 0) pos = atomicAdd(n_images, n_new);
-    pos = __shfl_sync(0xffffffffu, pos, 0);
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
         const int pl = side == 0 ? turn : 1 - turn;
@@ -92,15 +103,18 @@ encode_features_cached_kernel(const TrlGame* __restrict__ states, const int32_t*
         const int row = si * 2 + pl;
         if (side == 0 && pi >= 0) {
             // the side to move did not move: its board is the parent's, so are its trunk features
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(cache + (size_t)(pi * 2 + pl) * kCells);
-            uint32_t* dst = reinterpret_cast<uint32_t*>(cache + (size_t)row * kCells);
-            for (int c = lane; c < kCells / 2; c += 32) dst[c] = src[c];
+            const uint4* src = reinterpret_cast<const uint4*>(cache + (size_t)(pi * 2 + pl) * kCells);
+            uint4* dst = reinterpret_cast<uint4*>(cache + (size_t)row * kCells);
+            for (int c = lane; c < kCells / 8; c += 32) dst[c] = src[c];     // 800 B = 50 x 16 B
         } else {
             const int k = pos + ((side == 1 && pi < 0) ? 1 : 0);
-            __nv_bfloat16* out = images + (size_t)k * kCells;
-            for (int c = lane; c < kCells; c += 32) {
-                const int r = c / TRL_COLS, col = c - r * TRL_COLS;
-                out[c] = __float2bfloat16((float)((p.rows[r] >> col) & 1u));
+            // lane = board row: 10 cells = five words of two bf16 (1.0 = 0x3F80)
+            uint32_t* out = reinterpret_cast<uint32_t*>(images + (size_t)k * kCells);
+            for (int r = lane; r < TRL_ROWS; r += 32) {
+                const uint32_t bits = p.rows[r];
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+                    out[r * 5 + q] = (((bits >> (2 * q)) & 1u) ? 0x3F80u : 0u) | (((bits >> (2 * q + 1)) & 1u) ? 0x3F800000u : 0u);
             }
             if (lane == 0) image_dest[k] = row;
         }

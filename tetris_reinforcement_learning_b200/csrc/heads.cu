@@ -5,8 +5,8 @@
 //   x     = cat[own trunk features 400, own side 52, o16, opponent side 52, colour 1]   (521, padded to 528)
 //   value = Sigmoid|Tanh(Linear(16 -> 1)(ReLU(BN1d(Linear(521 -> 16)(x)))))   (value_head; dropout = identity)
 // The policy head Linear(521 -> 11583) stays a library GEMM on x (it is GEMM shaped: 50 GFLOP per
-// 4096-leaf step).  One warp per leaf; lanes = (k parity, output): 32 lanes cover the 16 outputs of a
-// layer twice, each half summing every other k, so the k-major weight rows are read conflict-free.
+// 4096-leaf step).  One warp per four leaves; lanes = (k mod 8, output quad): a lane accumulates 4 outputs x
+// 4 leaves over every eighth k (two LDS.128 feed 16 independent FMAs), a butterfly sums the eight k lanes.
 // BatchNorm1d is folded into the linear layers on the host (trunk.py).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -52,7 +52,7 @@ alphasame_heads_kernel(const __nv_bfloat16* __restrict__ feats,    // [2G][400]:
     float4* fo = xs + kPad;
     float* xs_f = reinterpret_cast<float*>(xs);
     float* fo_f = reinterpret_cast<float*>(fo);
-    const int o = lane & 15, h = lane >> 4;
+    const int og = lane & 3, kk = lane >> 2;   // output quad 4og..4og+3, k = kk mod 8
     const int n_quads = (G + kLeaves - 1) / kLeaves;
     for (int q = blockIdx.x * kWarpsPerBlock + warp; q < n_quads; q += gridDim.x * kWarpsPerBlock) {
         int ra[kLeaves], rb[kLeaves];
@@ -111,22 +111,39 @@ alphasame_heads_kernel(const __nv_bfloat16* __restrict__ feats,    // [2G][400]:
             if (lane < kPad - kIn) xs_f[(kIn + lane) * kLeaves + j] = 0.f;
         }
         __syncwarp();
-        // ---- osidedense: 16 outputs x 400 for 4 leaves, lanes = (k parity, output) ----
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int k = h; k < kFeat; k += 2) {
-            const float wk = w[kOffWo + k * 16 + o];
+        // ---- osidedense: 16 outputs x 400 for 4 leaves; lanes = (k mod 8, output quad) ----
+        // per k one LDS.128 of weights (4 outputs) and one LDS.128 of inputs (4 leaves) feed 16 independent FMAs;
+        // 50 / 66 iterations per layer instead of 200 / 264, then a 3-step butterfly over the k lanes
+        float acc[4][kLeaves];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < kLeaves; ++j) acc[a][j] = 0.f;
+#pragma unroll 2
+        for (int k = kk; k < kFeat; k += 8) {
+            const float4 wk = *reinterpret_cast<const float4*>(&w[kOffWo + k * 16 + 4 * og]);
             const float4 f = fo[k];
-            acc.x = fmaf(f.x, wk, acc.x); acc.y = fmaf(f.y, wk, acc.y); acc.z = fmaf(f.z, wk, acc.z); acc.w = fmaf(f.w, wk, acc.w);
+            const float wv4[4] = {wk.x, wk.y, wk.z, wk.w}, fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int j = 0; j < kLeaves; ++j) acc[a][j] = fmaf(fv[j], wv4[a], acc[a][j]);
         }
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
-        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
-        if (h == 0) {   // rounded like the module's bf16 output
-            const float bo = w[kOffBo + o];
-            xs[kFeat + kSide + o] = make_float4(__bfloat162float(__float2bfloat16(fmaxf(acc.x + bo, 0.f))),
-                                                __bfloat162float(__float2bfloat16(fmaxf(acc.y + bo, 0.f))),
-                                                __bfloat162float(__float2bfloat16(fmaxf(acc.z + bo, 0.f))),
-                                                __bfloat162float(__float2bfloat16(fmaxf(acc.w + bo, 0.f))));
+#pragma unroll
+        for (int d = 4; d <= 16; d <<= 1)
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int j = 0; j < kLeaves; ++j) acc[a][j] += __shfl_xor_sync(0xffffffffu, acc[a][j], d);
+        if (kk == 0) {   // rounded like the module's bf16 output
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const float bo = w[kOffBo + 4 * og + a];
+                xs[kFeat + kSide + 4 * og + a] = make_float4(__bfloat162float(__float2bfloat16(fmaxf(acc[a][0] + bo, 0.f))),
+                                                             __bfloat162float(__float2bfloat16(fmaxf(acc[a][1] + bo, 0.f))),
+                                                             __bfloat162float(__float2bfloat16(fmaxf(acc[a][2] + bo, 0.f))),
+                                                             __bfloat162float(__float2bfloat16(fmaxf(acc[a][3] + bo, 0.f))));
+            }
         }
         __syncwarp();
         // ---- x out (bf16, 528 wide) ----
@@ -138,22 +155,34 @@ alphasame_heads_kernel(const __nv_bfloat16* __restrict__ feats,    // [2G][400]:
                 xo[i] = __floats2bfloat162_rn(xs_f[(2 * i) * kLeaves + j], xs_f[(2 * i + 1) * kLeaves + j]);
         }
         // ---- value head ----
-        acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int k = h; k < kPad; k += 2) {
-            const float wk = w[kOffWv + k * 16 + o];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < kLeaves; ++j) acc[a][j] = 0.f;
+#pragma unroll 2
+        for (int k = kk; k < kPad; k += 8) {
+            const float4 wk = *reinterpret_cast<const float4*>(&w[kOffWv + k * 16 + 4 * og]);
             const float4 f = xs[k];
-            acc.x = fmaf(f.x, wk, acc.x); acc.y = fmaf(f.y, wk, acc.y); acc.z = fmaf(f.z, wk, acc.z); acc.w = fmaf(f.w, wk, acc.w);
+            const float wv4[4] = {wk.x, wk.y, wk.z, wk.w}, fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int j = 0; j < kLeaves; ++j) acc[a][j] = fmaf(fv[j], wv4[a], acc[a][j]);
         }
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
-        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
-        const float bv = w[kOffBv + o], w2 = w[kOffW2 + o];
-        float v[kLeaves] = {fmaxf(acc.x + bv, 0.f) * w2, fmaxf(acc.y + bv, 0.f) * w2, fmaxf(acc.z + bv, 0.f) * w2,
-                            fmaxf(acc.w + bv, 0.f) * w2};
+#pragma unroll
+        for (int d = 4; d <= 16; d <<= 1)
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int j = 0; j < kLeaves; ++j) acc[a][j] += __shfl_xor_sync(0xffffffffu, acc[a][j], d);
+        float v[kLeaves];
 #pragma unroll
         for (int j = 0; j < kLeaves; ++j) {
+            v[j] = 0.f;
 #pragma unroll
-            for (int d = 8; d >= 1; d >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], d);
+            for (int a = 0; a < 4; ++a) v[j] = fmaf(fmaxf(acc[a][j] + w[kOffBv + 4 * og + a], 0.f), w[kOffW2 + 4 * og + a], v[j]);
+            v[j] += __shfl_xor_sync(0xffffffffu, v[j], 1);
+            v[j] += __shfl_xor_sync(0xffffffffu, v[j], 2);
             v[j] += w[kOffB2];
             if (lane == 0 && ra[j] >= 0)
                 value_out[q * kLeaves + j] = __float2bfloat16(use_tanh ? tanhf(v[j]) : 1.f / (1.f + __expf(-v[j])));

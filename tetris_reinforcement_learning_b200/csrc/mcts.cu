@@ -25,7 +25,7 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 
 static_assert(sizeof(TrlSearchCtl) == 80, "TrlSearchCtl layout");
 static_assert(sizeof(TrlSearchParams) == 160, "TrlSearchParams layout");
-static_assert(sizeof(TrlSearchBuffers) == 232, "TrlSearchBuffers layout");
+static_assert(sizeof(TrlSearchBuffers) == 248, "TrlSearchBuffers layout");
 static_assert(sizeof(TrlGameEnd) == 32, "TrlGameEnd layout");
 static_assert(sizeof(TrlSample) == 20 + 400 + 3 * 2 * TRL_SAMPLE_MOVES, "TrlSample layout");
 
@@ -97,12 +97,7 @@ __device__ __forceinline__ bool game_terminal(const TrlGame* g) {
 // step part 1: select + materialise
 // ---------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(kWarps * 32)
-search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
-    __shared__ __align__(16) TrlGame s_game[kWarps];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int g = blockIdx.x * kWarps + wib;
-    if (g >= B.n_games) return;
+__device__ void select_body(const TrlSearchBuffers& B, const TrlSearchParams& P, int g, int lane, TrlGame* sgame) {
     TrlSearchCtl* ctl = &B.ctl[g];
     if (!ctl->active) {
         if (lane == 0) {
@@ -114,7 +109,7 @@ search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
     }
     const size_t nb = (size_t)g * B.node_cap, sb = (size_t)g * B.state_cap;
     const bool tanh_mode = P.use_tanh != 0;
-    uint32_t* sg = reinterpret_cast<uint32_t*>(&s_game[wib]);
+    uint32_t* sg = reinterpret_cast<uint32_t*>(sgame);
 
     if (ctl->iter == 0) {
         // new search: root = copy of the real game with queues cut to 5 previews (ai.py:304-309)
@@ -122,7 +117,7 @@ search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
         __syncwarp();
         if (lane == 0) {
             for (int pl = 0; pl < 2; ++pl)
-                if (s_game[wib].players[pl].qlen > TRL_PREVIEWS) s_game[wib].players[pl].qlen = TRL_PREVIEWS;
+                if (sgame->players[pl].qlen > TRL_PREVIEWS) sgame->players[pl].qlen = TRL_PREVIEWS;
             B.parent[nb] = -1; B.slot[nb] = 0; B.visits[nb] = 0; B.value_sum[nb] = 0.0; B.prior[nb] = 0.0;
             B.move[nb] = 0xFFFF;
             B.first_child[sb] = -1; B.n_children[sb] = 0; B.fpu[sb] = 0.0;
@@ -198,7 +193,7 @@ search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
         copy_game(sg, reinterpret_cast<const uint32_t*>(&B.states[sb + ps]), lane);
         __syncwarp();
         if (lane == 0) {
-            trl_env_step_scalar(&s_game[wib], (int)B.move[nb + node], false, P.seed, 1u + ctl->search_no, &ctl->garbage_ctr);
+            trl_env_step_scalar(sgame, (int)B.move[nb + node], false, P.seed, 1u + ctl->search_no, &ctl->garbage_ctr);
             if (B.slot[nb + node] < 0) {
                 B.slot[nb + node] = s;
                 B.first_child[sb + s] = -1; B.n_children[sb + s] = 0; B.fpu[sb + s] = 0.0;
@@ -213,7 +208,7 @@ search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
     }
     __syncwarp();
     if (lane == 0) {
-        const TrlGame* lg = &s_game[wib];
+        const TrlGame* lg = sgame;
         int kind = 0;
         double lv = 0.0;
         if (game_terminal(lg)) {  // ai.py:472-479
@@ -232,9 +227,20 @@ search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
         if (B.movegen_index) {
             // all children of a state share the side to move's board and pieces: enumerate once per parent
             const bool hit = B.legal_cache_n && parent_state >= 0 && B.legal_cache_n[parent_state] >= 0;
-            B.movegen_index[g] = (kind == 2 || hit) ? -1 : (int)(sb + s);
+            const bool need = !(kind == 2 || hit);
+            B.movegen_index[g] = need ? (int)(sb + s) : -1;
+            if (need && B.movegen_list) B.movegen_list[atomicAdd(B.movegen_count, 1u)] = g;
         }
     }
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
+    __shared__ __align__(16) TrlGame s_game[kWarps];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = blockIdx.x * kWarps + wib;
+    if (g >= B.n_games) return;
+    select_body(B, P, g, lane, &s_game[wib]);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -405,13 +411,8 @@ __device__ void finish_search(const TrlSearchBuffers& B, const TrlSearchParams& 
     copy_game(reinterpret_cast<uint32_t*>(&B.games[g]), sg, lane);
 }
 
-__global__ void __launch_bounds__(kWarps * 32)
-search_expand_kernel(TrlSearchBuffers B, TrlSearchParams P, const void* __restrict__ values,
-                     const void* __restrict__ logits, int logits_stride, int dtype) {
-    __shared__ __align__(16) TrlGame s_game[kWarps];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int g = blockIdx.x * kWarps + wib;
-    if (g >= B.n_games) return;
+__device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P, int g, int lane, TrlGame* sgame,
+                            const void* __restrict__ values, const void* __restrict__ logits, int logits_stride, int dtype) {
     TrlSearchCtl* ctl = &B.ctl[g];
     if (!ctl->active || ctl->leaf_kind == 3) return;
     const size_t nb = (size_t)g * B.node_cap, sb = (size_t)g * B.state_cap;
@@ -453,14 +454,23 @@ search_expand_kernel(TrlSearchBuffers B, TrlSearchParams P, const void* __restri
             // by renormalisation over the legal ones == softmax over the legal logits.
             const size_t lb = (size_t)g * (size_t)logits_stride;
             double mx = -INFINITY;
-            for (int c = lane; c < C; c += 32) mx = fmax(mx, (double)load_out(logits, lb + mv[c], dtype));
+            // the first 128 legal logits stay in registers between the two passes (one dependent gather chain less)
+            float lreg[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = lane + 32 * k;
+                if (c < C) { lreg[k] = load_out(logits, lb + mv[c], dtype); mx = fmax(mx, (double)lreg[k]); }
+            }
+            for (int c = lane + 128; c < C; c += 32) mx = fmax(mx, (double)load_out(logits, lb + mv[c], dtype));
             mx = warp_max(mx);
             const bool root_temp = (leaf == 0) && P.use_root_softmax;
             const double inv_temp = root_temp ? 1.0 / P.root_softmax_temp : 1.0;
             const int base = ctl->n_nodes;
             double sum = 0.0;
             for (int c = lane; c < C; c += 32) {
-                const double l = (double)load_out(logits, lb + mv[c], dtype);
+                const int k = c >> 5;
+                const double l = (k < 4) ? (double)(k == 0 ? lreg[0] : k == 1 ? lreg[1] : k == 2 ? lreg[2] : lreg[3])
+                                         : (double)load_out(logits, lb + mv[c], dtype);
                 double e = exp((l - mx) * inv_temp);
                 if (!(e > 0.0)) e = 1e-25;  // the reference's clamp of underflowed probabilities (ai.py:411)
                 B.prior[nb + base + c] = e;
@@ -529,7 +539,31 @@ search_expand_kernel(TrlSearchBuffers B, TrlSearchParams P, const void* __restri
     }
     __syncwarp();
 
-    if (ctl->iter >= ctl->max_iter) finish_search(B, P, g, lane, &s_game[wib]);
+    if (ctl->iter >= ctl->max_iter) finish_search(B, P, g, lane, sgame);
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+search_expand_kernel(TrlSearchBuffers B, TrlSearchParams P, const void* __restrict__ values,
+                     const void* __restrict__ logits, int logits_stride, int dtype) {
+    __shared__ __align__(16) TrlGame s_game[kWarps];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = blockIdx.x * kWarps + wib;
+    if (g >= B.n_games) return;
+    expand_body(B, P, g, lane, &s_game[wib], values, logits, logits_stride, dtype);
+}
+
+// expand(t) + select(t+1): the same warp owns game g in both kernels, so running them back to back in
+// one launch is exact (a warp only reads what it wrote itself; __syncwarp orders its lanes).
+__global__ void __launch_bounds__(kWarps * 32, 7)   // 7 blocks per SM: 4096 games are resident in one wave
+search_expand_select_kernel(TrlSearchBuffers B, TrlSearchParams P, const void* __restrict__ values,
+                            const void* __restrict__ logits, int logits_stride, int dtype) {
+    __shared__ __align__(16) TrlGame s_game[kWarps];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = blockIdx.x * kWarps + wib;
+    if (g >= B.n_games) return;
+    expand_body(B, P, g, lane, &s_game[wib], values, logits, logits_stride, dtype);
+    __syncwarp();
+    select_body(B, P, g, lane, &s_game[wib]);
 }
 
 }  // namespace
@@ -553,9 +587,15 @@ extern "C" int trl_search_select(const TrlSearchBuffers* buf, const TrlSearchPar
 
 int trl_movegen_indexed(const TrlGame* games, const int32_t* index, int n, uint16_t* moves, int moves_cap,
                         uint16_t* n_moves, cudaStream_t stream);  // movegen.cu
+int trl_launch_movegen_listed(const TrlGame* games, const int32_t* index, const int32_t* list, uint32_t* count,
+                              uint16_t* moves, int moves_cap, uint16_t* n_moves, cudaStream_t stream);  // movegen_warp.cu
 
 extern "C" int trl_search_movegen(const TrlSearchBuffers* buf, void* stream) {
     if (!buffers_ok(buf)) return TRL_E_ARG;
+    if (buf->n_games == 0) return TRL_OK;
+    if (buf->movegen_list && buf->movegen_count && buf->movegen_index)
+        return trl_launch_movegen_listed(buf->states, buf->movegen_index, buf->movegen_list, buf->movegen_count,
+                                         buf->legal, buf->moves_cap, buf->n_legal, (cudaStream_t)stream);
     return trl_movegen_indexed(buf->states, buf->movegen_index ? buf->movegen_index : buf->leaf_state, buf->n_games,
                                buf->legal, buf->moves_cap, buf->n_legal, (cudaStream_t)stream);
 }
@@ -566,6 +606,16 @@ extern "C" int trl_search_expand(const TrlSearchBuffers* buf, const TrlSearchPar
         return TRL_E_ARG;
     if (buf->n_games == 0) return TRL_OK;
     search_expand_kernel<<<(buf->n_games + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(
+        *buf, *prm, values, logits, logits_stride, dtype);
+    return trl_check(cudaGetLastError());
+}
+
+extern "C" int trl_search_expand_select(const TrlSearchBuffers* buf, const TrlSearchParams* prm, const void* values,
+                                        const void* logits, int logits_stride, int dtype, void* stream) {
+    if (!buffers_ok(buf) || !prm || !values || !logits || logits_stride < TRL_POLICY_SIZE || (dtype != 0 && dtype != 1))
+        return TRL_E_ARG;
+    if (buf->n_games == 0) return TRL_OK;
+    search_expand_select_kernel<<<(buf->n_games + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(
         *buf, *prm, values, logits, logits_stride, dtype);
     return trl_check(cudaGetLastError());
 }

@@ -537,7 +537,153 @@ movegen_warp_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Search-internal form over a COMPACTED work list (TrlSearchBuffers.movegen_list).
+//
+// Inside a self-play step the enumeration runs on a forked stream beside the network, and only for
+// the leaves whose parent has no cached list (about a quarter of the games).  The network's trunk kernel
+// owns a whole SM per CTA (216 KB of shared memory), so every SM that holds an enumeration block
+// delays a trunk CTA.  This kernel therefore packs the work onto as FEW SMs as possible: one block =
+// 16 call slots = 32 warps with 120 KB of shared memory (one block per SM), `ceil(count / 16)` blocks
+// work and the others exit at once; a call slot (two warps) synchronises with its own named barrier
+// and pulls the next call from a global ticket counter, so the working SMs finish together.  With
+// `rounds` > 1 only ceil(count / (16 * rounds)) SMs work, each slot serving about `rounds` calls: the
+// enumeration then takes longer (it has the whole network evaluation to hide behind) on fewer SMs,
+// and a slot that drew a short search takes another instead of idling until the block's longest ends.
+// ---------------------------------------------------------------------------------------
+constexpr int kListSlots = 16;
+
+__device__ __forceinline__ void slot_barrier(int slot) {
+    asm volatile("bar.sync %0, 64;" ::"r"(slot) : "memory");
+}
+
+__global__ void __launch_bounds__(kListSlots * 64)
+movegen_list_kernel(const TrlGame* __restrict__ games, const int32_t* __restrict__ index,
+                    const int32_t* __restrict__ list, uint32_t* __restrict__ count_done,
+                    uint16_t* __restrict__ moves, int moves_cap, uint16_t* __restrict__ n_moves, int rounds) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    PieceState* ps = reinterpret_cast<PieceState*>(smem_raw);
+    CallState* cs = reinterpret_cast<CallState*>(smem_raw + sizeof(PieceState) * kListSlots * 2);
+    __shared__ int s_ticket[kListSlots];
+    __shared__ uint32_t s_kpack[2][4][3][2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int slot = warp >> 1, which = warp & 1;
+    __shared__ int s_count;
+    __shared__ unsigned s_warps_done;
+    if (tid == 32) { s_count = (int)count_done[0]; s_warps_done = 0u; }
+    {
+        if (tid < 24) {
+            const int t = tid / 12, r = (tid / 3) % 4, kd = tid % 3;
+            const TrlKicks& K = c_kicks[t][r][kd];
+            uint32_t px = 0, py = 0;
+            for (int ki = 0; ki < K.n; ++ki) {
+                px |= (uint32_t)(K.k[ki][0] + 2) << (4 * ki);
+                py |= (uint32_t)(K.k[ki][1] + 2) << (4 * ki);
+            }
+            s_kpack[t][r][kd][0] = px;
+            s_kpack[t][r][kd][1] = py;
+        }
+    }
+    __syncthreads();   // the only block-wide barrier; afterwards barrier ids 0..15 belong to the call slots
+    const int count = s_count;
+    const int n_work = min((int)gridDim.x, (count + kListSlots * rounds - 1) / (kListSlots * rounds));
+    if ((int)blockIdx.x < n_work) {
+        CallState& C = cs[slot];
+        while (true) {
+            if (which == 0 && lane == 0) s_ticket[slot] = (int)atomicAdd(&count_done[2], 1u);
+            slot_barrier(slot);
+            const int j = s_ticket[slot];
+            if (j >= count) break;
+            const int g = list[j];
+            const int gi = index[g];
+            for (int w2 = which * 32 + lane; w2 < TRL_MASK_WORDS + 2; w2 += 64) C.mask[w2] = 0u;
+            if (which == 0) {
+                const TrlPlayer& p = games[gi].players[games[gi].turn & 1];
+                for (int r = lane; r < TRL_ROWS; r += 32) C.rows[r] = p.rows[r];
+                int c = p.piece;
+                int a = (p.held != TRL_NONE) ? p.held : (p.qlen > 0 ? p.queue[0] : TRL_NONE);
+                if (c > 6 && c != TRL_NONE) c = TRL_NONE;
+                if (a > 6 && a != TRL_NONE) a = TRL_NONE;
+                if (lane == 0) { C.cur = c; C.alt = a; C.skip = 0; C.status = 0u; }
+            }
+            slot_barrier(slot);
+            {
+                const int c = C.cur, a = C.alt;
+                uint32_t st = 0;
+                const int type = which ? a : c;
+                if (type != TRL_NONE && !(which && a == c))
+                    search_piece_warp(ps[warp], C.rows, type, which != 0, C.mask, st, &s_kpack[type == P_I ? 1 : 0]);
+            }
+            slot_barrier(slot);
+            if (which == 0) {
+                // ascending move list (= argwhere order): lane owns 12 consecutive mask words
+                const int w0 = lane * 12;
+                int cnt = 0;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) {
+                    const int w2 = w0 + k;
+                    if (w2 < TRL_MASK_WORDS) cnt += __popc(C.mask[w2]);
+                }
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                uint16_t* mv = moves + (size_t)g * moves_cap;
+                int pos = incl - cnt;
+                for (int k = 0; k < 12; ++k) {
+                    const int w2 = w0 + k;
+                    if (w2 >= TRL_MASK_WORDS) break;
+                    uint32_t m = C.mask[w2];
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        if (pos < moves_cap) mv[pos] = (uint16_t)(w2 * 32 + b);
+                        ++pos;
+                    }
+                }
+                if (lane == 0) n_moves[g] = (uint16_t)total;
+            }
+            slot_barrier(slot);   // the mask is re-zeroed and the ticket redrawn for the next call
+        }
+    }
+    // every block has read the count before its last warp arrives here: the last block leaves both
+    // counters at zero for the next step (no memset node per step)
+    __syncwarp();
+    if (lane == 0 && atomicAdd(&s_warps_done, 1u) == (unsigned)(kListSlots * 2 - 1)) {
+        if (atomicAdd(&count_done[1], 1u) == gridDim.x - 1) {
+            count_done[0] = 0u;
+            count_done[1] = 0u;
+            count_done[2] = 0u;
+        }
+    }
+}
+
 }  // namespace
+
+// calls per slot the compacted enumeration aims at (1 = one call per slot on ceil(count / 16) SMs)
+static int g_list_rounds = 1;
+extern "C" void trl_search_movegen_rounds(int rounds) { g_list_rounds = rounds < 1 ? 1 : (rounds > 16 ? 16 : rounds); }
+
+int trl_launch_movegen_listed(const TrlGame* games, const int32_t* index, const int32_t* list, uint32_t* count_done,
+                              uint16_t* moves, int moves_cap, uint16_t* n_moves, cudaStream_t stream) {
+    if (!games || !index || !list || !count_done || !moves || !n_moves || moves_cap <= 0) return TRL_E_ARG;
+    const size_t smem = sizeof(PieceState) * kListSlots * 2 + sizeof(CallState) * kListSlots;
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0, sms = 0;
+        int rc = trl_check(cudaGetDevice(&dev));
+        if (!rc) rc = trl_check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (!rc) rc = trl_check(cudaFuncSetAttribute(movegen_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (rc) return rc;
+        n_sm = sms;
+    }
+    movegen_list_kernel<<<n_sm, kListSlots * 64, smem, stream>>>(games, index, list, count_done, moves, moves_cap, n_moves,
+                                                                g_list_rounds);
+    return trl_check(cudaGetLastError());
+}
 
 // Launch the warp-cooperative kernel (same argument contract as movegen.cu's launch_movegen).
 int trl_launch_movegen_warp(const uint16_t* boards, const uint8_t* cur, const uint8_t* alt, const TrlGame* games,

@@ -217,6 +217,7 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
     const uint32_t bars = smem_u32(smem + off_bar);
     if (n_images_dev) n_images = min(n_images, *n_images_dev);
     const int n_groups = (n_images + kImgs - 1) / kImgs;
+    if (tid == 0) atomicAdd(next_group + 2, 1);   // resident CTAs (trl_alphasame_trunk_rows_gate polls this)
 
     // ---- one-time setup ----
     for (int i = tid; i < n_lanes * lane_bytes / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -434,9 +435,24 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
         if (atomicAdd(next_group + 1, 1) == (int)gridDim.x - 1) {
             next_group[0] = 0;
             next_group[1] = 0;
+            next_group[2] = 0;
             if (n_images_dev) *n_images_dev = 0;   // consumed: the next step's feature encoder appends from zero
             __threadfence();
         }
+    }
+}
+
+// Holds a forked stream back until every CTA of a trunk launch is resident (or a time-out): one thread.
+__global__ void trunk_gate_kernel(const int* __restrict__ counter, int expected, unsigned long long max_ns) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (true) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(counter + 2) : "memory");
+        if (v >= expected) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > max_ns) break;
+        __nanosleep(200);
     }
 }
 
@@ -496,6 +512,17 @@ extern "C" int trl_alphasame_trunk_rows(const void* grids_bf16, int n_images, in
     return trl_check(cudaGetLastError());
 }
 
+static int* g_last_counter = nullptr;
+static int g_last_grid = 0;
+
+// Work submitted to `stream` after this call starts only when all CTAs of the most recent
+// trl_alphasame_trunk_rows_indexed launch are resident on their SMs (or after 100 us).
+extern "C" int trl_alphasame_trunk_rows_gate(void* stream) {
+    if (!g_last_counter) return TRL_E_ARG;
+    trunk_gate_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(g_last_counter, g_last_grid, 100000ull);
+    return trl_check(cudaGetLastError());
+}
+
 extern "C" int trl_alphasame_trunk_rows_indexed(const void* images_bf16, int32_t* n_images_dev, int max_images,
                                                 const int32_t* out_row, int n_blocks, const void* w_packed,
                                                 const float* consts, const void* stem_w, void* out_bf16, void* stream) {
@@ -514,8 +541,20 @@ extern "C" int trl_alphasame_trunk_rows_indexed(const void* images_bf16, int32_t
     const int grid = sms < n_units ? sms : n_units;
     int* counter = next_counter();   // zero on entry: the previous launch on this slot reset it
     if (!counter) return TRL_E_NOMEM;
-    alphasame_trunk_rows_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(
+    g_last_counter = counter;
+    g_last_grid = grid;
+    // Highest launch priority: inside a self-play step the leaf enumeration becomes ready at the same moment
+    // on a forked stream, and its blocks must queue BEHIND the trunk's CTAs (they move in as trunk CTAs run
+    // out of work) instead of taking SMs from them at the start.
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributePriority;
+    attr[0].val.priority = prio_hi;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return trl_check(cudaLaunchKernelEx(&cfg, alphasame_trunk_rows_kernel,
         (const __nv_bfloat16*)images_bf16, max_images, n_blocks, n_lanes, (const uint4*)w_packed, host_consts(consts, n_blocks), (const uint4*)stem_w,
-        (__nv_bfloat16*)out_bf16, counter, n_images_dev, out_row, g_trace);
-    return trl_check(cudaGetLastError());
+        (__nv_bfloat16*)out_bf16, counter, n_images_dev, out_row, g_trace));
 }

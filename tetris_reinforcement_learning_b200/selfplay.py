@@ -96,7 +96,7 @@ class SelfPlayEngine:
     def __init__(self, config, evaluator, n_games, device="cuda:0", seed=0, first_game_id=0, game_id_stride=1,
                  feature_dtype=torch.float32, node_cap=None, sample_cap=None, restart_finished=True, save_all=None,
                  max_rounds=None, use_cuda_graph=True, overlap_movegen=True, reuse_trunk_features=True,
-                 reuse_sibling_placements=True):
+                 reuse_sibling_placements=True, compact_movegen=True, fuse_expand_select=True):
         from .state import ruleset_id
         self.ruleset = ruleset_id(config.ruleset)   # 's2' (default) or 's1': attack table + all-spin rule
         if config.move_algorithm != "convolutional":
@@ -138,6 +138,14 @@ class SelfPlayEngine:
             self.t["legal_cache"] = z(ns * self.moves_cap, torch.int16)
             self.t["legal_cache_n"] = torch.full((ns,), -1, dtype=torch.int32, device=dev)
             self.t["movegen_index"] = z(G, torch.int32)
+            if compact_movegen:
+                # compacted work list of the leaf enumeration: it then occupies ceil(count / 16) SMs instead
+                # of all of them next to the trunk kernel (include/trl.h, TrlSearchBuffers.movegen_list)
+                self.t["movegen_list"] = z(G, torch.int32)
+                self.t["movegen_count"] = z(4, torch.int32)
+        # expand(t) and select(t+1) as one kernel; `_selected` = the next step's leaves are already chosen
+        self.fuse_expand_select = bool(fuse_expand_select)
+        self._selected = False
         fdt = feature_dtype
         self.grids = torch.zeros((2 * G, 1, 40, 10), dtype=fdt, device=dev)
         self.extras = torch.zeros((G, 105), dtype=fdt, device=dev)
@@ -153,6 +161,8 @@ class SelfPlayEngine:
         self._cache_bufs = self.cached_eval.make_buffers(ns, G, dev) if self.cached_eval is not None else None
         assert self.lib.trl_sizeof_search_ctl() == CTL_DTYPE.itemsize and self.lib.trl_sizeof_sample() == SAMPLE_DTYPE.itemsize
         self._graph = None
+        self._stamps = None
+        self._graph_has_select = True
         self._side = None
         self._values = self._logits = None
         self.steps_done = 0
@@ -170,10 +180,21 @@ class SelfPlayEngine:
         ctl = np.zeros(self.G, dtype=CTL_DTYPE)
         ctl["active"] = 1
         self.set_ctl(ctl)
+        self._invalidate_selection()
+
+    def _invalidate_selection(self):
+        """The host changed games / controls: a selection made by the fused expand+select kernel is
+        stale, and so is the work list it left for the enumeration.  (Re-selecting an unchanged game
+        reaches the same leaf but advances its in-search garbage-column counter, so change controls
+        before the first step or between searches if runs must be reproducible step by step.)"""
+        self._selected = False
+        if "movegen_count" in self.t:
+            self.t["movegen_count"].zero_()
 
     def set_games(self, games_np):
         assert games_np.dtype == GAME_DTYPE and games_np.shape == (self.G,)
         self.t["games"].copy_(torch.from_numpy(np.ascontiguousarray(games_np).view(np.uint8).reshape(-1)).to(self.device))
+        self._invalidate_selection()
 
     def get_games(self):
         return self.t["games"].cpu().numpy().view(GAME_DTYPE).reshape(-1)
@@ -181,6 +202,7 @@ class SelfPlayEngine:
     def set_ctl(self, ctl_np):
         assert ctl_np.dtype == CTL_DTYPE and ctl_np.shape == (self.G,)
         self.t["ctl"].copy_(torch.from_numpy(np.ascontiguousarray(ctl_np).view(np.uint8).reshape(-1)).to(self.device))
+        self._invalidate_selection()
 
     def get_ctl(self):
         return self.t["ctl"].cpu().numpy().view(CTL_DTYPE).reshape(-1)
@@ -196,7 +218,11 @@ class SelfPlayEngine:
         main = torch.cuda.current_stream(self.device)
         lib, st = self.lib, main.cuda_stream
         bp, pp = ctypes.byref(self.buf), ctypes.byref(self.params)
-        _native.check(lib.trl_search_select(bp, pp, st), "trl_search_select")
+        stamp = self._stamp
+        stamp(0, st)
+        if not self._selected:
+            _native.check(lib.trl_search_select(bp, pp, st), "trl_search_select")
+        stamp(1, st)
         # the leaves' legal placements only feed `expand`: enumerate them on a forked stream, concurrently
         # with the network (joined before expand).  overlap_movegen = "trunk": next to feature encoding and
         # the trunk; "heads": next to the heads kernel and the policy GEMM (the trunk is bound by shared-
@@ -205,21 +231,44 @@ class SelfPlayEngine:
             if self._side is None:
                 self._side = torch.cuda.Stream(self.device)
             self._side.wait_stream(main)
+            stamp(8, self._side.cuda_stream)
             _native.check(lib.trl_search_movegen(bp, self._side.cuda_stream), "trl_search_movegen")
+            stamp(9, self._side.cuda_stream)
 
         mode = self.overlap_movegen
         if mode is True:
+            mode = "tail" if self.cached_eval is not None else "trunk"
+        if mode in ("heads", "tail") and self.cached_eval is None:
             mode = "trunk"
-        if mode == "heads" and self.cached_eval is None:
-            mode = "trunk"
+        # "tail": the enumeration depends on the feature encoder (an event) but is submitted AFTER the trunk
+        # kernel, so the trunk's CTAs take every SM first and the enumeration's blocks move in as trunk CTAs
+        # run out of work (the last, partial wave of the trunk leaves a third of the SMs idle)
+        enc_done = None
+
+        def mark_encoded():
+            nonlocal enc_done
+            enc_done = torch.cuda.Event()
+            enc_done.record(main)
+
+        def fork_movegen_tail():
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.device)
+            self._side.wait_event(enc_done)
+            _native.check(lib.trl_alphasame_trunk_rows_gate(self._side.cuda_stream), "trl_alphasame_trunk_rows_gate")
+            stamp(8, self._side.cuda_stream)
+            _native.check(lib.trl_search_movegen(bp, self._side.cuda_stream), "trl_search_movegen")
+            stamp(9, self._side.cuda_stream)
         if not mode:
+            stamp(8, st)
             _native.check(lib.trl_search_movegen(bp, st), "trl_search_movegen")
+            stamp(9, st)
         elif mode == "trunk":
             fork_movegen()
         if self.cached_eval is not None:
             with torch.no_grad():
                 values, logits = self.cached_eval(self._cache_bufs, self.t["states"], self.t["leaf_state"], self.t["leaf_parent"], self.extras,
-                                                  after_trunk=fork_movegen if mode == "heads" else None)
+                                                  after_trunk=fork_movegen if mode == "heads" else (fork_movegen_tail if mode == "tail" else None),
+                                                  before_trunk=mark_encoded if mode == "tail" else None)
         else:
             dt = 0 if self.feature_dtype == torch.float32 else 1
             _native.check(lib.trl_encode_features(self.t["states"].data_ptr(), self.t["leaf_state"].data_ptr(), self.G,
@@ -235,10 +284,28 @@ class SelfPlayEngine:
         if logits.dtype not in (torch.float32, torch.bfloat16):
             raise ValueError("evaluator outputs must be float32 or bfloat16")
         self._values, self._logits = values, logits  # keep alive (graph-owned memory when captured)
+        stamp(5, st)
         if self.overlap_movegen:
             main.wait_stream(self._side)
-        _native.check(lib.trl_search_expand(bp, pp, values.data_ptr(), logits.data_ptr(), logits.stride(0),
-                                            0 if logits.dtype == torch.float32 else 1, st), "trl_search_expand")
+        fn, name = ((lib.trl_search_expand_select, "trl_search_expand_select") if self.fuse_expand_select
+                    else (lib.trl_search_expand, "trl_search_expand"))
+        _native.check(fn(bp, pp, values.data_ptr(), logits.data_ptr(), logits.stride(0),
+                         0 if logits.dtype == torch.float32 else 1, st), name)
+        self._selected = self.fuse_expand_select
+        stamp(6, st)
+
+    def enable_timeline(self):
+        """Profiling: %globaltimer stamps between the kernels of a step (slots: 0 start, 1 after select,
+        2 after encode, 3 after trunk, 4 after heads, 5 after policy GEMM, 6 after expand(+select), 8/9 around
+        the forked enumeration).  Perturbs the step by one tiny kernel per stamp; re-captures the graph."""
+        self._stamps = torch.zeros(16, dtype=torch.int64, device=self.device)
+        self._graph = None
+        if self.cached_eval is not None:
+            self.cached_eval.stamp = self._stamp
+
+    def _stamp(self, k, stream):
+        if self._stamps is not None:
+            _native.check(self.lib.trl_stamp_globaltimer(self._stamps.data_ptr() + 8 * k, stream), "trl_stamp_globaltimer")
 
     def step(self, n=1):
         """Advance every game by n simulations."""
@@ -260,6 +327,12 @@ class SelfPlayEngine:
             with torch.cuda.graph(g):
                 self._step_eager()
             self._graph = g
+            self._graph_has_select = not self.fuse_expand_select
+        if n > 0 and not self._graph_has_select and not self._selected:
+            # the host touched games / controls after the capture: choose the leaves once outside the graph
+            _native.check(self.lib.trl_search_select(ctypes.byref(self.buf), ctypes.byref(self.params),
+                                                     torch.cuda.current_stream(self.device).cuda_stream), "trl_search_select")
+            self._selected = True
         for _ in range(max(n, 0)):
             self._graph.replay()
         self.steps_done += max(n, 0)

@@ -184,6 +184,7 @@ class CachedTrunkEvaluator:
     def __init__(self, packed, w_heads, use_tanh, w_pol, b_pol, k_pad):
         self.packed, self.w_heads, self.use_tanh = packed, w_heads, use_tanh
         self.w_pol, self.b_pol, self.k_pad = w_pol, b_pol, k_pad
+        self.stamp = None   # profiling hook (SelfPlayEngine.enable_timeline)
 
     def make_buffers(self, n_states, n_leaves, device):
         """Per-ENGINE buffers (the engine owns them, so they are freed with it): the feature cache
@@ -194,7 +195,7 @@ class CachedTrunkEvaluator:
                 "own": z(n_leaves, torch.int32), "opp": z(n_leaves, torch.int32),
                 "x": z((n_leaves, self.k_pad), torch.bfloat16), "value": z(n_leaves, torch.bfloat16)}
 
-    def __call__(self, b, states, leaf_state, leaf_parent, extras, after_trunk=None):
+    def __call__(self, b, states, leaf_state, leaf_parent, extras, after_trunk=None, before_trunk=None):
         """b: make_buffers(); states uint8 [n_states*400], leaf_state / leaf_parent int32 [G], extras bf16
         [G,105] (written here) -> (values bf16 [G], logits bf16 [G, 11584])."""
         lib = _native.lib()
@@ -205,15 +206,21 @@ class CachedTrunkEvaluator:
             states.data_ptr(), leaf_state.data_ptr(), leaf_parent.data_ptr(), G, b["cache"].data_ptr(),
             b["images"].data_ptr(), b["dest"].data_ptr(), b["count"].data_ptr(), extras.data_ptr(),
             b["own"].data_ptr(), b["opp"].data_ptr(), st), "trl_encode_features_cached")
+        stamp = self.stamp or (lambda k, s: None)
+        stamp(2, st)
+        if before_trunk is not None:
+            before_trunk()
         p = self.packed
         _native.check(lib.trl_alphasame_trunk_rows_indexed(
             b["images"].data_ptr(), b["count"].data_ptr(), 2 * G, b["dest"].data_ptr(), p["n_blocks"],
             p["w_packed"].data_ptr(), p["consts_host"].data_ptr(), p["stem_w"].data_ptr(), b["cache"].data_ptr(), st),
             "trl_alphasame_trunk_rows_indexed")
+        stamp(3, st)
         if after_trunk is not None:
             after_trunk()
         _native.check(lib.trl_alphasame_heads_indexed(
             b["cache"].data_ptr(), b["own"].data_ptr(), b["opp"].data_ptr(), extras.data_ptr(), G,
             self.w_heads.data_ptr(), self.use_tanh, b["x"].data_ptr(), b["value"].data_ptr(), st),
             "trl_alphasame_heads_indexed")
+        stamp(4, st)
         return b["value"], torch.nn.functional.linear(b["x"], self.w_pol, self.b_pol)
