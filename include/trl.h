@@ -370,6 +370,15 @@ int trl_search_expand(const TrlSearchBuffers* buf, const TrlSearchParams* prm, c
 int trl_search_expand_select(const TrlSearchBuffers* buf, const TrlSearchParams* prm, const void* values,
                              const void* logits, int logits_stride, int dtype, void* stream);
 
+/* ... and additionally trl_encode_features_cached for the selected leaves (arguments as there), from the
+ * leaf state the selection left in shared memory.  *n_images must be zero on entry (the trunk kernel of
+ * the step that produced `logits` has reset it).  The caller runs trl_search_select +
+ * trl_encode_features_cached once before the first step. */
+int trl_search_expand_select_encode(const TrlSearchBuffers* buf, const TrlSearchParams* prm, const void* values,
+                                    const void* logits, int logits_stride, int dtype, void* cache_bf16,
+                                    void* images_bf16, int32_t* image_dest, int32_t* n_images, void* extras_bf16,
+                                    int32_t* own_row, int32_t* opp_row, void* stream);
+
 /* ------------------------------------------------------------------------------------ */
 /* fused convolutional trunk of the policy/value net (tcgen05 tensor cores)               */
 /* replaces AlphaSame.process_grid (architectures.py:120-126, blocks :27-57) in eval mode  */

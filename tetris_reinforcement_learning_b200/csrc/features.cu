@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "features_dev.cuh"
 #include "trl_common.cuh"
 #include "trl_tables.cuh"
 
@@ -94,50 +95,10 @@ encode_features_cached_kernel(const TrlGame* __restrict__ states, const int32_t*
     }
     int pos = s_base;
     for (int w = 0; w < wib; ++w) pos += s_new[w];
-    const TrlGame& g = states[si];
-    const int turn = g.turn & 1;
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-        const int pl = side == 0 ? turn : 1 - turn;
-        const TrlPlayer& p = g.players[pl];
-        const int row = si * 2 + pl;
-        if (side == 0 && pi >= 0) {
-            // the side to move did not move: its board is the parent's, so are its trunk features
-            const uint4* src = reinterpret_cast<const uint4*>(cache + (size_t)(pi * 2 + pl) * kCells);
-            uint4* dst = reinterpret_cast<uint4*>(cache + (size_t)row * kCells);
-            for (int c = lane; c < kCells / 8; c += 32) dst[c] = src[c];     // 800 B = 50 x 16 B
-        } else {
-            const int k = pos + ((side == 1 && pi < 0) ? 1 : 0);
-            // lane = board row: 10 cells = five words of two bf16 (1.0 = 0x3F80)
-            uint32_t* out = reinterpret_cast<uint32_t*>(images + (size_t)k * kCells);
-            for (int r = lane; r < TRL_ROWS; r += 32) {
-                const uint32_t bits = p.rows[r];
-#pragma unroll
-                for (int q = 0; q < 5; ++q)
-                    out[r * 5 + q] = (((bits >> (2 * q)) & 1u) ? 0x3F80u : 0u) | (((bits >> (2 * q + 1)) & 1u) ? 0x3F800000u : 0u);
-            }
-            if (lane == 0) image_dest[k] = row;
-        }
-        __nv_bfloat16* ex = extras + (size_t)i * kExtras + side * 52;
-        for (int c = lane; c < 49; c += 32) {
-            const int slot = c / 7, mino = c - slot * 7;
-            int piece = TRL_NONE;
-            if (slot == 0) piece = p.piece;
-            else if (slot == 1) piece = p.held;
-            else if (slot - 2 < p.qlen) piece = p.queue[slot - 2];
-            ex[c] = __float2bfloat16(piece == mino ? 1.f : 0.f);
-        }
-        if (lane == 0) {
-            ex[49] = __float2bfloat16((float)p.b2b);
-            ex[50] = __float2bfloat16((float)p.combo);
-            ex[51] = __float2bfloat16((float)p.n_recv);
-        }
-    }
-    if (lane == 0) {
-        extras[(size_t)i * kExtras + 104] = __float2bfloat16((float)turn);
-        own_row[i] = si * 2 + turn;
-        opp_row[i] = si * 2 + (1 - turn);
-    }
+    TrlEncodeArgs E;
+    E.cache = cache; E.images = images; E.image_dest = image_dest; E.n_images = n_images; E.extras = extras;
+    E.own_row = own_row; E.opp_row = opp_row;
+    trl_encode_cached_leaf(states[si], i, si, pi, pos, lane, E);
 }
 
 }  // namespace

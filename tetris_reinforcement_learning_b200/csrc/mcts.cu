@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include "env_step.cuh"
+#include "features_dev.cuh"
 #include "trl_common.cuh"
 
 namespace {
@@ -97,8 +98,12 @@ __device__ __forceinline__ bool game_terminal(const TrlGame* g) {
 // step part 1: select + materialise
 // ---------------------------------------------------------------------------------------
 
-__device__ void select_body(const TrlSearchBuffers& B, const TrlSearchParams& P, int g, int lane, TrlGame* sgame) {
+// leaf_si / leaf_pi (all lanes): state index of the position to evaluate and of the state it was reached
+// from, as written to leaf_state[g] / leaf_parent[g]; on return *sgame holds the leaf state.
+__device__ void select_body(const TrlSearchBuffers& B, const TrlSearchParams& P, int g, int lane, TrlGame* sgame,
+                            int& leaf_si, int& leaf_pi) {
     TrlSearchCtl* ctl = &B.ctl[g];
+    leaf_si = -1; leaf_pi = -1;
     if (!ctl->active) {
         if (lane == 0) {
             B.leaf_state[g] = -1; ctl->leaf_kind = 3;
@@ -222,8 +227,10 @@ __device__ void select_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
         }
         ctl->leaf = node; ctl->leaf_kind = kind; ctl->leaf_value = lv;
         if (depth > ctl->max_depth) ctl->max_depth = depth;
-        B.leaf_state[g] = (kind == 2) ? -1 : (int)(sb + s);
-        if (B.leaf_parent) B.leaf_parent[g] = (kind == 2) ? -1 : parent_state;
+        leaf_si = (kind == 2) ? -1 : (int)(sb + s);
+        leaf_pi = (kind == 2) ? -1 : parent_state;
+        B.leaf_state[g] = leaf_si;
+        if (B.leaf_parent) B.leaf_parent[g] = leaf_pi;
         if (B.movegen_index) {
             // all children of a state share the side to move's board and pieces: enumerate once per parent
             const bool hit = B.legal_cache_n && parent_state >= 0 && B.legal_cache_n[parent_state] >= 0;
@@ -232,6 +239,8 @@ __device__ void select_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
             if (need && B.movegen_list) B.movegen_list[atomicAdd(B.movegen_count, 1u)] = g;
         }
     }
+    leaf_si = __shfl_sync(kFull, leaf_si, 0);
+    leaf_pi = __shfl_sync(kFull, leaf_pi, 0);
 }
 
 __global__ void __launch_bounds__(kWarps * 32)
@@ -240,7 +249,8 @@ search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = blockIdx.x * kWarps + wib;
     if (g >= B.n_games) return;
-    select_body(B, P, g, lane, &s_game[wib]);
+    int si, pi;
+    select_body(B, P, g, lane, &s_game[wib], si, pi);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -563,7 +573,32 @@ search_expand_select_kernel(TrlSearchBuffers B, TrlSearchParams P, const void* _
     if (g >= B.n_games) return;
     expand_body(B, P, g, lane, &s_game[wib], values, logits, logits_stride, dtype);
     __syncwarp();
-    select_body(B, P, g, lane, &s_game[wib]);
+    int si, pi;
+    select_body(B, P, g, lane, &s_game[wib], si, pi);
+}
+
+// ... + the feature encoding of the selected leaf (features_dev.cuh), straight from the leaf state that
+// select left in shared memory: one kernel boundary and one read of the state less per simulation.
+__global__ void __launch_bounds__(kWarps * 32, 7)
+search_expand_select_encode_kernel(TrlSearchBuffers B, TrlSearchParams P, const void* __restrict__ values,
+                                   const void* __restrict__ logits, int logits_stride, int dtype, TrlEncodeArgs E) {
+    __shared__ __align__(16) TrlGame s_game[kWarps];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = blockIdx.x * kWarps + wib;
+    if (g >= B.n_games) return;
+    expand_body(B, P, g, lane, &s_game[wib], values, logits, logits_stride, dtype);
+    __syncwarp();
+    int si, pi;
+    select_body(B, P, g, lane, &s_game[wib], si, pi);
+    __syncwarp();
+    if (si < 0) {
+        if (lane == 0) { E.own_row[g] = -1; E.opp_row[g] = -1; }
+        return;
+    }
+    int pos = 0;
+    if (lane == 0) pos = atomicAdd(E.n_images, (pi < 0) ? 2 : 1);
+    pos = __shfl_sync(kFull, pos, 0);
+    trl_encode_cached_leaf(s_game[wib], g, si, pi, pos, lane, E);
 }
 
 }  // namespace
@@ -617,5 +652,21 @@ extern "C" int trl_search_expand_select(const TrlSearchBuffers* buf, const TrlSe
     if (buf->n_games == 0) return TRL_OK;
     search_expand_select_kernel<<<(buf->n_games + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(
         *buf, *prm, values, logits, logits_stride, dtype);
+    return trl_check(cudaGetLastError());
+}
+
+extern "C" int trl_search_expand_select_encode(const TrlSearchBuffers* buf, const TrlSearchParams* prm, const void* values,
+                                               const void* logits, int logits_stride, int dtype, void* cache_bf16,
+                                               void* images_bf16, int32_t* image_dest, int32_t* n_images,
+                                               void* extras_bf16, int32_t* own_row, int32_t* opp_row, void* stream) {
+    if (!buffers_ok(buf) || !prm || !values || !logits || logits_stride < TRL_POLICY_SIZE || (dtype != 0 && dtype != 1) ||
+        !buf->leaf_parent || !cache_bf16 || !images_bf16 || !image_dest || !n_images || !extras_bf16 || !own_row || !opp_row)
+        return TRL_E_ARG;
+    if (buf->n_games == 0) return TRL_OK;
+    TrlEncodeArgs E;
+    E.cache = (__nv_bfloat16*)cache_bf16; E.images = (__nv_bfloat16*)images_bf16; E.image_dest = image_dest;
+    E.n_images = n_images; E.extras = (__nv_bfloat16*)extras_bf16; E.own_row = own_row; E.opp_row = opp_row;
+    search_expand_select_encode_kernel<<<(buf->n_games + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(
+        *buf, *prm, values, logits, logits_stride, dtype, E);
     return trl_check(cudaGetLastError());
 }

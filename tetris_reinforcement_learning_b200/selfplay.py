@@ -14,6 +14,7 @@ root children, post-prune visit counts) and finished games `TrlGameEnd` records 
 buffers that the host drains between graph replays.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -96,7 +97,7 @@ class SelfPlayEngine:
     def __init__(self, config, evaluator, n_games, device="cuda:0", seed=0, first_game_id=0, game_id_stride=1,
                  feature_dtype=torch.float32, node_cap=None, sample_cap=None, restart_finished=True, save_all=None,
                  max_rounds=None, use_cuda_graph=True, overlap_movegen=True, reuse_trunk_features=True,
-                 reuse_sibling_placements=True, compact_movegen=True, fuse_expand_select=True):
+                 reuse_sibling_placements=True, compact_movegen=True, fuse_expand_select=True, fuse_encode=True):
         from .state import ruleset_id
         self.ruleset = ruleset_id(config.ruleset)   # 's2' (default) or 's1': attack table + all-spin rule
         if config.move_algorithm != "convolutional":
@@ -145,7 +146,10 @@ class SelfPlayEngine:
                 self.t["movegen_count"] = z(4, torch.int32)
         # expand(t) and select(t+1) as one kernel; `_selected` = the next step's leaves are already chosen
         self.fuse_expand_select = bool(fuse_expand_select)
+        # ... and the feature encoding of the selected leaves in the same kernel (cached evaluator only)
+        self.fuse_encode = bool(fuse_encode) and self.fuse_expand_select and self.cached_eval is not None
         self._selected = False
+        self._encoded = False
         fdt = feature_dtype
         self.grids = torch.zeros((2 * G, 1, 40, 10), dtype=fdt, device=dev)
         self.extras = torch.zeros((G, 105), dtype=fdt, device=dev)
@@ -188,8 +192,11 @@ class SelfPlayEngine:
         reaches the same leaf but advances its in-search garbage-column counter, so change controls
         before the first step or between searches if runs must be reproducible step by step.)"""
         self._selected = False
+        self._encoded = False
         if "movegen_count" in self.t:
             self.t["movegen_count"].zero_()
+        if getattr(self, "_cache_bufs", None) is not None:
+            self._cache_bufs["count"].zero_()    # images queued by a fused encode of the stale selection
 
     def set_games(self, games_np):
         assert games_np.dtype == GAME_DTYPE and games_np.shape == (self.G,)
@@ -254,9 +261,15 @@ class SelfPlayEngine:
             if self._side is None:
                 self._side = torch.cuda.Stream(self.device)
             self._side.wait_event(enc_done)
-            _native.check(lib.trl_alphasame_trunk_rows_gate(self._side.cuda_stream), "trl_alphasame_trunk_rows_gate")
+            probe = os.environ.get("TRL_PROBE_TAIL", "")   # timing probes only (tools/step_timeline.py)
+            if "nogate" not in probe:
+                _native.check(lib.trl_alphasame_trunk_rows_gate(self._side.cuda_stream), "trl_alphasame_trunk_rows_gate")
             stamp(8, self._side.cuda_stream)
-            _native.check(lib.trl_search_movegen(bp, self._side.cuda_stream), "trl_search_movegen")
+            if "nomovegen" in probe:   # INVALID searches (stale move lists): only to time the rest of the step
+                with torch.cuda.stream(self._side):
+                    self.t["movegen_count"].zero_()
+            else:
+                _native.check(lib.trl_search_movegen(bp, self._side.cuda_stream), "trl_search_movegen")
             stamp(9, self._side.cuda_stream)
         if not mode:
             stamp(8, st)
@@ -268,7 +281,7 @@ class SelfPlayEngine:
             with torch.no_grad():
                 values, logits = self.cached_eval(self._cache_bufs, self.t["states"], self.t["leaf_state"], self.t["leaf_parent"], self.extras,
                                                   after_trunk=fork_movegen if mode == "heads" else (fork_movegen_tail if mode == "tail" else None),
-                                                  before_trunk=mark_encoded if mode == "tail" else None)
+                                                  before_trunk=mark_encoded if mode == "tail" else None, encoded=self._encoded)
         else:
             dt = 0 if self.feature_dtype == torch.float32 else 1
             _native.check(lib.trl_encode_features(self.t["states"].data_ptr(), self.t["leaf_state"].data_ptr(), self.G,
@@ -287,11 +300,19 @@ class SelfPlayEngine:
         stamp(5, st)
         if self.overlap_movegen:
             main.wait_stream(self._side)
-        fn, name = ((lib.trl_search_expand_select, "trl_search_expand_select") if self.fuse_expand_select
-                    else (lib.trl_search_expand, "trl_search_expand"))
-        _native.check(fn(bp, pp, values.data_ptr(), logits.data_ptr(), logits.stride(0),
-                         0 if logits.dtype == torch.float32 else 1, st), name)
+        ldt = 0 if logits.dtype == torch.float32 else 1
+        if self.fuse_encode:
+            cb = self._cache_bufs
+            _native.check(lib.trl_search_expand_select_encode(
+                bp, pp, values.data_ptr(), logits.data_ptr(), logits.stride(0), ldt, cb["cache"].data_ptr(),
+                cb["images"].data_ptr(), cb["dest"].data_ptr(), cb["count"].data_ptr(), self.extras.data_ptr(),
+                cb["own"].data_ptr(), cb["opp"].data_ptr(), st), "trl_search_expand_select_encode")
+        else:
+            fn, name = ((lib.trl_search_expand_select, "trl_search_expand_select") if self.fuse_expand_select
+                        else (lib.trl_search_expand, "trl_search_expand"))
+            _native.check(fn(bp, pp, values.data_ptr(), logits.data_ptr(), logits.stride(0), ldt, st), name)
         self._selected = self.fuse_expand_select
+        self._encoded = self.fuse_encode
         stamp(6, st)
 
     def enable_timeline(self):
@@ -329,10 +350,13 @@ class SelfPlayEngine:
             self._graph = g
             self._graph_has_select = not self.fuse_expand_select
         if n > 0 and not self._graph_has_select and not self._selected:
-            # the host touched games / controls after the capture: choose the leaves once outside the graph
+            # the host touched games / controls after the capture: choose (and encode) the leaves once outside the graph
             _native.check(self.lib.trl_search_select(ctypes.byref(self.buf), ctypes.byref(self.params),
                                                      torch.cuda.current_stream(self.device).cuda_stream), "trl_search_select")
             self._selected = True
+            if self.fuse_encode:
+                self.cached_eval.encode(self._cache_bufs, self.t["states"], self.t["leaf_state"], self.t["leaf_parent"], self.extras)
+                self._encoded = True
         for _ in range(max(n, 0)):
             self._graph.replay()
         self.steps_done += max(n, 0)

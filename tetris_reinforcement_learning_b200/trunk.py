@@ -195,17 +195,24 @@ class CachedTrunkEvaluator:
                 "own": z(n_leaves, torch.int32), "opp": z(n_leaves, torch.int32),
                 "x": z((n_leaves, self.k_pad), torch.bfloat16), "value": z(n_leaves, torch.bfloat16)}
 
-    def __call__(self, b, states, leaf_state, leaf_parent, extras, after_trunk=None, before_trunk=None):
+    def encode(self, b, states, leaf_state, leaf_parent, extras):
+        """Feature encoding of the selected leaves (a separate kernel; the engine normally has it done by
+        the fused expand + select + encode kernel of the previous step)."""
+        st = torch.cuda.current_stream(extras.device).cuda_stream   # b["count"] is zero here: the trunk kernel resets it
+        _native.check(_native.lib().trl_encode_features_cached(
+            states.data_ptr(), leaf_state.data_ptr(), leaf_parent.data_ptr(), leaf_state.numel(), b["cache"].data_ptr(),
+            b["images"].data_ptr(), b["dest"].data_ptr(), b["count"].data_ptr(), extras.data_ptr(),
+            b["own"].data_ptr(), b["opp"].data_ptr(), st), "trl_encode_features_cached")
+
+    def __call__(self, b, states, leaf_state, leaf_parent, extras, after_trunk=None, before_trunk=None, encoded=False):
         """b: make_buffers(); states uint8 [n_states*400], leaf_state / leaf_parent int32 [G], extras bf16
-        [G,105] (written here) -> (values bf16 [G], logits bf16 [G, 11584])."""
+        [G,105] (written here unless `encoded`) -> (values bf16 [G], logits bf16 [G, 11584])."""
         lib = _native.lib()
         dev = extras.device
         G = leaf_state.numel()
-        st = torch.cuda.current_stream(dev).cuda_stream   # b["count"] is zero here: the trunk kernel resets it
-        _native.check(lib.trl_encode_features_cached(
-            states.data_ptr(), leaf_state.data_ptr(), leaf_parent.data_ptr(), G, b["cache"].data_ptr(),
-            b["images"].data_ptr(), b["dest"].data_ptr(), b["count"].data_ptr(), extras.data_ptr(),
-            b["own"].data_ptr(), b["opp"].data_ptr(), st), "trl_encode_features_cached")
+        st = torch.cuda.current_stream(dev).cuda_stream
+        if not encoded:
+            self.encode(b, states, leaf_state, leaf_parent, extras)
         stamp = self.stamp or (lambda k, s: None)
         stamp(2, st)
         if before_trunk is not None:
