@@ -116,6 +116,11 @@ typedef struct TrlStepOut {
 /* ABI version of this header; bumped on any incompatible change. */
 int trl_abi_version(void);
 
+/* Programmatic dependent launch between the kernels of a self-play step (default on): the trunk kernel
+ * becomes resident and loads its weights while the search kernel before it drains.  0 switches it off
+ * (for A/B timing; results are identical either way). */
+void trl_set_pdl(int enabled);
+
 /* Profiling aid: a one-thread kernel writes the GPU's %globaltimer (ns) to *slot in stream order. */
 int trl_stamp_globaltimer(unsigned long long* slot, void* stream);
 /* Text of the last CUDA error seen by this thread's calls ("" if none). */

@@ -19,6 +19,7 @@ c_void_p, c_int, c_u64, c_u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, 
 SIGNATURES = {
     "trl_abi_version": (c_int, []),
     "trl_stamp_globaltimer": (c_int, [c_void_p, c_void_p]),
+    "trl_set_pdl": (None, [c_int]),
     "trl_last_error": (ctypes.c_char_p, []),
     "trl_sizeof_player": (c_int, []),
     "trl_sizeof_game": (c_int, []),

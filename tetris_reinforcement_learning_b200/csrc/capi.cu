@@ -40,6 +40,9 @@ cudaStream_t trl_host_stream(int which) {
     return g_host_stream[which];
 }
 
+int g_trl_pdl = 1;
+extern "C" void trl_set_pdl(int enabled) { g_trl_pdl = enabled ? 1 : 0; }
+
 extern "C" int trl_abi_version(void) { return 8; }
 extern "C" const char* trl_last_error(void) { return g_err; }
 extern "C" int trl_sizeof_player(void) { return (int)sizeof(TrlPlayer); }

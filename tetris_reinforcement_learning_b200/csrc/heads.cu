@@ -212,10 +212,9 @@ static int launch_heads(const void* feats_bf16, const int32_t* own_row, const in
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int blocks = ((n_leaves + kLeaves - 1) / kLeaves + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > sms) blocks = sms;
-    alphasame_heads_kernel<<<blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)feats_bf16, own_row, opp_row, (const __nv_bfloat16*)extras_bf16, n_leaves, weights, use_tanh,
-        (__nv_bfloat16*)x_out_bf16, (__nv_bfloat16*)value_out_bf16);
-    return trl_check(cudaGetLastError());
+    return trl_launch_ex(alphasame_heads_kernel, dim3(blocks), dim3(kWarpsPerBlock * 32), (size_t)smem, (cudaStream_t)stream, false, false,
+                         (const __nv_bfloat16*)feats_bf16, own_row, opp_row, (const __nv_bfloat16*)extras_bf16, n_leaves, weights,
+                         use_tanh, (__nv_bfloat16*)x_out_bf16, (__nv_bfloat16*)value_out_bf16);
 }
 
 extern "C" int trl_alphasame_heads(const void* feats_bf16, const void* extras_bf16, int n_leaves, const float* weights,

@@ -570,6 +570,8 @@ search_expand_select_kernel(TrlSearchBuffers B, TrlSearchParams P, const void* _
     __shared__ __align__(16) TrlGame s_game[kWarps];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = blockIdx.x * kWarps + wib;
+    trl_grid_dep_wait();
+    trl_grid_dep_launch();   // the next kernel (feature encoder / trunk) may move in as our blocks retire
     if (g >= B.n_games) return;
     expand_body(B, P, g, lane, &s_game[wib], values, logits, logits_stride, dtype);
     __syncwarp();
@@ -585,6 +587,8 @@ search_expand_select_encode_kernel(TrlSearchBuffers B, TrlSearchParams P, const 
     __shared__ __align__(16) TrlGame s_game[kWarps];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = blockIdx.x * kWarps + wib;
+    trl_grid_dep_wait();
+    trl_grid_dep_launch();   // the next kernel (feature encoder / trunk) may move in as our blocks retire
     if (g >= B.n_games) return;
     expand_body(B, P, g, lane, &s_game[wib], values, logits, logits_stride, dtype);
     __syncwarp();
@@ -650,9 +654,8 @@ extern "C" int trl_search_expand_select(const TrlSearchBuffers* buf, const TrlSe
     if (!buffers_ok(buf) || !prm || !values || !logits || logits_stride < TRL_POLICY_SIZE || (dtype != 0 && dtype != 1))
         return TRL_E_ARG;
     if (buf->n_games == 0) return TRL_OK;
-    search_expand_select_kernel<<<(buf->n_games + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(
-        *buf, *prm, values, logits, logits_stride, dtype);
-    return trl_check(cudaGetLastError());
+    return trl_launch_ex(search_expand_select_kernel, dim3((buf->n_games + kWarps - 1) / kWarps), dim3(kWarps * 32), 0,
+                         (cudaStream_t)stream, true, false, *buf, *prm, values, logits, logits_stride, dtype);
 }
 
 extern "C" int trl_search_expand_select_encode(const TrlSearchBuffers* buf, const TrlSearchParams* prm, const void* values,
@@ -666,7 +669,6 @@ extern "C" int trl_search_expand_select_encode(const TrlSearchBuffers* buf, cons
     TrlEncodeArgs E;
     E.cache = (__nv_bfloat16*)cache_bf16; E.images = (__nv_bfloat16*)images_bf16; E.image_dest = image_dest;
     E.n_images = n_images; E.extras = (__nv_bfloat16*)extras_bf16; E.own_row = own_row; E.opp_row = opp_row;
-    search_expand_select_encode_kernel<<<(buf->n_games + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(
-        *buf, *prm, values, logits, logits_stride, dtype, E);
-    return trl_check(cudaGetLastError());
+    return trl_launch_ex(search_expand_select_encode_kernel, dim3((buf->n_games + kWarps - 1) / kWarps), dim3(kWarps * 32), 0,
+                         (cudaStream_t)stream, true, false, *buf, *prm, values, logits, logits_stride, dtype, E);
 }

@@ -215,8 +215,6 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
     const float* s_const = consts.v;
     // per lane: I (cells staged), M[10] (MMAs of input column c complete), O[5] (operand columns 2p, 2p+1 written)
     const uint32_t bars = smem_u32(smem + off_bar);
-    if (n_images_dev) n_images = min(n_images, *n_images_dev);
-    const int n_groups = (n_images + kImgs - 1) / kImgs;
     if (tid == 0) atomicAdd(next_group + 2, 1);   // resident CTAs (trl_alphasame_trunk_rows_gate polls this)
 
     // ---- one-time setup ----
@@ -242,6 +240,12 @@ alphasame_trunk_rows_kernel(const __nv_bfloat16* __restrict__ grids, int n_image
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, s_tmem_base, 0);
+    // Everything above (weights, barriers, TMEM) is independent of the kernel before this one in the stream:
+    // with a programmatic dependent launch it overlapped that kernel's tail.  Its outputs (image list, count)
+    // are read only from here on.
+    trl_grid_dep_wait();
+    if (n_images_dev) n_images = min(n_images, *n_images_dev);
+    const int n_groups = (n_images + kImgs - 1) / kImgs;
 
     // epilogue thread geometry: slot = MMA row = TMEM lane; image j row y lives in slot 2 + 42 j + y
     const int set = warp >> 2;                              // owns columns 2*set, 2*set + 1
@@ -543,18 +547,11 @@ extern "C" int trl_alphasame_trunk_rows_indexed(const void* images_bf16, int32_t
     if (!counter) return TRL_E_NOMEM;
     g_last_counter = counter;
     g_last_grid = grid;
-    // Highest launch priority: inside a self-play step the leaf enumeration becomes ready at the same moment
-    // on a forked stream, and its blocks must queue BEHIND the trunk's CTAs (they move in as trunk CTAs run
-    // out of work) instead of taking SMs from them at the start.
-    int prio_lo = 0, prio_hi = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributePriority;
-    attr[0].val.priority = prio_hi;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return trl_check(cudaLaunchKernelEx(&cfg, alphasame_trunk_rows_kernel,
-        (const __nv_bfloat16*)images_bf16, max_images, n_blocks, n_lanes, (const uint4*)w_packed, host_consts(consts, n_blocks), (const uint4*)stem_w,
-        (__nv_bfloat16*)out_bf16, counter, n_images_dev, out_row, g_trace));
+    // Highest launch priority: inside a self-play step the leaf enumeration becomes ready at about the same
+    // time on a forked stream, and its blocks must queue BEHIND the trunk's CTAs.  Programmatic dependent
+    // launch: the CTAs move in and set themselves up while the search kernel before them drains.
+    return trl_launch_ex(alphasame_trunk_rows_kernel, dim3(grid), dim3(kThreads), (size_t)smem, (cudaStream_t)stream, true, true,
+                         (const __nv_bfloat16*)images_bf16, max_images, n_blocks, n_lanes, (const uint4*)w_packed,
+                         host_consts(consts, n_blocks), (const uint4*)stem_w, (__nv_bfloat16*)out_bf16, counter, n_images_dev,
+                         out_row, g_trace);
 }

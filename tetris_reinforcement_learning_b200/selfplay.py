@@ -97,7 +97,8 @@ class SelfPlayEngine:
     def __init__(self, config, evaluator, n_games, device="cuda:0", seed=0, first_game_id=0, game_id_stride=1,
                  feature_dtype=torch.float32, node_cap=None, sample_cap=None, restart_finished=True, save_all=None,
                  max_rounds=None, use_cuda_graph=True, overlap_movegen=True, reuse_trunk_features=True,
-                 reuse_sibling_placements=True, compact_movegen=True, fuse_expand_select=True, fuse_encode=True):
+                 reuse_sibling_placements=True, compact_movegen=True, fuse_expand_select=True, fuse_encode=True,
+                 steps_per_graph=4):
         from .state import ruleset_id
         self.ruleset = ruleset_id(config.ruleset)   # 's2' (default) or 's1': attack table + all-spin rule
         if config.move_algorithm != "convolutional":
@@ -165,6 +166,8 @@ class SelfPlayEngine:
         self._cache_bufs = self.cached_eval.make_buffers(ns, G, dev) if self.cached_eval is not None else None
         assert self.lib.trl_sizeof_search_ctl() == CTL_DTYPE.itemsize and self.lib.trl_sizeof_sample() == SAMPLE_DTYPE.itemsize
         self._graph = None
+        self._graph_k = None                        # steps_per_graph consecutive steps as ONE graph launch
+        self.steps_per_graph = max(1, int(steps_per_graph))
         self._stamps = None
         self._graph_has_select = True
         self._side = None
@@ -218,7 +221,7 @@ class SelfPlayEngine:
         """noise: float64 [G, moves_cap] Gamma draws used instead of the in-kernel sampler (tests)."""
         self.noise_override = torch.as_tensor(noise, dtype=torch.float64, device=self.device).contiguous()
         self.buf.noise_override = self.noise_override.data_ptr()
-        self._graph = None
+        self._graph = self._graph_k = None
 
     # ---- one simulation per game ---------------------------------------------------------
     def _step_eager(self):
@@ -320,7 +323,8 @@ class SelfPlayEngine:
         2 after encode, 3 after trunk, 4 after heads, 5 after policy GEMM, 6 after expand(+select), 8/9 around
         the forked enumeration).  Perturbs the step by one tiny kernel per stamp; re-captures the graph."""
         self._stamps = torch.zeros(16, dtype=torch.int64, device=self.device)
-        self._graph = None
+        self._graph = self._graph_k = None
+        self.steps_per_graph = 1
         if self.cached_eval is not None:
             self.cached_eval.stamp = self._stamp
 
@@ -357,9 +361,21 @@ class SelfPlayEngine:
             if self.fuse_encode:
                 self.cached_eval.encode(self._cache_bufs, self.t["states"], self.t["leaf_state"], self.t["leaf_parent"], self.extras)
                 self._encoded = True
-        for _ in range(max(n, 0)):
+        n = max(n, 0)
+        self.steps_done += n
+        K = self.steps_per_graph
+        if K > 1 and n >= K:
+            if self._graph_k is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for _ in range(K):
+                        self._step_eager()
+                self._graph_k = g
+            for _ in range(n // K):
+                self._graph_k.replay()
+            n %= K
+        for _ in range(n):
             self._graph.replay()
-        self.steps_done += max(n, 0)
 
     # ---- outputs ----------------------------------------------------------------------------
     def drain(self):

@@ -32,11 +32,15 @@ for v in args.variants:
     kw = {}
     for item in filter(None, v.split(",")):
         k, val = item.split("=")
+        if k == "pdl":
+            from tetris_reinforcement_learning_b200 import _native
+            _native.lib().trl_set_pdl(int(val))
+            continue
         if k == "rounds":
             from tetris_reinforcement_learning_b200 import _native
             _native.lib().trl_search_movegen_rounds(int(val))
             continue
-        kw[k] = val if k == "overlap_movegen" and not val.isdigit() else bool(int(val))
+        kw[k] = val if k == "overlap_movegen" and not val.isdigit() else (int(val) if k == "steps_per_graph" else bool(int(val)))
     eng = SelfPlayEngine(cfg, ev, args.games, seed=20261018, feature_dtype=torch.bfloat16, **kw)
     eng.step(12 + args.desync)
     eng.drain()
