@@ -382,7 +382,7 @@ int trl_search_expand_select(const TrlSearchBuffers* buf, const TrlSearchParams*
 int trl_search_expand_select_encode(const TrlSearchBuffers* buf, const TrlSearchParams* prm, const void* values,
                                     const void* logits, int logits_stride, int dtype, void* cache_bf16,
                                     void* images_bf16, int32_t* image_dest, int32_t* n_images, void* extras_bf16,
-                                    int32_t* own_row, int32_t* opp_row, void* stream);
+                                    int32_t* own_row, int32_t* opp_row, int32_t* row_of, void* stream);
 
 /* ------------------------------------------------------------------------------------ */
 /* fused convolutional trunk of the policy/value net (tcgen05 tensor cores)               */
@@ -428,15 +428,17 @@ int trl_alphasame_trunk_rows_max_blocks(void);
  * needs the trunk.  `cache` holds [n_states][2 players][400] bf16 trunk outputs.
  *
  * trl_encode_features_cached: per leaf g (leaf_state[g] >= 0) writes extras[g] (as
- * trl_encode_features), copies cache[parent][side to move] -> cache[leaf][side to move] (or, for a
- * root leaf, queues that board too), appends the 0/1 cells of every board that needs the trunk to
+ * trl_encode_features), lets the leaf inherit the parent's cache row of the side to move
+ * (row_of[leaf][side to move] = row_of[parent][side to move]; row_of is [n_states * 2]: the cache row
+ * holding the features of (state, player); for a root leaf that board is queued too), appends the 0/1
+ * cells of every board that needs the trunk to
  * `images` ([<= 2n][400] bf16, compact, *n_images = count) with image_dest[k] = cache row
  * (state*2 + player) the trunk must write, and sets own_row[g] / opp_row[g] = cache rows the heads
  * read (or -1).  *n_images must be zero on entry.
  */
 int trl_encode_features_cached(const TrlGame* states, const int32_t* leaf_state, const int32_t* leaf_parent, int n,
                                void* cache_bf16, void* images_bf16, int32_t* image_dest, int32_t* n_images,
-                               void* extras_bf16, int32_t* own_row, int32_t* opp_row, void* stream);
+                               void* extras_bf16, int32_t* own_row, int32_t* opp_row, int32_t* row_of, void* stream);
 
 /* trl_alphasame_trunk_rows with a device-side image count and scattered output rows:
  * out_bf16[out_row[k]][400] = trunk(images[k]) for k < *n_images_dev (capacity max_images).

@@ -42,13 +42,13 @@ SIGNATURES = {
     "trl_search_expand": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "trl_search_expand_select": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "trl_search_expand_select_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
-                                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "trl_alphasame_trunk": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "trl_alphasame_trunk_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "trl_alphasame_trunk_rows_max_blocks": (c_int, []),
     "trl_alphasame_heads": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "trl_alphasame_heads_weight_floats": (c_int, []),
-    "trl_encode_features_cached": (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] * 8),
+    "trl_encode_features_cached": (c_int, [c_void_p] * 3 + [c_int] + [c_void_p] * 9),
     "trl_alphasame_trunk_rows_indexed": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "trl_alphasame_trunk_rows_gate": (c_int, [c_void_p]),
     "trl_alphasame_heads_indexed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

@@ -70,7 +70,7 @@ encode_features_cached_kernel(const TrlGame* __restrict__ states, const int32_t*
                               const int32_t* __restrict__ leaf_parent, int n, __nv_bfloat16* __restrict__ cache,
                               __nv_bfloat16* __restrict__ images, int32_t* __restrict__ image_dest,
                               int32_t* __restrict__ n_images, __nv_bfloat16* __restrict__ extras,
-                              int32_t* __restrict__ own_row, int32_t* __restrict__ opp_row) {
+                              int32_t* __restrict__ own_row, int32_t* __restrict__ opp_row, int32_t* __restrict__ row_of) {
     __shared__ int s_new[kWarps];
     __shared__ int s_base;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -97,7 +97,7 @@ encode_features_cached_kernel(const TrlGame* __restrict__ states, const int32_t*
     for (int w = 0; w < wib; ++w) pos += s_new[w];
     TrlEncodeArgs E;
     E.cache = cache; E.images = images; E.image_dest = image_dest; E.n_images = n_images; E.extras = extras;
-    E.own_row = own_row; E.opp_row = opp_row;
+    E.own_row = own_row; E.opp_row = opp_row; E.row_of = row_of;
     trl_encode_cached_leaf(states[si], i, si, pi, pos, lane, E);
 }
 
@@ -106,14 +106,14 @@ encode_features_cached_kernel(const TrlGame* __restrict__ states, const int32_t*
 extern "C" int trl_encode_features_cached(const TrlGame* states, const int32_t* leaf_state, const int32_t* leaf_parent,
                                           int n, void* cache_bf16, void* images_bf16, int32_t* image_dest,
                                           int32_t* n_images, void* extras_bf16, int32_t* own_row, int32_t* opp_row,
-                                          void* stream) {
+                                          int32_t* row_of, void* stream) {
     if (n < 0 || !states || !leaf_state || !leaf_parent || !cache_bf16 || !images_bf16 || !image_dest || !n_images ||
-        !extras_bf16 || !own_row || !opp_row)
+        !extras_bf16 || !own_row || !opp_row || !row_of)
         return TRL_E_ARG;
     if (n == 0) return TRL_OK;
     encode_features_cached_kernel<<<(n + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(
         states, leaf_state, leaf_parent, n, (__nv_bfloat16*)cache_bf16, (__nv_bfloat16*)images_bf16, image_dest,
-        n_images, (__nv_bfloat16*)extras_bf16, own_row, opp_row);
+        n_images, (__nv_bfloat16*)extras_bf16, own_row, opp_row, row_of);
     return trl_check(cudaGetLastError());
 }
 

@@ -3,7 +3,7 @@
 //
 // Replaces ai.game_to_X for one leaf (reference ai.py:1364-1413) in the trunk-feature-cache form of
 // include/trl.h (trl_encode_features_cached): extras, the 0/1 cells of the boards whose trunk features
-// are unknown, the cache row copy of the side to move, own_row / opp_row.  One warp per leaf.
+// are unknown, the cache row of the side to move (inherited from the parent state), own_row / opp_row.  One warp per leaf.
 #pragma once
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -18,6 +18,7 @@ struct TrlEncodeArgs {
     __nv_bfloat16* extras;       // [n][105]
     int32_t* own_row;            // [n]
     int32_t* opp_row;            // [n]
+    int32_t* row_of;             // [n_states * 2] cache row that holds the features of (state, player)
 };
 
 // g: the leaf state (any address space), i: leaf index, si / pi: state index of the leaf / its parent
@@ -26,17 +27,19 @@ __device__ __forceinline__ void trl_encode_cached_leaf(const TrlGame& g, int i, 
                                                        const TrlEncodeArgs& E) {
     constexpr int kCells = TRL_ROWS * TRL_COLS, kExtras = 105;
     const int turn = g.turn & 1;
+    int own_r = si * 2 + turn;
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
         const int pl = side == 0 ? turn : 1 - turn;
         const TrlPlayer& p = g.players[pl];
         const int row = si * 2 + pl;
         if (side == 0 && pi >= 0) {
-            // the side to move did not move: its board is the parent's, so are its trunk features
-            const uint4* src = reinterpret_cast<const uint4*>(E.cache + (size_t)(pi * 2 + pl) * kCells);
-            uint4* dst = reinterpret_cast<uint4*>(E.cache + (size_t)row * kCells);
-            for (int c = lane; c < kCells / 8; c += 32) dst[c] = src[c];     // 800 B = 50 x 16 B
+            // the side to move did not move: its board is the parent's, so are its trunk features: the leaf
+            // points at the row that holds them (no 800-byte copy)
+            own_r = E.row_of[pi * 2 + pl];
+            if (lane == 0) E.row_of[row] = own_r;
         } else {
+            if (lane == 0) E.row_of[row] = row;
             const int k = pos + ((side == 1 && pi < 0) ? 1 : 0);
             // lane = board row: 10 cells = five words of two bf16 (1.0 = 0x3F80)
             uint32_t* out = reinterpret_cast<uint32_t*>(E.images + (size_t)k * kCells);
@@ -66,7 +69,7 @@ __device__ __forceinline__ void trl_encode_cached_leaf(const TrlGame& g, int i, 
     }
     if (lane == 0) {
         E.extras[(size_t)i * kExtras + 104] = __float2bfloat16((float)turn);   // players[turn].color == turn
-        E.own_row[i] = si * 2 + turn;
+        E.own_row[i] = own_r;
         E.opp_row[i] = si * 2 + (1 - turn);
     }
 }

@@ -37,21 +37,19 @@ alphasame_heads_kernel(const __nv_bfloat16* __restrict__ feats,    // [2G][400]:
     extern __shared__ __align__(16) float sm[];
     float* w = sm;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    {   // weights -> shared memory: 16-byte loads, several in flight per thread (a scalar copy loop is
-        // latency bound: 59 dependent L2 round trips per thread)
-        const float4* src = reinterpret_cast<const float4*>(weights);
-        float4* dst = reinterpret_cast<float4*>(w);
+    {   // weights -> shared memory with cp.async (no registers, all 15 16-byte copies of a thread in flight);
+        // they are only waited for before the first dense layer, so the copy runs under the input gather
         constexpr int kVec = kWFloats / 4;
-        static_assert(kWFloats % 4 == 0, "weights are copied as float4");
-#pragma unroll 8
-        for (int i = tid; i < kVec; i += kWarpsPerBlock * 32) dst[i] = src[i];
+        static_assert(kWFloats % 4 == 0, "weights are copied in 16-byte pieces");
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(w);
+        for (int i = tid; i < kVec; i += kWarpsPerBlock * 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16u * (uint32_t)i), "l"(weights + 4 * i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    __syncthreads();
+    bool weights_ready = false;
     // per warp: xs[k][leaf] (528 x 4) and fo[k][leaf] (400 x 4), leaf-interleaved so one LDS.128 feeds 4 FMAs
     float4* xs = reinterpret_cast<float4*>(sm + kWFloats) + warp * (kPad + kFeat);
     float4* fo = xs + kPad;
-    float* xs_f = reinterpret_cast<float*>(xs);
-    float* fo_f = reinterpret_cast<float*>(fo);
     const int og = lane & 3, kk = lane >> 2;   // output quad 4og..4og+3, k = kk mod 8
     const int n_quads = (G + kLeaves - 1) / kLeaves;
     for (int q = blockIdx.x * kWarpsPerBlock + warp; q < n_quads; q += gridDim.x * kWarpsPerBlock) {
@@ -64,7 +62,6 @@ alphasame_heads_kernel(const __nv_bfloat16* __restrict__ feats,    // [2G][400]:
             rb[j] = (g < G) ? (own_row ? opp_row[g] : G + g) : -1;
             any = any || ra[j] >= 0;
         }
-        if (!any) continue;   // warp-uniform
         // ---- stage: own features, side inputs, opponent features (zeros for skipped leaves) ----
         // all global loads of the pass are issued before the first use (the pass is latency bound otherwise)
         constexpr int kFI = (kFeat / 2 + 31) / 32;            // 7 bf16x2 words per lane and feature row
@@ -89,27 +86,41 @@ alphasame_heads_kernel(const __nv_bfloat16* __restrict__ feats,    // [2G][400]:
                 ue[j][t] = (ra[j] >= 0 && i < 2 * kSide + 1) ? ex[i] : (uint16_t)0;
             }
         }
-#pragma unroll
-        for (int j = 0; j < kLeaves; ++j) {
-#pragma unroll
-            for (int t = 0; t < kFI; ++t) {
-                const int i = lane + 32 * t;
-                if (i < kFeat / 2) {
-                    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ua[j][t]));
-                    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ub[j][t]));
-                    xs_f[(2 * i) * kLeaves + j] = a.x; xs_f[(2 * i + 1) * kLeaves + j] = a.y;
-                    fo_f[(2 * i) * kLeaves + j] = b.x; fo_f[(2 * i + 1) * kLeaves + j] = b.y;
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < kEI; ++t) {
-                const int i = lane + 32 * t;
-                if (i < 2 * kSide + 1)
-                    xs_f[(kFeat + i + (i >= kSide ? kOpp : 0)) * kLeaves + j] = __bfloat162float(__ushort_as_bfloat16(ue[j][t]));
-            }
-            if (lane < kOpp) xs_f[(kFeat + kSide + lane) * kLeaves + j] = 0.f;
-            if (lane < kPad - kIn) xs_f[(kIn + lane) * kLeaves + j] = 0.f;
+        if (!weights_ready) {
+            // first pass of this warp (every thread of the block gets here exactly once, here or after the loop):
+            // the gather above is in flight while the block's weights land
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            weights_ready = true;
         }
+        if (!any) continue;   // warp-uniform
+        // feature word i = features 2i, 2i+1 of all four leaves -> two float4 rows per tensor (STS.128)
+#pragma unroll
+        for (int t = 0; t < kFI; ++t) {
+            const int i = lane + 32 * t;
+            if (i < kFeat / 2) {
+                float2 a[kLeaves], b[kLeaves];
+#pragma unroll
+                for (int j = 0; j < kLeaves; ++j) {
+                    a[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ua[j][t]));
+                    b[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ub[j][t]));
+                }
+                xs[2 * i] = make_float4(a[0].x, a[1].x, a[2].x, a[3].x);
+                xs[2 * i + 1] = make_float4(a[0].y, a[1].y, a[2].y, a[3].y);
+                fo[2 * i] = make_float4(b[0].x, b[1].x, b[2].x, b[3].x);
+                fo[2 * i + 1] = make_float4(b[0].y, b[1].y, b[2].y, b[3].y);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < kEI; ++t) {
+            const int i = lane + 32 * t;
+            if (i < 2 * kSide + 1)
+                xs[kFeat + i + (i >= kSide ? kOpp : 0)] =
+                    make_float4(__bfloat162float(__ushort_as_bfloat16(ue[0][t])), __bfloat162float(__ushort_as_bfloat16(ue[1][t])),
+                                __bfloat162float(__ushort_as_bfloat16(ue[2][t])), __bfloat162float(__ushort_as_bfloat16(ue[3][t])));
+        }
+        if (lane < kOpp) xs[kFeat + kSide + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < kPad - kIn) xs[kIn + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
         // ---- osidedense: 16 outputs x 400 for 4 leaves; lanes = (k mod 8, output quad) ----
         // per k one LDS.128 of weights (4 outputs) and one LDS.128 of inputs (4 leaves) feed 16 independent FMAs;
@@ -147,12 +158,13 @@ alphasame_heads_kernel(const __nv_bfloat16* __restrict__ feats,    // [2G][400]:
         }
         __syncwarp();
         // ---- x out (bf16, 528 wide) ----
+        for (int i = lane; i < kPad / 2; i += 32) {
+            const float4 e = xs[2 * i], o4 = xs[2 * i + 1];
+            const float ev[kLeaves] = {e.x, e.y, e.z, e.w}, ov[kLeaves] = {o4.x, o4.y, o4.z, o4.w};
 #pragma unroll
-        for (int j = 0; j < kLeaves; ++j) {
-            if (ra[j] < 0) continue;
-            __nv_bfloat162* xo = reinterpret_cast<__nv_bfloat162*>(x_out + (size_t)(q * kLeaves + j) * kPad);
-            for (int i = lane; i < kPad / 2; i += 32)
-                xo[i] = __floats2bfloat162_rn(xs_f[(2 * i) * kLeaves + j], xs_f[(2 * i + 1) * kLeaves + j]);
+            for (int j = 0; j < kLeaves; ++j)
+                if (ra[j] >= 0)
+                    reinterpret_cast<__nv_bfloat162*>(x_out + (size_t)(q * kLeaves + j) * kPad)[i] = __floats2bfloat162_rn(ev[j], ov[j]);
         }
         // ---- value head ----
 #pragma unroll
@@ -188,6 +200,10 @@ alphasame_heads_kernel(const __nv_bfloat16* __restrict__ feats,    // [2G][400]:
                 value_out[q * kLeaves + j] = __float2bfloat16(use_tanh ? tanhf(v[j]) : 1.f / (1.f + __expf(-v[j])));
         }
         __syncwarp();
+    }
+    if (!weights_ready) {   // a warp without a pass still owes the block its barrier arrival
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
     }
 }
 

@@ -172,15 +172,30 @@ __device__ void select_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
         const bool check_forced = forced_on && node == 0;
         double best = -1.0;  // max_child_score starts at -1 (ai.py:348)
         int best_i = -1;
-        for (int c = lane; c < C; c += 32) {
-            const int vc = B.visits[nb + base + c];
-            const double pr = B.prior[nb + base + c];
-            double q, u;
-            if (vc == 0) { q = fpu_q; u = unvisited_scale * pr; }
-            else { q = B.value_sum[nb + base + c] / (double)vc; u = P.cpuct * pr * sqrt_parent / (P.dpuct + (double)vc); }
-            double score = q + u;
-            if (check_forced && vc >= 1 && (double)vc < sqrt(P.c_forced * pr * (double)pv)) score = INFINITY;
-            if (score >= best) { best = score; best_i = c; }
+        for (int c0 = lane; c0 < C; c0 += 64) {
+            // two children per lane with all six loads in flight (a typical node has ~50 children)
+            int vcs[2]; double prs[2], vss[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = c0 + 32 * h;
+                const bool in = c < C;
+                vcs[h] = in ? B.visits[nb + base + c] : 0;
+                prs[h] = in ? B.prior[nb + base + c] : 0.0;
+                vss[h] = in ? B.value_sum[nb + base + c] : 0.0;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = c0 + 32 * h;
+                if (c >= C) break;
+                const int vc = vcs[h];
+                const double pr = prs[h];
+                double q, u;
+                if (vc == 0) { q = fpu_q; u = unvisited_scale * pr; }
+                else { q = vss[h] / (double)vc; u = P.cpuct * pr * sqrt_parent / (P.dpuct + (double)vc); }
+                double score = q + u;
+                if (check_forced && vc >= 1 && (double)vc < sqrt(P.c_forced * pr * (double)pv)) score = INFINITY;
+                if (score >= best) { best = score; best_i = c; }
+            }
         }
         warp_argmax_last(best, best_i);
         if (best_i < 0) best_i = C - 1;  // every score < -1 (tanh only): the reference would raise
@@ -661,14 +676,17 @@ extern "C" int trl_search_expand_select(const TrlSearchBuffers* buf, const TrlSe
 extern "C" int trl_search_expand_select_encode(const TrlSearchBuffers* buf, const TrlSearchParams* prm, const void* values,
                                                const void* logits, int logits_stride, int dtype, void* cache_bf16,
                                                void* images_bf16, int32_t* image_dest, int32_t* n_images,
-                                               void* extras_bf16, int32_t* own_row, int32_t* opp_row, void* stream) {
+                                               void* extras_bf16, int32_t* own_row, int32_t* opp_row, int32_t* row_of,
+                                               void* stream) {
     if (!buffers_ok(buf) || !prm || !values || !logits || logits_stride < TRL_POLICY_SIZE || (dtype != 0 && dtype != 1) ||
-        !buf->leaf_parent || !cache_bf16 || !images_bf16 || !image_dest || !n_images || !extras_bf16 || !own_row || !opp_row)
+        !buf->leaf_parent || !cache_bf16 || !images_bf16 || !image_dest || !n_images || !extras_bf16 || !own_row || !opp_row ||
+        !row_of)
         return TRL_E_ARG;
     if (buf->n_games == 0) return TRL_OK;
     TrlEncodeArgs E;
     E.cache = (__nv_bfloat16*)cache_bf16; E.images = (__nv_bfloat16*)images_bf16; E.image_dest = image_dest;
     E.n_images = n_images; E.extras = (__nv_bfloat16*)extras_bf16; E.own_row = own_row; E.opp_row = opp_row;
+    E.row_of = row_of;
     return trl_launch_ex(search_expand_select_encode_kernel, dim3((buf->n_games + kWarps - 1) / kWarps), dim3(kWarps * 32), 0,
                          (cudaStream_t)stream, true, false, *buf, *prm, values, logits, logits_stride, dtype, E);
 }

@@ -309,7 +309,7 @@ class SelfPlayEngine:
             _native.check(lib.trl_search_expand_select_encode(
                 bp, pp, values.data_ptr(), logits.data_ptr(), logits.stride(0), ldt, cb["cache"].data_ptr(),
                 cb["images"].data_ptr(), cb["dest"].data_ptr(), cb["count"].data_ptr(), self.extras.data_ptr(),
-                cb["own"].data_ptr(), cb["opp"].data_ptr(), st), "trl_search_expand_select_encode")
+                cb["own"].data_ptr(), cb["opp"].data_ptr(), cb["rowof"].data_ptr(), st), "trl_search_expand_select_encode")
         else:
             fn, name = ((lib.trl_search_expand_select, "trl_search_expand_select") if self.fuse_expand_select
                         else (lib.trl_search_expand, "trl_search_expand"))

@@ -192,7 +192,7 @@ class CachedTrunkEvaluator:
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)  # noqa: E731
         return {"cache": z((n_states * 2, 400), torch.bfloat16), "images": z((2 * n_leaves, 400), torch.bfloat16),
                 "dest": z(2 * n_leaves, torch.int32), "count": z(1, torch.int32),
-                "own": z(n_leaves, torch.int32), "opp": z(n_leaves, torch.int32),
+                "own": z(n_leaves, torch.int32), "opp": z(n_leaves, torch.int32), "rowof": z(n_states * 2, torch.int32),
                 "x": z((n_leaves, self.k_pad), torch.bfloat16), "value": z(n_leaves, torch.bfloat16)}
 
     def encode(self, b, states, leaf_state, leaf_parent, extras):
@@ -202,7 +202,7 @@ class CachedTrunkEvaluator:
         _native.check(_native.lib().trl_encode_features_cached(
             states.data_ptr(), leaf_state.data_ptr(), leaf_parent.data_ptr(), leaf_state.numel(), b["cache"].data_ptr(),
             b["images"].data_ptr(), b["dest"].data_ptr(), b["count"].data_ptr(), extras.data_ptr(),
-            b["own"].data_ptr(), b["opp"].data_ptr(), st), "trl_encode_features_cached")
+            b["own"].data_ptr(), b["opp"].data_ptr(), b["rowof"].data_ptr(), st), "trl_encode_features_cached")
 
     def __call__(self, b, states, leaf_state, leaf_parent, extras, after_trunk=None, before_trunk=None, encoded=False):
         """b: make_buffers(); states uint8 [n_states*400], leaf_state / leaf_parent int32 [G], extras bf16
