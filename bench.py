@@ -156,7 +156,9 @@ def run_selfplay(args, rank, world, local_rank):
     ms = timed(eng)
     samples, _ = eng.drain()
     ctl = eng.get_ctl()
-    launches_per_step = 8 if reuse else 7   # select, movegen, (count reset,) encode, trunk, heads, policy GEMM, expand
+    # own kernels per step (the cuBLAS policy GEMM is not counted): with the cached evaluator gate, enumeration,
+    # trunk, heads, expand+select+encode; else select, enumeration, encode, expand (+ the PyTorch net)
+    launches_per_step = 5 if reuse else 4
     ms_both = None
     if reuse and not args.no_game_length:
         # the same step with BOTH boards of every leaf through the trunk (the reference's amount of work)
@@ -209,7 +211,9 @@ def run_selfplay(args, rank, world, local_rank):
         "mcts_sims_per_sec": {
             "value": sims_per_s, "unit": "sims/s", "games_per_gpu": G, "n_gpus": world, "steps": args.selfplay_steps,
             "ms_per_step": ms / args.selfplay_steps, "max_iter": 160, "net": "AlphaSame(blocks=10, filters=16) bf16, " + ("PyTorch/cuDNN" if args.net_path == "pytorch" else
-                                                               "row-Toeplitz tcgen05 trunk + fused heads kernel + cuBLAS policy GEMM") + ", CUDA graph",
+                                                               "row-Toeplitz tcgen05 trunk + fused heads kernel + cuBLAS policy GEMM") + ", CUDA graph (4 steps per launch)",
+            "step": "enumeration of the leaves without a cached sibling list (compacted, queued behind the trunk on a forked stream) || "
+                    "trunk -> heads -> policy GEMM -> expand + select + feature encoding of the next leaves (one kernel)",
             "trunk_feature_reuse": reuse, "sibling_placement_reuse": bool(getattr(eng_flags, "reuse_sibling_placements", False)),
             "trunk_feature_reuse_note": "exact: a move changes only the mover's board, so per simulation one board goes through the "
                                         "trunk and the other board's features are the parent state's (bit-identical searches, "
@@ -276,7 +280,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -442,10 +446,29 @@ def run_ours(args, rank, world, local_rank):
     if also is not None:
         line["also"] = also
         line["gpu_launches"] += also.pop("_launches", 0)
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    # Libraries chat on stdout (e.g. "NCCL version ..." when the box exports NCCL_DEBUG=VERSION): keep fd 1 for
+    # the JSON line only and send everything else to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
