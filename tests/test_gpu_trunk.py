@@ -140,7 +140,7 @@ def test_compact_movegen_and_fused_expand_select_are_exact():
     enumeration over a compacted work list on as few SMs as the count needs (movegen_list_kernel)
     instead of one call slot per game, (ii) expand(t), select(t+1) and the feature encoding of the selected
     leaves as one kernel, (iii) where the enumeration overlaps the network (queued behind the trunk kernel,
-    next to it, next to heads + GEMM, or serial)."""
+    next to it, next to heads + GEMM, or serial), (iv) the backup over the recorded path in parallel lanes."""
     import copy
     import torch
     from tetris_reinforcement_learning_b200 import architectures as arch, trunk
@@ -151,11 +151,12 @@ def test_compact_movegen_and_fused_expand_select_are_exact():
     cfg = Config(visual=False, ruleset="s2", model="pytorch", model_config=arch.AlphaSameConfig(blocks=2), MAX_ITER=24,
                  training=True, use_forced_playouts_and_policy_target_pruning=True)
     out = []
-    for compact, fuse, fuse_enc, overlap in ((True, True, True, True), (False, False, False, "trunk"), (True, False, False, "heads"),
-                                             (False, True, False, False), (True, True, False, "tail")):
+    for compact, fuse, fuse_enc, overlap, par in ((True, True, True, True, True), (False, False, False, "trunk", False),
+                                                  (True, False, False, "heads", True), (False, True, False, False, False),
+                                                  (True, True, False, "tail", True)):
         eng = SelfPlayEngine(cfg, ev, 2500, seed=4, feature_dtype=torch.bfloat16, max_rounds=3, sample_cap=65536,
                              compact_movegen=compact, fuse_expand_select=fuse, fuse_encode=fuse_enc,
-                             overlap_movegen=overlap)   # 2500 games: > 148 x 16 call slots at iteration 0
+                             overlap_movegen=overlap, parallel_backup=par)   # 2500 games: > 148 x 16 call slots at iteration 0
         assert eng.fuse_encode == fuse_enc
         eng.step(150)
         eng.drain()               # reading results between graph replays must not disturb a pending selection

@@ -113,5 +113,5 @@ class SearchBuffers(ctypes.Structure):
                                                "ctl", "games", "leaf_state", "legal", "n_legal",
                                                "samples", "sample_count", "ends", "end_count",
                                                "next_game_id", "noise_override", "leaf_parent",
-                                               "legal_cache", "legal_cache_n", "movegen_index",
+                                               "legal_cache", "legal_cache_n", "movegen_index", "path",
                                                "movegen_list", "movegen_count")]

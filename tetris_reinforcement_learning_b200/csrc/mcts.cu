@@ -26,7 +26,7 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 
 static_assert(sizeof(TrlSearchCtl) == 80, "TrlSearchCtl layout");
 static_assert(sizeof(TrlSearchParams) == 160, "TrlSearchParams layout");
-static_assert(sizeof(TrlSearchBuffers) == 248, "TrlSearchBuffers layout");
+static_assert(sizeof(TrlSearchBuffers) == 256, "TrlSearchBuffers layout");
 static_assert(sizeof(TrlGameEnd) == 32, "TrlGameEnd layout");
 static_assert(sizeof(TrlSample) == 20 + 400 + 3 * 2 * TRL_SAMPLE_MOVES, "TrlSample layout");
 
@@ -159,7 +159,9 @@ __device__ void select_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
     // ---- select (ai.py:346-393) ----
     int node = 0, depth = 0;
     const bool forced_on = P.use_forced && P.training && !(P.use_playout_cap && ctl->fast);
+    int* path = B.path ? B.path + (size_t)g * 32 : nullptr;
     while (true) {
+        if (path && lane == 0 && depth <= 30) path[1 + depth] = node;
         const int s = B.slot[nb + node];
         if (s < 0) break;
         const int C = B.n_children[sb + s];
@@ -203,12 +205,16 @@ __device__ void select_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
         ++depth;
     }
 
+    if (path && lane == 0) path[0] = depth <= 30 ? depth : -1;
+
     // ---- materialise the leaf (ai.py:398-403) ----
     int s = B.slot[nb + node];
     int parent_state = -1;
+    int parent_cached = -1;   // number of legal moves already listed under the parent (loaded early: used after the env step)
     if (node != 0) {
         const int ps = B.slot[nb + B.parent[nb + node]];
         parent_state = (int)(sb + ps);
+        if (B.legal_cache_n) parent_cached = B.legal_cache_n[parent_state];
         if (s < 0) s = ctl->n_states;  // first visit: new state slot (uniform across lanes)
         copy_game(sg, reinterpret_cast<const uint32_t*>(&B.states[sb + ps]), lane);
         __syncwarp();
@@ -248,7 +254,7 @@ __device__ void select_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
         if (B.leaf_parent) B.leaf_parent[g] = leaf_pi;
         if (B.movegen_index) {
             // all children of a state share the side to move's board and pieces: enumerate once per parent
-            const bool hit = B.legal_cache_n && parent_state >= 0 && B.legal_cache_n[parent_state] >= 0;
+            const bool hit = parent_cached >= 0;
             const bool need = !(kind == 2 || hit);
             B.movegen_index[g] = need ? (int)(sb + s) : -1;
             if (need && B.movegen_list) B.movegen_list[atomicAdd(B.movegen_count, 1u)] = g;
@@ -456,7 +462,8 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
         const uint16_t* mv = B.legal + (size_t)g * B.moves_cap;
         int C = (kind == 0) ? (int)B.n_legal[g] : 0;
         if (B.legal_cache_n && B.movegen_index && leaf != 0) {
-            const size_t pstate = sb + (size_t)B.slot[nb + B.parent[nb + leaf]];
+            // the selection left the parent's state index in leaf_parent (two dependent loads less)
+            const size_t pstate = B.leaf_parent ? (size_t)B.leaf_parent[g] : sb + (size_t)B.slot[nb + B.parent[nb + leaf]];
             const int cached = B.legal_cache_n[pstate];
             uint16_t* slot_mv = B.legal_cache + pstate * (size_t)B.moves_cap;
             if (cached >= 0) {
@@ -529,7 +536,22 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
     __syncwarp();
 
     // ---- backup (ai.py:511-533) ----
-    if (lane == 0) {
+    const int* path = B.path ? B.path + (size_t)g * 32 : nullptr;
+    const int pdepth = path ? path[0] : -1;
+    if (pdepth >= 0 && path[1 + pdepth] == leaf) {
+        // the selection recorded the path: lane i updates the ancestor at depth i (every node gets exactly one
+        // addition, as in the serial walk below)
+        const double pos = negate_value(value, tanh_mode);
+        const double neg = negate_value(pos, tanh_mode);
+        const int leaf_turn = B.states[sb + ls].turn;
+        if (lane <= pdepth) {
+            const int n = path[1 + lane];
+            const int ns = B.slot[nb + n];
+            B.visits[nb + n] += 1;
+            B.value_sum[nb + n] += (B.states[sb + ns].turn == leaf_turn) ? pos : neg;
+        }
+        if (lane == 0) { ctl->iter += 1; ctl->sims += 1; }
+    } else if (lane == 0) {
         const double pos = negate_value(value, tanh_mode);
         const double neg = negate_value(pos, tanh_mode);
         const int leaf_turn = B.states[sb + ls].turn;

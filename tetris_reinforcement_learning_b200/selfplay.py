@@ -98,7 +98,7 @@ class SelfPlayEngine:
                  feature_dtype=torch.float32, node_cap=None, sample_cap=None, restart_finished=True, save_all=None,
                  max_rounds=None, use_cuda_graph=True, overlap_movegen=True, reuse_trunk_features=True,
                  reuse_sibling_placements=True, compact_movegen=True, fuse_expand_select=True, fuse_encode=True,
-                 steps_per_graph=4):
+                 steps_per_graph=4, parallel_backup=True):
         from .state import ruleset_id
         self.ruleset = ruleset_id(config.ruleset)   # 's2' (default) or 's1': attack table + all-spin rule
         if config.move_algorithm != "convolutional":
@@ -132,7 +132,7 @@ class SelfPlayEngine:
             "leaf_state": z(G, torch.int32), "legal": z(G * self.moves_cap, torch.int16), "n_legal": z(G, torch.int16),
             "samples": z(self.sample_cap * SAMPLE_DTYPE.itemsize, torch.uint8), "sample_count": z(1, torch.int32),
             "ends": z(self.end_cap * GAME_END_DTYPE.itemsize, torch.uint8), "end_count": z(1, torch.int32),
-            "next_game_id": z(1, torch.int32), "leaf_parent": z(G, torch.int32),
+            "next_game_id": z(1, torch.int32), "leaf_parent": z(G, torch.int32), "path": z(G * 32, torch.int32),
         }
         # exact reuse of legal-placement lists between siblings (include/trl.h, TrlSearchBuffers.legal_cache)
         self.reuse_sibling_placements = bool(reuse_sibling_placements)
@@ -162,6 +162,8 @@ class SelfPlayEngine:
             setattr(b, name, ten.data_ptr())
         b.noise_override = None
         b.leaf_parent = self.t["leaf_parent"].data_ptr()
+        if not parallel_backup:
+            b.path = None        # the backup then walks the parent links serially
         self.buf = b
         self._cache_bufs = self.cached_eval.make_buffers(ns, G, dev) if self.cached_eval is not None else None
         assert self.lib.trl_sizeof_search_ctl() == CTL_DTYPE.itemsize and self.lib.trl_sizeof_sample() == SAMPLE_DTYPE.itemsize
