@@ -340,9 +340,9 @@ typedef struct TrlSearchBuffers {
      * an enumeration; trl_search_movegen consumes the list with as few, fully occupied thread blocks as
      * the count needs (one 16-call block per SM), so the SMs it does not use are free for the network
      * kernels that run beside it, and leaves both counters at zero for the next step. */
-    int32_t* path;                           /* [n_games * 32] or NULL: [0] depth of the selected leaf (-1: deeper
-                                                than 30), [1 + i] node at depth i; lets the backup update the
-                                                ancestors in parallel lanes instead of walking parent links   */
+    int32_t* path;                           /* [n_games * 64] or NULL: [0] depth of the selected leaf (-1: deeper
+                                                than 30), [1 + i] node and [32 + i] state slot at depth i; lets
+                                                expand / backup work without walking parent and slot links     */
     int32_t* movegen_list;                   /* [n_games] game indices, arbitrary order                   */
     uint32_t* movegen_count;                 /* [4] entries in movegen_list; finished blocks; next ticket; pad.
                                                 Zero between steps (the enumeration kernel resets them)    */

@@ -23,8 +23,9 @@ struct TrlEncodeArgs {
 
 // g: the leaf state (any address space), i: leaf index, si / pi: state index of the leaf / its parent
 // (pi < 0: root, both boards are new), pos: first slot in `images` reserved for this leaf.
+// inherit_row: row_of[parent][side to move] if the caller has loaded it already, else -1 (loaded here).
 __device__ __forceinline__ void trl_encode_cached_leaf(const TrlGame& g, int i, int si, int pi, int pos, int lane,
-                                                       const TrlEncodeArgs& E) {
+                                                       const TrlEncodeArgs& E, int inherit_row = -1) {
     constexpr int kCells = TRL_ROWS * TRL_COLS, kExtras = 105;
     const int turn = g.turn & 1;
     int own_r = si * 2 + turn;
@@ -36,7 +37,7 @@ __device__ __forceinline__ void trl_encode_cached_leaf(const TrlGame& g, int i, 
         if (side == 0 && pi >= 0) {
             // the side to move did not move: its board is the parent's, so are its trunk features: the leaf
             // points at the row that holds them (no 800-byte copy)
-            own_r = E.row_of[pi * 2 + pl];
+            own_r = inherit_row >= 0 ? inherit_row : E.row_of[pi * 2 + pl];
             if (lane == 0) E.row_of[row] = own_r;
         } else {
             if (lane == 0) E.row_of[row] = row;

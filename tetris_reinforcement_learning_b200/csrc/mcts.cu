@@ -23,6 +23,8 @@ namespace {
 constexpr int kWarps = 4;
 constexpr int kGameWords = sizeof(TrlGame) / 4;
 constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr int TRL_PATH_INTS = 64;        // per game: [0] depth, [1..31] nodes, [32..63] state slots along the selected path
+constexpr int TRL_PATH_MAX_DEPTH = 30;
 
 static_assert(sizeof(TrlSearchCtl) == 80, "TrlSearchCtl layout");
 static_assert(sizeof(TrlSearchParams) == 160, "TrlSearchParams layout");
@@ -101,7 +103,7 @@ __device__ __forceinline__ bool game_terminal(const TrlGame* g) {
 // leaf_si / leaf_pi (all lanes): state index of the position to evaluate and of the state it was reached
 // from, as written to leaf_state[g] / leaf_parent[g]; on return *sgame holds the leaf state.
 __device__ void select_body(const TrlSearchBuffers& B, const TrlSearchParams& P, int g, int lane, TrlGame* sgame,
-                            int& leaf_si, int& leaf_pi) {
+                            int& leaf_si, int& leaf_pi, const int32_t* __restrict__ row_of = nullptr, int2* parent_rows = nullptr) {
     TrlSearchCtl* ctl = &B.ctl[g];
     leaf_si = -1; leaf_pi = -1;
     if (!ctl->active) {
@@ -159,10 +161,12 @@ __device__ void select_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
     // ---- select (ai.py:346-393) ----
     int node = 0, depth = 0;
     const bool forced_on = P.use_forced && P.training && !(P.use_playout_cap && ctl->fast);
-    int* path = B.path ? B.path + (size_t)g * 32 : nullptr;
+    int* path = B.path ? B.path + (size_t)g * TRL_PATH_INTS : nullptr;
+    int parent_s = -1, s_leaf = -1;   // state slots of the last two levels (no reload after the loop)
     while (true) {
-        if (path && lane == 0 && depth <= 30) path[1 + depth] = node;
         const int s = B.slot[nb + node];
+        if (path && lane == 0 && depth <= TRL_PATH_MAX_DEPTH) { path[1 + depth] = node; path[32 + depth] = s; }
+        s_leaf = s;
         if (s < 0) break;
         const int C = B.n_children[sb + s];
         if (C <= 0) break;
@@ -201,21 +205,24 @@ __device__ void select_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
         }
         warp_argmax_last(best, best_i);
         if (best_i < 0) best_i = C - 1;  // every score < -1 (tanh only): the reference would raise
+        parent_s = s;
         node = base + best_i;
         ++depth;
     }
 
-    if (path && lane == 0) path[0] = depth <= 30 ? depth : -1;
+    if (path && lane == 0) path[0] = depth <= TRL_PATH_MAX_DEPTH ? depth : -1;
 
     // ---- materialise the leaf (ai.py:398-403) ----
-    int s = B.slot[nb + node];
+    int s = s_leaf;
     int parent_state = -1;
     int parent_cached = -1;   // number of legal moves already listed under the parent (loaded early: used after the env step)
     if (node != 0) {
-        const int ps = B.slot[nb + B.parent[nb + node]];
+        const int ps = parent_s;
         parent_state = (int)(sb + ps);
         if (B.legal_cache_n) parent_cached = B.legal_cache_n[parent_state];
+        if (row_of) *parent_rows = *reinterpret_cast<const int2*>(row_of + 2 * (size_t)parent_state);   // for the encoder, in flight under the env step
         if (s < 0) s = ctl->n_states;  // first visit: new state slot (uniform across lanes)
+        if (path && lane == 0 && depth <= TRL_PATH_MAX_DEPTH) path[32 + depth] = s;
         copy_game(sg, reinterpret_cast<const uint32_t*>(&B.states[sb + ps]), lane);
         __syncwarp();
         if (lane == 0) {
@@ -451,7 +458,11 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
     const double vmin = tanh_mode ? -1.0 : 0.0;
     const int leaf = ctl->leaf;
     const int kind = ctl->leaf_kind;
-    const int ls = B.slot[nb + leaf];
+    // the selection recorded nodes and state slots along the path: no pointer chasing below when it is valid
+    const int* path = B.path ? B.path + (size_t)g * TRL_PATH_INTS : nullptr;
+    int pdepth = path ? path[0] : -1;
+    if (pdepth >= 0 && path[1 + pdepth] != leaf) pdepth = -1;
+    const int ls = pdepth >= 0 ? path[32 + pdepth] : B.slot[nb + leaf];
 
     double value;
     if (kind == 2) {
@@ -536,9 +547,7 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
     __syncwarp();
 
     // ---- backup (ai.py:511-533) ----
-    const int* path = B.path ? B.path + (size_t)g * 32 : nullptr;
-    const int pdepth = path ? path[0] : -1;
-    if (pdepth >= 0 && path[1 + pdepth] == leaf) {
+    if (pdepth >= 0) {
         // the selection recorded the path: lane i updates the ancestor at depth i (every node gets exactly one
         // addition, as in the serial walk below)
         const double pos = negate_value(value, tanh_mode);
@@ -546,7 +555,7 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
         const int leaf_turn = B.states[sb + ls].turn;
         if (lane <= pdepth) {
             const int n = path[1 + lane];
-            const int ns = B.slot[nb + n];
+            const int ns = path[32 + lane];
             B.visits[nb + n] += 1;
             B.value_sum[nb + n] += (B.states[sb + ns].turn == leaf_turn) ? pos : neg;
         }
@@ -570,9 +579,9 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
 
     // ---- FPU refresh of the played-out node's unvisited siblings (ai.py:542-565) ----
     if (leaf != 0 && P.fpu_reduction) {
-        const int par = B.parent[nb + leaf];
+        const int par = pdepth >= 1 ? path[pdepth] : B.parent[nb + leaf];
         if (par != 0) {
-            const int ps = B.slot[nb + par];
+            const int ps = pdepth >= 1 ? path[32 + pdepth - 1] : B.slot[nb + par];
             const int C = B.n_children[sb + ps], base = B.first_child[sb + ps];
             double explored = 0.0;
             for (int c = lane; c < C; c += 32)
@@ -630,7 +639,8 @@ search_expand_select_encode_kernel(TrlSearchBuffers B, TrlSearchParams P, const 
     expand_body(B, P, g, lane, &s_game[wib], values, logits, logits_stride, dtype);
     __syncwarp();
     int si, pi;
-    select_body(B, P, g, lane, &s_game[wib], si, pi);
+    int2 prow = make_int2(-1, -1);
+    select_body(B, P, g, lane, &s_game[wib], si, pi, E.row_of, &prow);
     __syncwarp();
     if (si < 0) {
         if (lane == 0) { E.own_row[g] = -1; E.opp_row[g] = -1; }
@@ -639,7 +649,8 @@ search_expand_select_encode_kernel(TrlSearchBuffers B, TrlSearchParams P, const 
     int pos = 0;
     if (lane == 0) pos = atomicAdd(E.n_images, (pi < 0) ? 2 : 1);
     pos = __shfl_sync(kFull, pos, 0);
-    trl_encode_cached_leaf(s_game[wib], g, si, pi, pos, lane, E);
+    const int inherit = (pi >= 0) ? ((s_game[wib].turn & 1) ? prow.y : prow.x) : -1;   // parent's cache row of the side to move
+    trl_encode_cached_leaf(s_game[wib], g, si, pi, pos, lane, E, inherit);
 }
 
 }  // namespace

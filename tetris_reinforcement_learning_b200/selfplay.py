@@ -132,7 +132,7 @@ class SelfPlayEngine:
             "leaf_state": z(G, torch.int32), "legal": z(G * self.moves_cap, torch.int16), "n_legal": z(G, torch.int16),
             "samples": z(self.sample_cap * SAMPLE_DTYPE.itemsize, torch.uint8), "sample_count": z(1, torch.int32),
             "ends": z(self.end_cap * GAME_END_DTYPE.itemsize, torch.uint8), "end_count": z(1, torch.int32),
-            "next_game_id": z(1, torch.int32), "leaf_parent": z(G, torch.int32), "path": z(G * 32, torch.int32),
+            "next_game_id": z(1, torch.int32), "leaf_parent": z(G, torch.int32), "path": z(G * 64, torch.int32),
         }
         # exact reuse of legal-placement lists between siblings (include/trl.h, TrlSearchBuffers.legal_cache)
         self.reuse_sibling_placements = bool(reuse_sibling_placements)
