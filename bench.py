@@ -172,24 +172,40 @@ def run_selfplay(args, rank, world, local_rank):
     # games restart in place); after one mean game length of warm-up, count the games that END inside a timed
     # window of about two mean game lengths.  (The mean game length itself comes from the ends seen.)
     games_done, game_ms, mean_plies, plies = 0, 0.0, float("nan"), []
+    n_samples_drained, d2h_bytes, game_status_nonzero, game_status_or = 0, 0, 0, 0
     if not args.no_game_length:
+        # End to end: the sample and game-end records are drained to the host every `chunk` steps INSIDE the timed
+        # window (device sync + D2H of the ring buffers, as make_training_set does), so no record is dropped.
         eng = engine(160)
+        chunk = 448                       # at most 3 searches per game in 448 steps: 12 288 records < the 16 384-record ring
         warm_steps = int(args.game_warm_steps)
-        eng.step(warm_steps)
-        _, ends0 = eng.drain()
+        for _ in range(max(1, warm_steps // chunk)):
+            eng.step(chunk)
+            eng.drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        eng.step(int(args.game_steps))
+        ends_all, n_samples_drained, d2h_bytes = [], 0, 0
+        n_chunks = max(1, int(args.game_steps) // chunk)
+        for _ in range(n_chunks):
+            eng.step(chunk)
+            smp, ends = eng.drain(copy=False)     # views into pinned staging; a consumer would serialise them here
+            ends_all.append(ends.copy())
+            n_samples_drained += len(smp)
+            d2h_bytes += smp.nbytes + ends.nbytes
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         game_ms = e0.elapsed_time(e1)
-        _, ends = eng.drain()
+        args.game_steps = n_chunks * chunk
+        ends = np.concatenate(ends_all) if ends_all else np.zeros(0)
         games_done = len(ends)
+        st_all = eng.get_ctl()["status"]
+        game_status_nonzero = int((st_all != 0).sum())
+        game_status_or = int(np.bitwise_or.reduce(st_all)) if len(st_all) else 0
         plies = [int(e["plies"]) for e in ends]
         mean_plies = float(np.mean(plies)) if plies else float("nan")
         del eng
@@ -236,7 +252,10 @@ def run_selfplay(args, rank, world, local_rank):
             "window_ms": game_ms, "window_steps": int(args.game_steps), "warmup_steps": int(args.game_warm_steps),
             "mean_plies_per_game": mean_plies,
             "how": "complete self-play games (MAX_ITER=160 simulations per move, Gamma root noise, temperature move choice, "
-                   "finished games restart in place) that ended inside the timed window, all GPUs",
+                   "finished games restart in place) that ended inside the timed window, all GPUs; the sample and game-end "
+                   "records are drained to the host every 448 steps inside the window (rank 0's counts below)",
+            "samples_drained_rank0": n_samples_drained, "d2h_bytes_rank0": d2h_bytes, "status_nonzero_rank0": game_status_nonzero,
+            "status_bits_rank0": game_status_or,   # TRL_ST_* (include/trl.h) OR-ed over the games
         },
     }
 
