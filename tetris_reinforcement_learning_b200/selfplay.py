@@ -4,17 +4,19 @@ Replaces the body of make_training_set / _make_training_set_async / aplay_game /
 BatchedEvaluator (reference ai.py:670-996, 1702-1869): G games per GPU advance in lock-step,
 one MCTS simulation per game per step:
 
-    select+materialise (mcts.cu) -> legal placements of the leaves (movegen.cu)
-    -> feature encode (features.cu) -> policy/value net on the G-leaf batch (PyTorch)
+    select+materialise (mcts.cu) -> legal placements of the leaves (movegen_warp.cu)
+    -> feature encode (features.cu) -> policy/value net on the G-leaf batch
     -> expand+backup(+finish search, play the move, restart finished games) (mcts.cu)
 
-The whole step is stream-ordered on one CUDA stream and captured into one CUDA graph; there are
-no host round-trips inside a step.  Finished searches leave `TrlSample` records (position,
-root children, post-prune visit counts) and finished games `TrlGameEnd` records in HBM ring
-buffers that the host drains between graph replays.
+With the fused AlphaSame evaluator (trunk.CachedTrunkEvaluator) a step is launched as
+    forked stream:  gate -> enumeration of the leaves without a cached sibling list (compacted work list)
+    main stream  :  trunk -> heads -> policy GEMM -> [expand(t) + select(t+1) + encode(t+1)] (one kernel)
+(DESIGN.md section 3.4).  Steps are captured into CUDA graphs (steps_per_graph per launch); there are no
+host round-trips inside a step.  Finished searches leave `TrlSample` records (position, root children,
+post-prune visit counts) and finished games `TrlGameEnd` records in HBM ring buffers that the host
+drains between graph replays (drain(): pinned, double-buffered).
 """
 import ctypes
-import os
 
 import numpy as np
 import torch
@@ -269,15 +271,9 @@ class SelfPlayEngine:
             if self._side is None:
                 self._side = torch.cuda.Stream(self.device)
             self._side.wait_event(enc_done)
-            probe = os.environ.get("TRL_PROBE_TAIL", "")   # timing probes only (tools/step_timeline.py)
-            if "nogate" not in probe:
-                _native.check(lib.trl_alphasame_trunk_rows_gate(self._side.cuda_stream), "trl_alphasame_trunk_rows_gate")
+            _native.check(lib.trl_alphasame_trunk_rows_gate(self._side.cuda_stream), "trl_alphasame_trunk_rows_gate")
             stamp(8, self._side.cuda_stream)
-            if "nomovegen" in probe:   # INVALID searches (stale move lists): only to time the rest of the step
-                with torch.cuda.stream(self._side):
-                    self.t["movegen_count"].zero_()
-            else:
-                _native.check(lib.trl_search_movegen(bp, self._side.cuda_stream), "trl_search_movegen")
+            _native.check(lib.trl_search_movegen(bp, self._side.cuda_stream), "trl_search_movegen")
             stamp(9, self._side.cuda_stream)
         if not mode:
             stamp(8, st)
