@@ -37,7 +37,8 @@ namespace {
 
 constexpr int kFifoCap = 768;             // live entries; adversarial cave boards peak < 500.
                                           // 768 keeps a block at 30 KB of shared memory: 7 blocks = 56 warps per SM
-constexpr int kCallsPerBlock = 8;   // 16 warps, 60 KB of shared memory, 3 blocks per SM (measured best of 1/2/4/8)
+constexpr int kCallsPerBlock = 8;   // 16 warps, 60 KB of shared memory, 62 registers: 2 blocks per SM (measured best of 1/2/4/8;
+                                    // __launch_bounds__(512, 3) = 40 registers with spills: 125 ms vs 119 ms on the sweep)
 constexpr int kWarps = 2 * kCallsPerBlock;
 constexpr int kVRows = TRL_MAP_H + 2;     // rows 44, 45 stay 0: "below the map" is never valid
 
