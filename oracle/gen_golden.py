@@ -134,13 +134,14 @@ def gen_env(n_games=260, plies=40, ruleset="s2"):
     print(name, len(moves), "transitions", stats)
 
 
-def gen_mcts(n_searches=24, iters=48):
-    """mcts_golden.npz: reference ai.MCTS outputs under the fake evaluator and the Philox tape."""
+def gen_mcts(n_searches=24, iters=48, out_name="mcts_golden.npz"):
+    """mcts_golden.npz: reference ai.MCTS outputs under the fake evaluator and the Philox tape.
+    mcts_golden_160.npz: the same at BASELINE's MAX_ITER=160 (playout-cap searches run 400 / 80 iterations)."""
     from oracle import features_oracle, mcts_oracle
     from oracle.pin_mcts_against_reference import config_families, positions, tanh_wrap
     m = rh.full_modules()
     fams = config_families(m.ai, iters)
-    pos = positions(40, SEED)
+    pos = positions(max(40, n_searches), SEED)   # one position (game id) per search
     recs, fam_idx, moves, saves, n_nodes, root_q = [], [], [], [], [], []
     child_moves = np.full((n_searches, 512), 0xFFFF, np.uint16)
     child_visits = np.zeros((n_searches, 512), np.int32)
@@ -156,14 +157,14 @@ def gen_mcts(n_searches=24, iters=48):
         n_nodes.append(r["n_nodes"]); root_q.append(r["root_value_avg"]); n_children[k] = c
         child_moves[k, :c] = r["moves"]; child_visits[k, :c] = r["visits_post"]; child_priors[k, :c] = r["priors"]
     recs = np.concatenate(recs)
-    np.savez_compressed(os.path.join(OUT, "mcts_golden.npz"),
+    np.savez_compressed(os.path.join(OUT, out_name),
                         games=recs.view(np.uint8).reshape(len(recs), -1), family=np.array(fam_idx, np.int32),
                         family_names=np.array([f[0] for f in fams]), iters=iters, seed=SEED,
                         move=np.array(moves, np.int32), save=np.array(saves, np.uint8),
                         n_nodes=np.array(n_nodes, np.int32), root_value_avg=np.array(root_q, np.float64),
                         n_children=n_children, child_moves=child_moves, child_visits=child_visits,
                         child_priors=child_priors)
-    print("mcts_golden:", n_searches, "searches x", iters, "iterations")
+    print(out_name, n_searches, "searches x", iters, "iterations")
 
 
 if __name__ == "__main__":
@@ -179,6 +180,8 @@ if __name__ == "__main__":
         gen_env()
     if "mcts" in which:
         gen_mcts()
+    if "mcts160" in which:
+        gen_mcts(n_searches=64, iters=160, out_name="mcts_golden_160.npz")
     if "s1" in which:   # ruleset s1: attack table (stats.py:49-86) and env transitions without the all-spin rule
         gen_attack("s1")
         gen_env(n_games=140, plies=40, ruleset="s1")

@@ -96,23 +96,27 @@ def _run_family(golden, fam, cfg, sel, use_graph):
     budget = long_iters if (cfg.training and cfg.use_playout_cap_randomization) else cfg.MAX_ITER
     eng.step(budget)
     samples, _ = eng.drain()
+    # the first search of slot i is the record with (game id, search number) = (games[i].game_id, sel[i])
+    want = {(int(games[i]["game_id"]), int(sel[i])) for i in range(G)}
     first = {}
     for s in samples:
-        key = int(s["game_id"])
-        if key not in first or int(s["search_no"]) < int(first[key]["search_no"]):
+        key = (int(s["game_id"]), int(s["search_no"]))
+        if key in want:
             first[key] = s
     return games, first, eng
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_search_vs_reference_vectors(golden_dir, use_graph):
-    """Device search vs the reference's ai.MCTS (24 searches, 4 config families, 48 iterations,
-    playout-cap / Gamma noise / temperature / forced playouts + pruning / tanh + absolute FPU).
+@pytest.mark.parametrize("use_graph,vectors", [(False, "mcts_golden.npz"), (True, "mcts_golden.npz"), (True, "mcts_golden_160.npz")])
+def test_search_vs_reference_vectors(golden_dir, use_graph, vectors):
+    """Device search vs the reference's ai.MCTS: 24 searches x 48 iterations and 64 searches at BASELINE's
+    MAX_ITER = 160 (400 / 80 with the playout cap), 4 config families (playout-cap / Gamma noise /
+    temperature / forced playouts + pruning / tanh + absolute FPU).
 
     Tolerance: root children and their order are bit-exact (integer work); per search the
-    total-variation distance between device and reference visit distributions must be <= 0.05
-    and at least 80 % of the searches must match the reference's visit counts exactly."""
-    golden = np.load(os.path.join(golden_dir, "mcts_golden.npz"))
+    total-variation distance between device and reference visit distributions must be <= 0.02
+    and at most one search in twenty may differ from the reference's visit counts at all (device sums
+    with warp reductions and uses CUDA libm; measured on B200: every search identical, distance 0)."""
+    golden = np.load(os.path.join(golden_dir, vectors))
     fams = config_families(int(golden["iters"]))
     exact = total = 0
     worst_tv = 0.0
@@ -121,8 +125,7 @@ def test_search_vs_reference_vectors(golden_dir, use_graph):
         games, first, eng = _run_family(golden, fam, cfg, sel, use_graph)
         assert len(first) == len(sel)
         for k, gi in zip(sel, range(len(sel))):
-            s = first[int(games[gi]["game_id"])]
-            assert int(s["search_no"]) == k
+            s = first[(int(games[gi]["game_id"]), int(k))]
             C = int(golden["n_children"][k])
             assert int(s["n_children"]) == C
             assert np.array_equal(s["moves"][:C], golden["child_moves"][k][:C])      # argwhere order, bit-exact
@@ -138,8 +141,9 @@ def test_search_vs_reference_vectors(golden_dir, use_graph):
                 assert int(s["chosen_move"]) == int(golden["move"][k])
         ctl = eng.get_ctl()
         assert (ctl["status"] == 0).all()
-    assert worst_tv <= 0.05, f"worst total-variation distance {worst_tv}"
-    assert exact >= 0.8 * total, f"only {exact}/{total} searches match the reference's visit counts exactly"
+    print(f"search parity vs the reference: {exact}/{total} searches with identical visit counts, worst total-variation distance {worst_tv:.4f}")
+    assert worst_tv <= 0.02, f"worst total-variation distance {worst_tv}"
+    assert exact >= 0.95 * total, f"only {exact}/{total} searches match the reference's visit counts exactly"
 
 
 def test_search_tree_invariants_and_selfplay_with_network():
