@@ -312,3 +312,41 @@ def test_env_device_api_and_skip(env, oracle):
     exp_out = oracle.env_step(want, mv, False, seed)
     assert games_equal(got, want).all()
     assert np.array_equal(d_out.cpu().numpy().view(STEPOUT_DTYPE).reshape(-1).view(np.uint8), exp_out.view(np.uint8))
+
+
+def test_every_emitted_placement_steps_like_the_oracle(env, oracle):
+    """BASELINE config 2, second half: for EVERY placement the device enumerates on a sample of the sweep
+    workload, the device env step (lock, spin detection, line clears, all-clear, attack, b2b / combo, garbage
+    with a fixed column tape, next piece, top-out) equals the oracle's on the same state, bit for bit."""
+    from tetris_reinforcement_learning_b200 import move_generation as mgen
+    seed = 20261018
+    boards, cur, alt = synth.movegen_workload(1200)            # 8400 calls, all three board families
+    n = boards.shape[0]
+    res = mgen.movegen_host(boards, cur, alt, want_mask=False, want_moves=True, moves_cap=256)
+    counts = res["n_moves"].astype(np.int64)
+    assert (counts <= 256).all() and counts.sum() > 40 * n // 7
+    base = env.game_setup_host(n, 0, seed)
+    base["turn"] = 0
+    p0 = base["players"][:, 0]
+    p0["rows"] = boards
+    p0["piece"] = cur
+    p0["held"] = alt                                            # the sweep's second piece is the hold piece
+    base["players"][:, 0] = p0
+    rep = np.repeat(np.arange(n), counts)
+    games = base[rep].copy()
+    games["game_id"] = np.arange(len(rep), dtype=np.uint32)     # one garbage-column stream per placement
+    shadow = games.copy()
+    moves = np.concatenate([res["moves"][i, :counts[i]] for i in range(n)]).astype(np.uint16)
+    assert len(moves) == len(games) > 300000 // 7
+    out = env.env_step_host(games, moves, True, seed)
+    want = oracle.env_step(shadow, moves, True, seed)
+    assert np.array_equal(out.view(np.uint8), want.view(np.uint8))
+    assert games_equal(games, shadow).all()
+    assert (out["status"] == 0).all()
+    # the sample exercises the rules: clears, spins, all-spin minis, attacks, holds, top-outs
+    print("placements", len(moves), "clears", int((out["rows_cleared"] > 0).sum()), "attacks", int((out["attack"] > 0).sum()),
+          "t-spins", int(((out["flags"] & 1) != 0).sum()), "minis", int(((out["flags"] & 2) != 0).sum()),
+          "all-clears", int(((out["flags"] & 4) != 0).sum()), "holds", int(((out["flags"] & 8) != 0).sum()),
+          "top-outs", int(((out["flags"] & 0x10) != 0).sum()))
+    assert (out["rows_cleared"] > 0).sum() > 100 and (out["attack"] > 0).sum() > 10
+    assert ((out["flags"] & 1) != 0).sum() > 0 and ((out["flags"] & 2) != 0).sum() > 0 and ((out["flags"] & 8) != 0).sum() > 1000
