@@ -19,15 +19,28 @@ ap.add_argument("--steps", type=int, default=320)
 ap.add_argument("--games", type=int, default=4096)
 ap.add_argument("--desync", type=int, default=0, help="warm-up steps before timing (games drift apart after ~10k)")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--net", default="alphasame", choices=["alphasame", "alphasame64", "base", "aux"],
+                help="alphasame = AlphaSame(10,16) (fused trunk); alphasame64 = AlphaSame(20,64), base / aux = BaseResNet / "
+                     "AuxBaseResNet(8,32) (the Config default) through the PyTorch evaluator")
+ap.add_argument("--forced", action="store_true", help="forced playouts + policy-target pruning (BASELINE config 4)")
 ap.add_argument("variants", nargs="*", default=["", "compact_movegen=0", "fuse_expand_select=0", "compact_movegen=0,fuse_expand_select=0"])
 args = ap.parse_args()
 
 torch.manual_seed(0)
-mc = arch.AlphaSameConfig(blocks=10, filters=16)
-net = arch.AlphaSame(mc).to("cuda:0")
+if args.net == "alphasame":
+    mc = arch.AlphaSameConfig(blocks=10, filters=16); net = arch.AlphaSame(mc)
+elif args.net == "alphasame64":
+    mc = arch.AlphaSameConfig(blocks=20, filters=64); net = arch.AlphaSame(mc)
+elif args.net == "base":
+    mc = arch.BaseResNetConfig(); net = arch.BaseResNet(mc)
+else:
+    mc = arch.AuxBaseResNetConfig(); net = arch.AuxBaseResNet(mc)
+net = net.to("cuda:0")
 ev = best_evaluator(net, torch.bfloat16)
 cfg = Config(visual=False, ruleset="s2", model="pytorch", model_config=mc, MAX_ITER=160, CPUCT=0.75, training=True,
-             use_playout_cap_randomization=False, use_dirichlet_noise=True, FpuStrategy="reduction")
+             use_playout_cap_randomization=False, use_dirichlet_noise=True, FpuStrategy="reduction",
+             use_forced_playouts_and_policy_target_pruning=args.forced)
+print("net", args.net, "forced", args.forced, flush=True)
 for v in args.variants:
     kw = {}
     for item in filter(None, v.split(",")):
