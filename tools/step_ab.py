@@ -23,6 +23,8 @@ ap.add_argument("--net", default="alphasame", choices=["alphasame", "alphasame64
                 help="alphasame = AlphaSame(10,16) (fused trunk); alphasame64 = AlphaSame(20,64), base / aux = BaseResNet / "
                      "AuxBaseResNet(8,32) (the Config default) through the PyTorch evaluator")
 ap.add_argument("--forced", action="store_true", help="forced playouts + policy-target pruning (BASELINE config 4)")
+ap.add_argument("--cudnn-benchmark", action="store_true")
+ap.add_argument("--nchw", action="store_true", help="PyTorch evaluator without channels-last")
 ap.add_argument("variants", nargs="*", default=["", "compact_movegen=0", "fuse_expand_select=0", "compact_movegen=0,fuse_expand_select=0"])
 args = ap.parse_args()
 
@@ -36,7 +38,12 @@ elif args.net == "base":
 else:
     mc = arch.AuxBaseResNetConfig(); net = arch.AuxBaseResNet(mc)
 net = net.to("cuda:0")
-ev = best_evaluator(net, torch.bfloat16)
+torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
+if args.nchw:
+    from tetris_reinforcement_learning_b200.selfplay import make_net_evaluator
+    ev = make_net_evaluator(net, torch.bfloat16, channels_last=False)
+else:
+    ev = best_evaluator(net, torch.bfloat16)
 cfg = Config(visual=False, ruleset="s2", model="pytorch", model_config=mc, MAX_ITER=160, CPUCT=0.75, training=True,
              use_playout_cap_randomization=False, use_dirichlet_noise=True, FpuStrategy="reduction",
              use_forced_playouts_and_policy_target_pruning=args.forced)
