@@ -52,6 +52,40 @@ def test_selfplay_train_gate_loop(tmp_path, monkeypatch, family):
     assert wins.sum() == cfg.battle_games and accepted in (True, False)
 
 
+def test_compact_data_format_holds_the_same_samples_and_trains(tmp_path, monkeypatch):
+    """make_training_set(data_format="compact") with the same seed: <n>.npz expands to exactly the tensors of the JSON set
+    <n>.txt (same games, same order), and load_data_and_train_model / the training step consume it on the GPU."""
+    import torch
+    from tetris_reinforcement_learning_b200 import ai, training
+    from tetris_reinforcement_learning_b200 import architectures as arch
+    from tetris_reinforcement_learning_b200.compact import CompactSet
+    monkeypatch.setenv("TRL_STORAGE", str(tmp_path / "Storage"))
+    cfg = ai.Config(visual=False, ruleset="s2", model="pytorch", model_config=arch.AlphaSameConfig(blocks=2, filters=16),
+                    MAX_ITER=6, training_games=8, epochs=1, batch_size=64, use_playout_cap_randomization=False, training=True)
+    torch.manual_seed(0)
+    net = ai.instantiate_network(cfg, show_summary=False, save_network=True)
+    infer = ai.get_interference_network(cfg, net)
+    os.makedirs(cfg.data_dir, exist_ok=True)
+    ai.make_training_set(cfg, infer, num_games=8, save_game=True, save_stats=True, seed=5)
+    ccfg = cfg.copy()
+    ccfg.engine_data_format = "compact"
+    assert ccfg.copy().engine_data_format == "compact"
+    ai.make_training_set(ccfg, infer, num_games=8, save_game=True, save_stats=True, seed=5)
+    assert ai.highest_data_number(cfg) == 1 and os.path.exists(f"{cfg.data_dir}/1.npz")
+    want = training._to_tensors(json.load(open(f"{cfg.data_dir}/0.txt")))
+    cs = CompactSet.load(f"{cfg.data_dir}/1.npz")
+    got = cs.batch_tensors(np.arange(len(cs)), device="cuda:0")
+    assert len(cs) == len(want[0]) > 0 and os.path.getsize(f"{cfg.data_dir}/1.npz") * 50 < os.path.getsize(f"{cfg.data_dir}/0.txt")
+    for col, (w, t) in enumerate(zip(want, got)):
+        if col == 11:          # outcomes: torch.tensor() of the JSON column is int64 when no game was drawn; training casts to float
+            w = w.float()
+        assert w.shape == t.shape and w.dtype == t.dtype and torch.equal(w, t.cpu())
+    os.remove(f"{cfg.data_dir}/0.txt")                      # train on the compact set alone
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    out = training.load_data_and_train_model(ccfg, net)
+    assert np.isfinite(out["loss"]) and sum(int(not torch.equal(before[k], v)) for k, v in net.state_dict().items()) > 0
+
+
 def test_mcts_dropin_on_a_reference_style_game():
     """ai.MCTS(config, game, net) on a duck-typed Game: returns a legal (plane, col, row) move."""
     import torch

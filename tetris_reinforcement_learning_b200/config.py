@@ -42,6 +42,10 @@ _DEFAULTS = dict(
 
 
 class Config:
+    # B200-only knob (not a constructor argument of the reference): "json" = the reference's <n>.txt list of
+    # 13-element samples, "compact" = <n>.npz CompactSet (compact.py), 270x smaller and expanded on the training device
+    engine_data_format = "json"
+
     def __init__(self, **kwargs):
         unknown = set(kwargs) - set(_DEFAULTS)
         if unknown:
@@ -54,7 +58,11 @@ class Config:
             self.loss_weights = [1, 1]
 
     def copy(self):
-        return Config(**{k: getattr(self, k) for k in _DEFAULTS})
+        c = Config(**{k: getattr(self, k) for k in _DEFAULTS})
+        for k, v in vars(self).items():
+            if k.startswith("engine_"):
+                setattr(c, k, v)
+        return c
 
     @property
     def model_dir(self):

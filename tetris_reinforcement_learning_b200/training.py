@@ -33,8 +33,32 @@ def get_data_filenames(config):
     return names
 
 
+def _load_set(path):
+    """One data set: the reference's JSON sample list (<n>.txt) or a compact.CompactSet (<n>.npz)."""
+    if path.endswith(".npz"):
+        from .compact import CompactSet
+        return CompactSet.load(path)
+    with open(path) as f:
+        return json.load(f)
+
+
 def load_data(config):
-    return [json.load(open(f"{config.data_dir}/{f}")) for f in get_data_filenames(config)]
+    return [_load_set(f"{config.data_dir}/{f}") for f in get_data_filenames(config)]
+
+
+class _CompactSelection:
+    """Samples `index` of a CompactSet, expanded batch by batch on the training device."""
+
+    def __init__(self, cset, index):
+        self.cset, self.index = cset, np.asarray(index, dtype=np.int64)
+
+    def __len__(self):
+        return len(self.index)
+
+    def batches(self, batch_size, shuffle, device):
+        order = np.random.permutation(len(self.index)) if shuffle else np.arange(len(self.index))
+        for lo in range(0, len(order), batch_size):
+            yield self.cset.batch_tensors(self.index[order[lo:lo + batch_size]], device)
 
 
 def _to_tensors(samples):
@@ -68,9 +92,18 @@ def train_network_pytorch(config, model, samples, data_number=None, log=True):
     """AdamW on MSE(value) + CE(policy) (+ aux_weight * MSE(aux)); returns the mean losses."""
     from .ai import highest_data_number, logs_dir
     device = next(model.parameters()).device
-    feats = _to_tensors(samples)
-    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(*feats), batch_size=config.batch_size,
-                                         shuffle=config.shuffle)
+    from .compact import CompactSet
+    if isinstance(samples, CompactSet):
+        samples = _CompactSelection(samples, np.arange(len(samples)))
+    if isinstance(samples, _CompactSelection):
+        class _Loader:   # same batches as the TensorDataset path, built on `device` from the packed records
+            def __iter__(self_inner):
+                return samples.batches(config.batch_size, config.shuffle, device)
+        loader = _Loader()
+    else:
+        feats = _to_tensors(samples)
+        loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(*feats), batch_size=config.batch_size,
+                                             shuffle=config.shuffle)
     mse, ce = nn.MSELoss(), nn.CrossEntropyLoss()
     opt = torch.optim.AdamW(model.parameters(), lr=config.learning_rate, weight_decay=config.weight_decay)
     has_aux = isinstance(config.model_config, AuxBaseResNetConfig)
@@ -123,19 +156,34 @@ def load_data_and_train_model(config, model, data=None):
     fraction of its samples (ai.py:1871-1901)."""
     if config.data_loading_style != "merge":
         raise NotImplementedError(f"data_loading_style={config.data_loading_style!r}")
+    from .compact import CompactSet
     n_sets = 0
     if data is None:
-        data = []
+        sets, fractions = [], []
         names = sorted(get_data_filenames(config), key=lambda x: int(x.split(".")[0]), reverse=True)
         for age, name in enumerate(names):
-            one = json.load(open(f"{config.data_dir}/{name}"))
-            data.extend(random.sample(one, int(len(one) * config.decay_factor ** age)))
+            sets.append(_load_set(f"{config.data_dir}/{name}"))
+            fractions.append(config.decay_factor ** age)
         n_sets = len(names)
     else:
         n_sets = len(data)
-        data = [x for one in data for x in one]
-    if config.shuffle:
-        random.shuffle(data)
+        sets, fractions = list(data), [None] * len(data)      # None: every sample, in order (ai.py:1895)
+    if sets and all(isinstance(one, CompactSet) for one in sets):
+        # compact sets: the same recency-weighted sample of every set, as indices into the concatenation
+        index, base = [], 0
+        for one, frac in zip(sets, fractions):
+            sel = range(len(one)) if frac is None else random.sample(range(len(one)), int(len(one) * frac))
+            index.append(base + np.asarray(sel, dtype=np.int64))
+            base += len(one)
+        data = _CompactSelection(CompactSet.concatenate(sets), np.concatenate(index) if index else np.zeros(0, np.int64))
+    elif any(isinstance(one, CompactSet) for one in sets):
+        raise NotImplementedError("mixing JSON and compact data sets in one training run")
+    else:
+        data = []
+        for one, frac in zip(sets, fractions):
+            data.extend(one if frac is None else random.sample(one, int(len(one) * frac)))
+        if config.shuffle:
+            random.shuffle(data)
     print(f"Training with {len(data)} samples over {n_sets} sets with decay factor {config.decay_factor}")
     out = train_network(config, model, data)
     gc.collect()
