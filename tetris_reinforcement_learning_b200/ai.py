@@ -281,13 +281,18 @@ def generate_games(config, net, num_games, seed=None, concurrent=None, augment=N
                       game_id_stride=game_id_stride, restart_finished=(G < num_games))
     chunk = max(8, config.MAX_ITER // 2)
     per_game, finished = {}, {}
+    all_samples, all_ends = [], []
     steps = 0
     while len(finished) < num_games:
         eng.step(chunk)
         steps += chunk
         samples, ends = eng.drain()
-        for s in samples:
-            per_game.setdefault(int(s["game_id"]), []).append(s)
+        if compact:       # no per-record Python: the set is assembled from the arrays at the end
+            all_samples.append(samples)
+            all_ends.append(ends)
+        else:
+            for s in samples:
+                per_game.setdefault(int(s["game_id"]), []).append(s)
         for e in ends:
             finished[int(e["game_id"])] = e
         if max_steps is not None and steps >= max_steps:
@@ -295,7 +300,7 @@ def generate_games(config, net, num_games, seed=None, concurrent=None, augment=N
         if not eng.get_ctl()["active"].any():
             break
     data_number, model_number = highest_data_number(config) + 1, highest_model_number(config)
-    series_data, series_stats, searches = [], [], []
+    series_data, series_stats = [], []
     for gid in sorted(finished)[:num_games]:
         e = finished[gid]
         winner = int(e["winner"])
@@ -304,26 +309,24 @@ def generate_games(config, net, num_games, seed=None, concurrent=None, augment=N
             if not (s["saved"] or config.save_all):
                 continue
             C = int(s["n_children"])
-            if compact:
-                by_player[int(s["turn"])].append((s["state"], s["moves"][:C], s["visits"][:C]))
-            else:
-                by_player[int(s["turn"])].extend(samples_from_search(s["state"], s["moves"][:C], s["visits"][:C], augment))
+            by_player[int(s["turn"])].extend(samples_from_search(s["state"], s["moves"][:C], s["visits"][:C], augment))
         for pl in range(2):
             value = config.value_mid if winner == -1 else (config.value_max if winner == pl else config.value_min)
-            if compact:
-                searches.extend((st, mv, vis, value) for st, mv, vis in by_player[pl])
-                continue
             for sample in by_player[pl]:
                 sample.insert(-1, value)
-        if not compact:
-            series_data.extend(by_player[0] + by_player[1])
+        series_data.extend(by_player[0] + by_player[1])
         pieces = max(int(e["pieces0"]), 1)
         series_stats.append({"model_number": model_number, "model_version": config.model_version,
                              "data_number": data_number, "data_version": config.data_version,
                              "app": int(e["lines_sent0"]) / pieces, "dspp": int(e["lines_cleared0"]) / pieces})
     if compact:
         from .compact import CompactSet
-        series_data = CompactSet.from_searches(searches, augment)
+        from .selfplay import GAME_END_DTYPE, SAMPLE_DTYPE
+        series_data = CompactSet.from_records(
+            np.concatenate(all_samples) if all_samples else np.zeros(0, SAMPLE_DTYPE),
+            np.concatenate(all_ends) if all_ends else np.zeros(0, GAME_END_DTYPE),
+            (config.value_min, config.value_mid, config.value_max), num_games=num_games, save_all=config.save_all,
+            augment=augment)
     return series_data, series_stats
 
 

@@ -46,6 +46,20 @@ def _policy_mirror_index():
 POLICY_MIRROR = _policy_mirror_index()
 
 
+def round4(x):
+    """Vectorised Python round(x, 4) on float64 (the rounding of search_statistics, ai.py:1353): nearest multiple of
+    1e-4 to the EXACT value of the double, ties to even.  np.rint(x * 1e4) agrees except where the product lands on a
+    half although x itself is not one (3/160 = 0.01875 is stored slightly below the tie: Python gives 0.0187); those few
+    elements go through Python's round."""
+    x = np.asarray(x, dtype=np.float64)
+    y = x * 1e4
+    out = np.rint(y) / 1e4
+    sus = np.flatnonzero(np.abs(y - np.floor(y) - 0.5) < 1e-6)
+    if sus.size:
+        out[sus] = [round(float(v), 4) for v in x[sus]]
+    return out
+
+
 class CompactSet:
     """state GAME_DTYPE[S], value f32[S], offsets i64[S+1], moves u16[T], frac f64[T] (visit fraction of a
     visited root child, rounded to 4 decimals exactly like search_statistics), augment bool."""
@@ -88,6 +102,37 @@ class CompactSet:
         if not states:
             return cls.empty(augment)
         return cls(np.concatenate(states), values, offs, np.concatenate(moves), np.concatenate(frac), augment)
+
+    @classmethod
+    def from_records(cls, samples, ends, value_of, num_games=None, save_all=False, augment=True):
+        """Vectorised form of generate_games' bookkeeping: `samples` (selfplay.SAMPLE_DTYPE) and `ends`
+        (GAME_END_DTYPE) drained from the engine -> the saved searches of the first `num_games` finished games
+        (by game id), per game player 0's searches in order then player 1's, with the outcome from the mover's
+        point of view: value_of = (value_min, value_mid, value_max).  Same set, same order as from_searches
+        over the reference-style loop."""
+        if len(ends) == 0 or len(samples) == 0:
+            return cls.empty(augment)
+        ids, first = np.unique(ends["game_id"], return_index=True)
+        if num_games is not None:
+            ids, first = ids[:num_games], first[:num_games]
+        winners = ends["winner"][first].astype(np.int64)
+        keep = np.isin(samples["game_id"], ids) & ((samples["saved"] != 0) | bool(save_all))
+        smp = samples[keep]
+        smp = smp[np.lexsort((smp["search_no"], smp["turn"], smp["game_id"]))]
+        w = winners[np.searchsorted(ids, smp["game_id"])]
+        vmin, vmid, vmax = value_of
+        value = np.where(w == -1, vmid, np.where(w == smp["turn"].astype(np.int64), vmax, vmin)).astype(np.float32)
+        C = smp["n_children"].astype(np.int64)
+        vis = smp["visits"].astype(np.int64)
+        live = np.arange(vis.shape[1])[None, :] < C[:, None]
+        vis = np.where(live, vis, 0)
+        total = vis.sum(axis=1)
+        assert (total > 0).all()
+        nz = vis > 0
+        cnt = nz.sum(axis=1)
+        offsets = np.concatenate([[0], np.cumsum(cnt)])
+        frac = round4(vis[nz] / np.repeat(total, cnt))
+        return cls(smp["state"], value, offsets, smp["moves"][nz], frac, augment)
 
     @classmethod
     def concatenate(cls, sets):
