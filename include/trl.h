@@ -62,6 +62,9 @@ extern "C" {
 #define TRL_ST_NO_PIECE       0x4u   /* cur == none and alt == none (Game.no_move)      */
 #define TRL_ST_RECV_OVERFLOW  0x8u   /* pending-garbage list exceeded TRL_RECV_CAP      */
 #define TRL_ST_BAD_MOVE       0x10u  /* env step: move index out of range / undecodable */
+#define TRL_ST_SAMPLE_OVERFLOW 0x20u /* search: the TrlSample ring was full, a record was dropped */
+#define TRL_ST_ARENA_FULL     0x40u  /* search: node arena full, a leaf stayed childless */
+#define TRL_ST_END_OVERFLOW   0x80u  /* search: the TrlGameEnd ring was full, a record was dropped */
 
 /*
  * One player.  Mirrors the fields Player.copy() carries (player.py:217-233):
@@ -346,6 +349,9 @@ typedef struct TrlSearchBuffers {
     int32_t* movegen_list;                   /* [n_games] game indices, arbitrary order                   */
     uint32_t* movegen_count;                 /* [4] entries in movegen_list; finished blocks; next ticket; pad.
                                                 Zero between steps (the enumeration kernel resets them)    */
+    uint32_t* movegen_status;                /* [n_games] or NULL: TRL_ST_* bits of the uncompacted enumeration
+                                                (movegen_list == NULL); trl_search_expand folds them into
+                                                ctl.status.  The compacted enumeration writes ctl.status itself */
 } TrlSearchBuffers;
 
 int trl_sizeof_search_ctl(void);
@@ -473,6 +479,40 @@ int trl_alphasame_heads_indexed(const void* cache_bf16, const int32_t* own_row, 
 int trl_alphasame_heads(const void* feats_bf16, const void* extras_bf16, int n_leaves, const float* weights,
                         int use_tanh, void* x_out_bf16, void* value_out_bf16, void* stream);
 int trl_alphasame_heads_weight_floats(void);
+
+/* ------------------------------------------------------------------------------------ */
+/* wide fused trunk (csrc/trunk_wide.cu): 32 or 64 filters, both block styles              */
+/* replaces, in eval mode with BatchNorm folded,                                           */
+/*   post_act = 0: AlphaSame.process_grid (architectures.py:120-126; pre-activation blocks */
+/*                 :27-57; 5x5 stem) -> out [rows][400]                                    */
+/*   post_act = 1: BaseResNet._process_grid (architectures.py:231-233; post-activation     */
+/*                 blocks :159-171; 3x3 stem + BN + ReLU) followed by the two 1x1 collapses */
+/*                 (:191-196, :210-214) -> out [rows][5][400]: channels 0-3 = bn scale *    */
+/*                 own_collapse conv (its bias joins the FiLM-add term in the heads, :254), */
+/*                 channel 4 = ReLU(BN(opp_collapse conv)).                                 */
+/* ------------------------------------------------------------------------------------ */
+
+/*
+ * grids     [n_images][400] bf16 0/1 board cells
+ * n_images_dev / out_row: optional device-side image count (<= n_images, reset to 0 when consumed) and the
+ *           output row of image k (both or neither), as trl_alphasame_trunk_rows_indexed
+ * w_packed  [2*n_blocks][3 dy][F/8][3F/8][8][8] bf16: per layer and vertical tap the 3F x F matrix
+ *           B[(j, oc), ic] = w[oc][ic][dy][2 - j] in K-major UMMA core-matrix order
+ * consts    [(2*n_blocks + 1)][3][F] f32 device: per stage (stem, then every conv) bias added to the
+ *           accumulator, and for pre-activation second convs the next BatchNorm's scale and bias; then the
+ *           head: W[n_out][F], scale[n_out], bias[n_out] (n_out = 1 or 5)
+ * stem_lut  [taps][2^taps][F] f32 device: partial sums of one stem kernel row per input bit pattern
+ * scratch   device, >= trl_trunk_wide_scratch_bytes(filters) bytes, ZERO-initialised once by the caller and
+ *           then owned by launches of this operator on one stream at a time (activations stream through it)
+ * status    [8] int32 device, zero-initialised: status[0] != 0 after a launch means a pipeline wait timed
+ *           out (the kernel bounds every wait instead of hanging) and the outputs are invalid
+ * pdl       launch as a programmatic dependent of the previous kernel in `stream`
+ */
+int trl_trunk_wide(const void* grids_bf16, int n_images, int32_t* n_images_dev, const int32_t* out_row,
+                   int filters, int n_blocks, int post_act, int stem_taps, const void* w_packed,
+                   const float* consts, const float* stem_lut, void* out_bf16, void* scratch,
+                   long long scratch_bytes, int32_t* status, int pdl, void* stream);
+long long trl_trunk_wide_scratch_bytes(int filters);
 
 #ifdef __cplusplus
 }

@@ -230,9 +230,9 @@ def test_engine_ruleset_s1_runs_and_survives_restarts():
 
 
 def test_random_starting_moves(oracle):
-    """use_random_starting_moves (ai.py:1588-1608): every game opens with ceil(Exp(0.04 * DIRICHLET_S)) plies that
-    are one-iteration searches sampled from the raw policy and are not saved; the count per game follows the
-    Philox draw (purpose 6) exactly."""
+    """use_random_starting_moves (ai.py:1588-1608): play_game opens every game with ceil(Exp(0.04 * DIRICHLET_S))
+    plies that are one-iteration searches sampled from the raw policy; the reference never stores a sample for
+    them, so they leave no record even with save_all; the count per game follows the Philox draw (purpose 6)."""
     import math
     import torch
     from tetris_reinforcement_learning_b200.selfplay import SelfPlayEngine
@@ -240,7 +240,7 @@ def test_random_starting_moves(oracle):
     cfg = Config(visual=False, ruleset="s2", model="pytorch", MAX_ITER=6, training=True, use_random_starting_moves=True,
                  use_playout_cap_randomization=False)
     eng = SelfPlayEngine(cfg, fake_evaluator_torch(torch.device("cuda:0")), G, seed=seed, save_all=True,
-                         restart_finished=False, max_rounds=4, use_cuda_graph=False, sample_cap=65536)
+                         restart_finished=False, max_rounds=4, use_cuda_graph=False, sample_cap=65536, random_openings=True)
     eng.step(120)
     samples, _ = eng.drain()
     assert (eng.get_ctl()["status"] == 0).all()
@@ -249,16 +249,31 @@ def test_random_starting_moves(oracle):
         by_game.setdefault(int(s["game_id"]), []).append(s)
     ks = []
     for gid in range(G):
-        recs = sorted(by_game[gid], key=lambda r: int(r["search_no"]))
+        recs = sorted(by_game.get(gid, []), key=lambda r: int(r["search_no"]))
         u = oracle.uniform(seed, gid, 0, 6, 0)
         k = int(math.ceil(-1.0 * math.log(1.0 - u)))          # scale = 0.04 * DIRICHLET_S = 1.0
         ks.append(k)
+        if recs:
+            assert int(recs[0]["search_no"]) == k, (gid, int(recs[0]["search_no"]), k)   # the first stored search follows the opening
         for r in recs:
-            opening = int(r["search_no"]) < k
-            assert int(r["iterations"]) == (1 if opening else cfg.MAX_ITER), (gid, int(r["search_no"]), k)
-            assert int(r["saved"]) == (0 if opening else 1)
+            assert int(r["search_no"]) >= k
+            assert int(r["iterations"]) == cfg.MAX_ITER and int(r["saved"]) == 1
             C = int(r["n_children"])
             assert int(r["chosen_move"]) in set(int(m) for m in r["moves"][:C])
-            if opening:
-                assert int(r["visits_pre"][:C].sum()) == 0        # the root was expanded, nothing else
+            assert int(r["visits"][:C].sum()) > 0             # a stored search always has visits (ai.py:1347)
     assert 1.3 < np.mean(ks) < 1.9 and min(ks) >= 1               # E[ceil(Exp(1))] = 1 / (1 - 1/e) = 1.58
+
+
+def test_random_openings_only_in_self_play():
+    """MCTS() and battle_networks never draw random opening plies (ai.py:1588-1608 is play_game only): an engine
+    built without random_openings runs full searches from the first ply even if the Config flag is set."""
+    import torch
+    from tetris_reinforcement_learning_b200.selfplay import SelfPlayEngine
+    cfg = Config(visual=False, ruleset="s2", model="pytorch", MAX_ITER=6, training=True, use_random_starting_moves=True,
+                 use_playout_cap_randomization=False)
+    eng = SelfPlayEngine(cfg, fake_evaluator_torch(torch.device("cuda:0")), 64, seed=5, save_all=True,
+                         restart_finished=False, max_rounds=2, use_cuda_graph=False)
+    eng.step(6)
+    samples, _ = eng.drain()
+    assert len(samples) == 64 and (samples["search_no"] == 0).all() and (samples["iterations"] == 6).all()
+    assert (eng.get_ctl()["random_left"] == 0).all()

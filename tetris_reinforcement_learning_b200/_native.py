@@ -11,7 +11,7 @@ from .state import GAME_DTYPE, PLAYER_DTYPE
 _SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtrl_b200.so")
 _lib = None
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 c_void_p, c_int, c_u64, c_u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32
 
@@ -52,6 +52,9 @@ SIGNATURES = {
     "trl_alphasame_trunk_rows_indexed": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "trl_alphasame_trunk_rows_gate": (c_int, [c_void_p]),
     "trl_alphasame_heads_indexed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "trl_trunk_wide_scratch_bytes": (ctypes.c_longlong, [c_int]),
+    "trl_trunk_wide": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_int, c_void_p]),
     "trl_encode_features": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
 }
 
@@ -114,4 +117,4 @@ class SearchBuffers(ctypes.Structure):
                                                "samples", "sample_count", "ends", "end_count",
                                                "next_game_id", "noise_override", "leaf_parent",
                                                "legal_cache", "legal_cache_n", "movegen_index", "path",
-                                               "movegen_list", "movegen_count")]
+                                               "movegen_list", "movegen_count", "movegen_status")]

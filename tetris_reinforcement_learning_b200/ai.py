@@ -278,8 +278,11 @@ def generate_games(config, net, num_games, seed=None, concurrent=None, augment=N
     augment = config.augment_data if augment is None else augment
     G = int(concurrent or num_games)
     eng = _engine_for(config, net, G, seed=seed, dtype=dtype, first_game_id=first_game_id,
-                      game_id_stride=game_id_stride, restart_finished=(G < num_games))
-    chunk = max(8, config.MAX_ITER // 2)
+                      game_id_stride=game_id_stride, restart_finished=(G < num_games), random_openings=True)
+    # steps between two drains: a game finishes at most one search per `iters_min` steps and the sample ring holds
+    # 4 records per game, so at most 3 * iters_min steps may pass (random opening plies leave no record)
+    iters_min = config.playout_iterations()[1] if (config.training and config.use_playout_cap_randomization) else config.MAX_ITER
+    chunk = max(1, min(max(8, config.MAX_ITER // 2), 3 * max(1, iters_min)))
     per_game, finished = {}, {}
     all_samples, all_ends = [], []
     steps = 0
@@ -287,6 +290,7 @@ def generate_games(config, net, num_games, seed=None, concurrent=None, augment=N
         eng.step(chunk)
         steps += chunk
         samples, ends = eng.drain()
+        eng.check_status()   # overflowed FIFO / arena / rings, a root without a move: the reference asserts (ai.py:417,1347)
         if compact:       # no per-record Python: the set is assembled from the arrays at the end
             all_samples.append(samples)
             all_ends.append(ends)
@@ -378,21 +382,50 @@ class SearchResult:
         return [(index_to_move(m), int(n)) for m, n in zip(self.moves, self.visits)]
 
 
+_SEARCH_KEYS = ("MAX_ITER", "CPUCT", "DPUCT", "FpuStrategy", "FpuValue", "use_root_softmax", "RootSoftmaxTemp", "use_tanh",
+                "training", "temperature", "use_playout_cap_randomization", "playout_cap_chance", "playout_cap_mult",
+                "use_dirichlet_noise", "DIRICHLET_ALPHA", "DIRICHLET_S", "DIRICHLET_EXPLORATION", "use_dirichlet_s",
+                "use_forced_playouts_and_policy_target_pruning", "CForcedPlayout", "ruleset", "move_algorithm")
+_mcts_engines = {}   # (network identity + weight versions, search settings, seed) -> one-game engine, reused between calls
+
+
+def _mcts_engine(config, net, seed):
+    """main.py-style callers search move after move with the same network (reference main.py:80,145): keep the
+    one-game engine (evaluator, packed weights, tree buffers) instead of rebuilding it per call.  The key carries
+    the in-place version counters of the parameters, so a trained / re-loaded network gets a fresh engine."""
+    if isinstance(net, torch.nn.Module):
+        ident = (id(net), tuple(int(t._version) for t in list(net.parameters()) + list(net.buffers())))
+    else:
+        ident = (id(net),)
+    key = (ident, tuple(repr(getattr(config, k, None)) for k in _SEARCH_KEYS), seed)
+    eng = _mcts_engines.get(key)
+    if eng is None:
+        if len(_mcts_engines) >= 4:
+            _mcts_engines.pop(next(iter(_mcts_engines)))
+        eng = _engine_for(config, net, 1, seed=seed, restart_finished=False, save_all=True, use_cuda_graph=False)
+        _mcts_engines[key] = eng
+    return eng
+
+
 def MCTS(config, game, interference_network, seed=None, game_id=0, search_no=0):
     """One search of one reference-style `Game` (ai.py:299): returns (move=(plane, col, row),
-    SearchResult, save_bool).  `game` is not mutated."""
+    SearchResult, save_bool).  `game` is not mutated.  No random opening plies here, whatever
+    config.use_random_starting_moves says: only play_game draws them (ai.py:1588-1608)."""
+    from .selfplay import CTL_DTYPE
     rec = np.zeros(1, dtype=GAME_DTYPE)
     pack_game(game, game_id=game_id, out=rec[0])
-    eng = _engine_for(config, interference_network, 1, seed=seed, restart_finished=False, save_all=True,
-                      use_cuda_graph=False)
+    eng = _mcts_engine(config, interference_network, seed)
+    eng.drain()
     eng.set_games(rec)
-    ctl = eng.get_ctl()
+    ctl = np.zeros(1, dtype=CTL_DTYPE)
+    ctl["active"] = 1
     ctl["search_no"] = search_no
     eng.set_ctl(ctl)
     long_iters, _ = config.playout_iterations()
     budget = long_iters if (config.training and config.use_playout_cap_randomization) else config.MAX_ITER
     eng.step(budget)
     samples, _ = eng.drain()
+    eng.check_status()
     if not len(samples):
         raise RuntimeError("search produced no result (game already over or no legal move)")
     s = min(samples, key=lambda r: int(r["search_no"]))

@@ -108,7 +108,12 @@ class AlphaSame(nn.Module):
 
     def forward_packed(self, grids, extras):
         b = extras.shape[0]
-        feats = self.grid_features(grids)
+        if self.training:
+            # the reference runs process_grid on the two boards separately (architectures.py:128-129): BatchNorm
+            # sees two batches of B (statistics and running-stat updates), not one of 2B
+            feats = torch.cat([self.grid_features(grids[:b]), self.grid_features(grids[b:])], dim=0)
+        else:
+            feats = self.grid_features(grids)
         x = torch.cat([feats[:b], extras[:, :SIDE_FEATS], self.osidedense(feats[b:]), extras[:, SIDE_FEATS:]], dim=1)
         return self.value_head(x), self.policy_head(x)
 
@@ -157,7 +162,10 @@ class BaseResNet(nn.Module):
 
     def head_input(self, grids, extras):
         b = extras.shape[0]
-        feats = self._process_grid(grids)
+        if self.training:   # two BatchNorm batches like the reference (architectures.py:236-237), see AlphaSame
+            feats = torch.cat([self._process_grid(grids[:b]), self._process_grid(grids[b:])], dim=0)
+        else:
+            feats = self._process_grid(grids)
         own, opp, color = extras[:, :SIDE_FEATS], extras[:, SIDE_FEATS:2 * SIDE_FEATS], extras[:, 2 * SIDE_FEATS:]
         opp_repr = self.opp_encode(torch.cat([self.opp_collapse(feats[b:]).flatten(1), opp], dim=1))
         bias = self.bias_project(torch.cat([opp_repr, own, color], dim=1))

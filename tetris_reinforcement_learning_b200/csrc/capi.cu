@@ -7,8 +7,8 @@
 
 static thread_local char g_err[256] = "";
 static std::mutex g_ws_mutex;
-static void* g_ws_ptr[TRL_WS_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
-static size_t g_ws_size[TRL_WS_SLOTS] = {0, 0, 0, 0};
+static void* g_ws_ptr[TRL_WS_SLOTS] = {};
+static size_t g_ws_size[TRL_WS_SLOTS] = {};
 static cudaStream_t g_host_stream[2] = {nullptr, nullptr};
 
 int trl_check(cudaError_t e) {
@@ -43,7 +43,7 @@ cudaStream_t trl_host_stream(int which) {
 int g_trl_pdl = 1;
 extern "C" void trl_set_pdl(int enabled) { g_trl_pdl = enabled ? 1 : 0; }
 
-extern "C" int trl_abi_version(void) { return 8; }
+extern "C" int trl_abi_version(void) { return 9; }
 extern "C" const char* trl_last_error(void) { return g_err; }
 extern "C" int trl_sizeof_player(void) { return (int)sizeof(TrlPlayer); }
 extern "C" int trl_sizeof_game(void) { return (int)sizeof(TrlGame); }

@@ -28,7 +28,7 @@ constexpr int TRL_PATH_MAX_DEPTH = 30;
 
 static_assert(sizeof(TrlSearchCtl) == 80, "TrlSearchCtl layout");
 static_assert(sizeof(TrlSearchParams) == 160, "TrlSearchParams layout");
-static_assert(sizeof(TrlSearchBuffers) == 256, "TrlSearchBuffers layout");
+static_assert(sizeof(TrlSearchBuffers) == 264, "TrlSearchBuffers layout");
 static_assert(sizeof(TrlGameEnd) == 32, "TrlGameEnd layout");
 static_assert(sizeof(TrlSample) == 20 + 400 + 3 * 2 * TRL_SAMPLE_MOVES, "TrlSample layout");
 
@@ -301,6 +301,11 @@ __device__ void finish_search(const TrlSearchBuffers& B, const TrlSearchParams& 
 
     int chosen = -1;
     TrlSample* rec = nullptr;
+    // random opening ply (ai.py:1597-1608): one iteration, move sampled from the priors, never stored.  Read by
+    // lane 0 and broadcast: lane 0 decrements the counter below.
+    int random_ply = 0;
+    if (lane == 0) random_ply = ctl->random_left > 0;
+    random_ply = __shfl_sync(kFull, random_ply, 0);
     if (C > 0) {
         // most visited root child, LAST maximum (ai.py:579-587)
         double bestn = -1.0; int max_i = -1;
@@ -314,7 +319,7 @@ __device__ void finish_search(const TrlSearchBuffers& B, const TrlSearchParams& 
         // random.choices' accumulate + bisect
         const double temp = P.training ? P.temperature : 0.0;
         if (lane == 0) {
-            if (ctl->random_left > 0) {
+            if (random_ply) {
                 // pick_random_move_by_policy (ai.py:999-1014): random.choices(moves, priors); purpose 7
                 double total = 0.0;
                 for (int c = 0; c < C; ++c) total += B.prior[nb + base + c];
@@ -348,13 +353,13 @@ __device__ void finish_search(const TrlSearchBuffers& B, const TrlSearchParams& 
         chosen = __shfl_sync(kFull, chosen, 0);
 
         const bool save = !ctl->fast;
-        const bool want_rec = save || P.save_all;
+        const bool want_rec = (save || P.save_all) && !random_ply;
         uint32_t slot_i = 0;
         if (want_rec) {
             if (lane == 0) slot_i = atomicAdd(B.sample_count, 1u);
             slot_i = __shfl_sync(kFull, slot_i, 0);
             if (slot_i < (uint32_t)B.sample_cap) rec = &B.samples[slot_i];
-            else if (lane == 0) ctl->status |= TRL_ST_MOVES_TRUNC;
+            else if (lane == 0) ctl->status |= TRL_ST_SAMPLE_OVERFLOW;   // the record of this search is lost
         }
         if (rec)
             for (int c = lane; c < C && c < TRL_SAMPLE_MOVES; c += 32) {
@@ -434,6 +439,8 @@ __device__ void finish_search(const TrlSearchBuffers& B, const TrlSearchParams& 
                 ge.pieces0 = rg->players[0].pieces; ge.lines_sent0 = ctl->lines_sent0;
                 ge.lines_cleared0 = ctl->lines_cleared0; ge.pad_ = 0;
                 B.ends[e] = ge;
+            } else {
+                ctl->status |= TRL_ST_END_OVERFLOW;
             }
             ctl->games_finished += 1;
             ctl->search_no = 0; ctl->lines_sent0 = 0; ctl->lines_cleared0 = 0;
@@ -472,6 +479,10 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
         // legal placements: enumerated this step, or the list stored under the parent state by a sibling
         const uint16_t* mv = B.legal + (size_t)g * B.moves_cap;
         int C = (kind == 0) ? (int)B.n_legal[g] : 0;
+        if (B.movegen_status && !B.movegen_list && lane == 0 && (!B.movegen_index || B.movegen_index[g] >= 0)) {
+            const uint32_t st = B.movegen_status[g] & (TRL_ST_QUEUE_OVERFLOW | TRL_ST_MOVES_TRUNC);
+            if (st) ctl->status |= st;
+        }
         if (B.legal_cache_n && B.movegen_index && leaf != 0) {
             // the selection left the parent's state index in leaf_parent (two dependent loads less)
             const size_t pstate = B.leaf_parent ? (size_t)B.leaf_parent[g] : sb + (size_t)B.slot[nb + B.parent[nb + leaf]];
@@ -490,7 +501,7 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
         if (C > B.moves_cap) C = B.moves_cap;
         if (C > 0 && ctl->n_nodes + C > B.node_cap) {  // arena full: the leaf stays childless
             C = 0;
-            if (lane == 0) ctl->status |= TRL_ST_QUEUE_OVERFLOW;
+            if (lane == 0) ctl->status |= TRL_ST_ARENA_FULL;
         }
         if (C > 0) {
             // priors over the legal moves (ai.py:411-443).  softmax over all 11583 logits followed
@@ -673,18 +684,18 @@ extern "C" int trl_search_select(const TrlSearchBuffers* buf, const TrlSearchPar
 }
 
 int trl_movegen_indexed(const TrlGame* games, const int32_t* index, int n, uint16_t* moves, int moves_cap,
-                        uint16_t* n_moves, cudaStream_t stream);  // movegen.cu
+                        uint16_t* n_moves, uint32_t* status, cudaStream_t stream);  // movegen.cu
 int trl_launch_movegen_listed(const TrlGame* games, const int32_t* index, const int32_t* list, uint32_t* count,
-                              uint16_t* moves, int moves_cap, uint16_t* n_moves, cudaStream_t stream);  // movegen_warp.cu
+                              uint16_t* moves, int moves_cap, uint16_t* n_moves, TrlSearchCtl* ctl, cudaStream_t stream);  // movegen_warp.cu
 
 extern "C" int trl_search_movegen(const TrlSearchBuffers* buf, void* stream) {
     if (!buffers_ok(buf)) return TRL_E_ARG;
     if (buf->n_games == 0) return TRL_OK;
     if (buf->movegen_list && buf->movegen_count && buf->movegen_index)
         return trl_launch_movegen_listed(buf->states, buf->movegen_index, buf->movegen_list, buf->movegen_count,
-                                         buf->legal, buf->moves_cap, buf->n_legal, (cudaStream_t)stream);
+                                         buf->legal, buf->moves_cap, buf->n_legal, buf->ctl, (cudaStream_t)stream);
     return trl_movegen_indexed(buf->states, buf->movegen_index ? buf->movegen_index : buf->leaf_state, buf->n_games,
-                               buf->legal, buf->moves_cap, buf->n_legal, (cudaStream_t)stream);
+                               buf->legal, buf->moves_cap, buf->n_legal, buf->movegen_status, (cudaStream_t)stream);
 }
 
 extern "C" int trl_search_expand(const TrlSearchBuffers* buf, const TrlSearchParams* prm, const void* values,

@@ -282,8 +282,8 @@ extern "C" int trl_movegen_games(const TrlGame* games, int n, uint32_t* mask_bit
 
 // Search-internal form: item i enumerates games[index[i]] (index[i] < 0: no moves).
 int trl_movegen_indexed(const TrlGame* games, const int32_t* index, int n, uint16_t* moves, int moves_cap,
-                        uint16_t* n_moves, cudaStream_t stream) {
-    return launch_movegen(nullptr, nullptr, nullptr, games, index, n, nullptr, moves, moves_cap, n_moves, nullptr, stream);
+                        uint16_t* n_moves, uint32_t* status, cudaStream_t stream) {
+    return launch_movegen(nullptr, nullptr, nullptr, games, index, n, nullptr, moves, moves_cap, n_moves, status, stream);
 }
 
 extern "C" int trl_movegen_host(const uint16_t* boards, const uint8_t* cur, const uint8_t* alt, int n,

@@ -36,6 +36,7 @@
 namespace {
 
 constexpr int kFifoCap = 768;             // live entries; adversarial cave boards peak < 500.
+__constant__ int c_fifo_limit = kFifoCap;   // <= kFifoCap; lowered only by trl_debug_movegen_fifo_limit (tests force the overflow bit)
                                           // 768 keeps a block at 30 KB of shared memory: 7 blocks = 56 warps per SM
 constexpr int kCallsPerBlock = 8;   // 16 warps, 60 KB of shared memory, 62 registers: 2 blocks per SM (measured best of 1/2/4/8;
                                     // __launch_bounds__(512, 3) = 40 registers with spills: 125 ms vs 119 ms on the sweep)
@@ -229,7 +230,7 @@ __device__ void search_piece_warp(PieceState& S, const uint16_t* rows, int type,
                     }
                     const uint32_t pm = __ballot_sync(0xffffffffu, res == 1);
                     const int total = __popc(pm);
-                    if ((tail - head) + (uint32_t)total > (uint32_t)kFifoCap) status |= TRL_ST_QUEUE_OVERFLOW;
+                    if ((tail - head) + (uint32_t)total > (uint32_t)c_fifo_limit) status |= TRL_ST_QUEUE_OVERFLOW;
                     else {
                         if (res == 1)   // lane order = (row, column, direction) = the reference's queue order
                             S.fifo[(tail + (uint32_t)__popc(pm & ((1u << lane) - 1u))) % kFifoCap] = (uint16_t)fifo_pack(tx, ty, nrot, 1, nulk);
@@ -302,7 +303,7 @@ __device__ void search_piece_warp(PieceState& S, const uint16_t* rows, int type,
                 if (lane >= d) incl += t;
             }
             const int total = __shfl_sync(0xffffffffu, incl, 31);
-            const bool room = (tail - head) + (uint32_t)total <= (uint32_t)kFifoCap;
+            const bool room = (tail - head) + (uint32_t)total <= (uint32_t)c_fifo_limit;
             if (!room) status |= TRL_ST_QUEUE_OVERFLOW;
             const uint32_t any_im = is_T ? __ballot_sync(0xffffffffu, (Im[0] | Im[1] | Im[2]) != 0u) : 0u;
             if ((total && room) || any_im) {
@@ -561,7 +562,8 @@ __device__ __forceinline__ void slot_barrier(int slot) {
 __global__ void __launch_bounds__(kListSlots * 64)
 movegen_list_kernel(const TrlGame* __restrict__ games, const int32_t* __restrict__ index,
                     const int32_t* __restrict__ list, uint32_t* __restrict__ count_done,
-                    uint16_t* __restrict__ moves, int moves_cap, uint16_t* __restrict__ n_moves, int rounds) {
+                    uint16_t* __restrict__ moves, int moves_cap, uint16_t* __restrict__ n_moves, int rounds,
+                    TrlSearchCtl* __restrict__ ctl) {   // optional: per-game control blocks that collect the TRL_ST_* bits
     extern __shared__ __align__(16) uint8_t smem_raw[];
     PieceState* ps = reinterpret_cast<PieceState*>(smem_raw);
     CallState* cs = reinterpret_cast<CallState*>(smem_raw + sizeof(PieceState) * kListSlots * 2);
@@ -614,6 +616,7 @@ movegen_list_kernel(const TrlGame* __restrict__ games, const int32_t* __restrict
                 const int type = which ? a : c;
                 if (type != TRL_NONE && !(which && a == c))
                     search_piece_warp(ps[warp], C.rows, type, which != 0, C.mask, st, &s_kpack[type == P_I ? 1 : 0]);
+                if (st && lane == 0) atomicOr(&C.status, st);   // FIFO overflow of either piece search
             }
             slot_barrier(slot);
             if (which == 0) {
@@ -645,7 +648,11 @@ movegen_list_kernel(const TrlGame* __restrict__ games, const int32_t* __restrict
                         ++pos;
                     }
                 }
-                if (lane == 0) n_moves[g] = (uint16_t)total;
+                if (lane == 0) {
+                    n_moves[g] = (uint16_t)total;
+                    const uint32_t st = C.status | (total > moves_cap ? TRL_ST_MOVES_TRUNC : 0u);
+                    if (st && ctl) atomicOr(&ctl[g].status, st);   // sticky: the host reads it with the other bits
+                }
             }
             slot_barrier(slot);   // the mask is re-zeroed and the ticket redrawn for the next call
         }
@@ -668,8 +675,13 @@ movegen_list_kernel(const TrlGame* __restrict__ games, const int32_t* __restrict
 static int g_list_rounds = 1;
 extern "C" void trl_search_movegen_rounds(int rounds) { g_list_rounds = rounds < 1 ? 1 : (rounds > 16 ? 16 : rounds); }
 
+extern "C" int trl_debug_movegen_fifo_limit(int limit) {
+    if (limit < 1 || limit > kFifoCap) limit = kFifoCap;
+    return trl_check(cudaMemcpyToSymbol(c_fifo_limit, &limit, sizeof(int)));
+}
+
 int trl_launch_movegen_listed(const TrlGame* games, const int32_t* index, const int32_t* list, uint32_t* count_done,
-                              uint16_t* moves, int moves_cap, uint16_t* n_moves, cudaStream_t stream) {
+                              uint16_t* moves, int moves_cap, uint16_t* n_moves, TrlSearchCtl* ctl, cudaStream_t stream) {
     if (!games || !index || !list || !count_done || !moves || !n_moves || moves_cap <= 0) return TRL_E_ARG;
     const size_t smem = sizeof(PieceState) * kListSlots * 2 + sizeof(CallState) * kListSlots;
     static int n_sm = 0;
@@ -682,7 +694,7 @@ int trl_launch_movegen_listed(const TrlGame* games, const int32_t* index, const 
         n_sm = sms;
     }
     movegen_list_kernel<<<n_sm, kListSlots * 64, smem, stream>>>(games, index, list, count_done, moves, moves_cap, n_moves,
-                                                                g_list_rounds);
+                                                                g_list_rounds, ctl);
     return trl_check(cudaGetLastError());
 }
 

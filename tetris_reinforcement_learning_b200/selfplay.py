@@ -54,8 +54,22 @@ GAME_END_DTYPE = np.dtype({
 })
 
 
-def search_params_from_config(config, seed=0, restart_finished=True, game_id_stride=1, save_all=None, max_rounds=None):
-    """Config (ai.py:97-137) -> TrlSearchParams."""
+STATUS_BITS = {0x1: "QUEUE_OVERFLOW (movegen FIFO)", 0x2: "MOVES_TRUNC (move list longer than moves_cap)",
+               0x4: "NO_PIECE (root without a legal move)", 0x8: "RECV_OVERFLOW (pending-garbage list)",
+               0x10: "BAD_MOVE", 0x20: "SAMPLE_OVERFLOW (sample ring full: records dropped)",
+               0x40: "ARENA_FULL (node arena full: a leaf stayed childless)",
+               0x80: "END_OVERFLOW (game-end ring full: records dropped)"}
+
+
+class EngineStatusError(RuntimeError):
+    """A device-side TRL_ST_* bit is set: the data of this run is not what the reference would have produced
+    (the reference asserts / raises in these situations, ai.py:417,1347)."""
+
+
+def search_params_from_config(config, seed=0, restart_finished=True, game_id_stride=1, save_all=None, max_rounds=None,
+                              random_openings=False):
+    """Config (ai.py:97-137) -> TrlSearchParams.  random_openings: only play_game draws random opening plies
+    (ai.py:1588-1608); MCTS() and battle_networks never do, whatever config.use_random_starting_moves says."""
     from .const import MAX_MOVES
     p = _native.SearchParams()
     p.seed = int(seed)
@@ -83,7 +97,7 @@ def search_params_from_config(config, seed=0, restart_finished=True, game_id_str
     p.restart_finished = int(bool(restart_finished))
     p.game_id_stride = int(game_id_stride)
     # random opening plies sampled from the raw policy (ai.py:1588-1608); scale = 0.04 * DIRICHLET_S
-    p.use_random_start = int(bool(getattr(config, "use_random_starting_moves", False)))
+    p.use_random_start = int(bool(random_openings) and bool(getattr(config, "use_random_starting_moves", False)))
     p.random_start_scale = 0.04 * float(config.DIRICHLET_S)
     return p
 
@@ -100,7 +114,7 @@ class SelfPlayEngine:
                  feature_dtype=torch.float32, node_cap=None, sample_cap=None, restart_finished=True, save_all=None,
                  max_rounds=None, use_cuda_graph=True, overlap_movegen=True, reuse_trunk_features=True,
                  reuse_sibling_placements=True, compact_movegen=True, fuse_expand_select=True, fuse_encode=True,
-                 steps_per_graph=4, parallel_backup=True):
+                 steps_per_graph=4, parallel_backup=True, random_openings=False):
         from .state import ruleset_id
         self.ruleset = ruleset_id(config.ruleset)   # 's2' (default) or 's1': attack table + all-spin rule
         if config.move_algorithm != "convolutional":
@@ -109,7 +123,8 @@ class SelfPlayEngine:
         self.config, self.evaluator = config, evaluator
         self.G = int(n_games)
         self.device = torch.device(device)
-        self.params = search_params_from_config(config, seed, restart_finished, game_id_stride, save_all, max_rounds)
+        self.params = search_params_from_config(config, seed, restart_finished, game_id_stride, save_all, max_rounds,
+                                                random_openings)
         self.seed = int(seed)
         self.feature_dtype = feature_dtype
         self.use_cuda_graph = use_cuda_graph
@@ -137,6 +152,7 @@ class SelfPlayEngine:
             "samples": z(self.sample_cap * SAMPLE_DTYPE.itemsize, torch.uint8), "sample_count": z(1, torch.int32),
             "ends": z(self.end_cap * GAME_END_DTYPE.itemsize, torch.uint8), "end_count": z(1, torch.int32),
             "next_game_id": z(1, torch.int32), "leaf_parent": z(G, torch.int32), "path": z(G * 64, torch.int32),
+            "movegen_status": z(G, torch.int32),
         }
         # exact reuse of legal-placement lists between siblings (include/trl.h, TrlSearchBuffers.legal_cache)
         self.reuse_sibling_placements = bool(reuse_sibling_placements)
@@ -254,7 +270,7 @@ class SelfPlayEngine:
 
         mode = self.overlap_movegen
         if mode is True:
-            mode = "tail" if self.cached_eval is not None else "trunk"
+            mode = getattr(self.cached_eval, "overlap_mode", "tail") if self.cached_eval is not None else "trunk"
         if mode in ("heads", "tail") and self.cached_eval is None:
             mode = "trunk"
         # "tail": the enumeration depends on the feature encoder (an event) but is submitted AFTER the trunk
@@ -394,7 +410,12 @@ class SelfPlayEngine:
         hc[4:].copy_(self.t["end_count"].view(torch.uint8), non_blocking=True)
         torch.cuda.synchronize(self.device)
         cnt = hc.numpy().view(np.uint32)
-        ns, ne = min(int(cnt[0]), self.sample_cap), min(int(cnt[1]), self.end_cap)
+        if int(cnt[0]) > self.sample_cap or int(cnt[1]) > self.end_cap:
+            # the kernels also set TRL_ST_SAMPLE_OVERFLOW / TRL_ST_END_OVERFLOW in the games that lost a record
+            raise EngineStatusError(f"record rings overflowed between two drains: {int(cnt[0])} samples (capacity "
+                                    f"{self.sample_cap}), {int(cnt[1])} game ends (capacity {self.end_cap}); drain more "
+                                    "often or pass a larger sample_cap")
+        ns, ne = int(cnt[0]), int(cnt[1])
         nsb, neb = ns * SAMPLE_DTYPE.itemsize, ne * GAME_END_DTYPE.itemsize
         hs[:nsb].copy_(self.t["samples"][:nsb], non_blocking=True)
         he[:neb].copy_(self.t["ends"][:neb], non_blocking=True)
@@ -405,16 +426,32 @@ class SelfPlayEngine:
         ends = he[:neb].numpy().view(GAME_END_DTYPE)
         return (samples.copy(), ends.copy()) if copy else (samples, ends)
 
+    def status_bits(self):
+        """OR of the sticky TRL_ST_* bits of all games (0 = clean)."""
+        return int(np.bitwise_or.reduce(self.get_ctl()["status"])) if self.G else 0
+
+    def check_status(self, ignore=0):
+        """Raise EngineStatusError if any game carries a status bit outside `ignore`."""
+        st = self.get_ctl()["status"]
+        bad = st & ~np.uint32(ignore)
+        if bad.any():
+            bits = int(np.bitwise_or.reduce(bad))
+            names = [n for b, n in STATUS_BITS.items() if bits & b]
+            raise EngineStatusError(f"{int((bad != 0).sum())} of {self.G} games report device status 0x{bits:x}: " + "; ".join(names))
+
     def total_sims(self):
         return int(self.get_ctl()["sims"].sum())
 
 
 def best_evaluator(net, dtype=torch.bfloat16):
-    """The fastest evaluator for `net`: the fused tcgen05 trunk + PyTorch heads where the
-    architecture allows it (AlphaSame, 16 filters), else the plain PyTorch path."""
-    from . import trunk
+    """The fastest evaluator for `net`: a fused tcgen05 trunk where the architecture allows it (AlphaSame with
+    16 filters: csrc/trunk_rows.cu; AlphaSame / BaseResNet / AuxBaseResNet with 32 or 64 filters:
+    csrc/trunk_wide.cu), else the plain PyTorch path."""
+    from . import trunk, trunk_wide
     if dtype == torch.bfloat16 and trunk.supports(net):
         return trunk.make_fused_evaluator(net, dtype)
+    if dtype == torch.bfloat16 and trunk_wide.supports(net):
+        return trunk_wide.make_wide_evaluator(net, dtype)
     return make_net_evaluator(net, dtype)
 
 

@@ -88,6 +88,41 @@ def allreduce_gradients(model):
         off += n
 
 
+def sync_batchnorm_buffers(model):
+    """Average the floating-point buffers (BatchNorm running mean / variance) over all ranks and take rank 0's
+    integer buffers: after a data-parallel epoch every replica then holds the same module, buffers included."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    bufs = [b for b in model.buffers() if b.is_floating_point()]
+    if bufs:
+        flat = torch.cat([b.reshape(-1).float() for b in bufs])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat /= dist.get_world_size()
+        off = 0
+        for b in bufs:
+            n = b.numel()
+            b.copy_(flat[off:off + n].view_as(b).to(b.dtype))
+            off += n
+    for b in model.buffers():
+        if not b.is_floating_point():
+            dist.broadcast(b, src=0)
+
+
+def _assert_same_step_count(n_batches, device):
+    """Ranks with different batch counts would deadlock in the gradient all-reduce: fail loudly instead."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    lo = torch.tensor([n_batches], dtype=torch.int64, device=device)
+    hi = lo.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if int(lo) != int(hi):
+        raise RuntimeError(f"data-parallel training needs the same number of batches on every rank (min {int(lo)}, max {int(hi)}): "
+                           "give every rank the same number of samples")
+
+
 def train_network_pytorch(config, model, samples, data_number=None, log=True):
     """AdamW on MSE(value) + CE(policy) (+ aux_weight * MSE(aux)); returns the mean losses."""
     from .ai import highest_data_number, logs_dir
@@ -111,6 +146,8 @@ def train_network_pytorch(config, model, samples, data_number=None, log=True):
     model.train()
     tot = dict(loss=0.0, value=0.0, policy=0.0, aux=0.0)
     batches = 0
+    n_samples = len(samples) if hasattr(samples, "__len__") else 0
+    _assert_same_step_count((n_samples + config.batch_size - 1) // config.batch_size, device)
     for _ in range(config.epochs):
         for batch in loader:
             batch = [b.to(device) for b in batch]
@@ -130,6 +167,7 @@ def train_network_pytorch(config, model, samples, data_number=None, log=True):
             opt.zero_grad()
             tot["loss"] += loss.item(); tot["value"] += l_value.item(); tot["policy"] += l_policy.item()
             batches += 1
+    sync_batchnorm_buffers(model)
     model.eval()
     avg = {k: v / max(batches, 1) for k, v in tot.items()}
     print(f"loss: {avg['loss']:>7f}  value: {avg['value']:>7f}  policy: {avg['policy']:>7f}" +

@@ -10,8 +10,11 @@ from .architectures import SIDE_FEATS, AlphaSame
 
 
 def supports(net):
+    """csrc/trunk_rows.cu / trunk.cu hard-code 16 filters and one 1x1 kernel; csrc/heads.cu the 16-wide
+    opponent summary and value hidden layer."""
     return (isinstance(net, AlphaSame) and net.conv1.out_channels == 16 and net.kernel1.out_channels == 1
-            and len(net.res_blocks) <= 20)
+            and len(net.res_blocks) <= 20 and net.osidedense[0].out_features == 16
+            and net.value_head[0].out_features == 16)
 
 
 def _fold_bn(bn):
