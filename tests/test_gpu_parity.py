@@ -180,7 +180,7 @@ def test_get_move_matrix_dropin(mg, oracle):
 
 def test_movegen_full_size_properties(mg, oracle):
     """BASELINE config 2 at full size (1M boards x 7 pieces) on device tensors: determinism,
-    n_moves == popcount(mask) == len(move list), and a strided sample against the oracle."""
+    n_moves == popcount(mask) == len(move list), and ALL 7M masks / counts against the oracle."""
     import torch
     n_boards = int(os.environ.get("TRL_FULL_BOARDS", "1000000"))
     boards, cur, alt = synth.movegen_workload(n_boards)
@@ -218,16 +218,27 @@ def test_movegen_full_size_properties(mg, oracle):
     assert checksum(d_mask2) == checksum1
     assert torch.equal(d_mask[::9973], d_mask2[::9973])
     del d_mask2
-    # strided sample vs oracle (bit-exact) incl. ascending move lists
-    idx = np.arange(0, n, max(1, n // 20000))
-    want_masks, want_n, _, _ = oracle.movegen_batch(boards[idx], cur[idx], alt[idx], n_threads=os.cpu_count() or 1)
-    t_idx = torch.from_numpy(idx).to(dev)
-    got = d_mask[t_idx].cpu().numpy().view(np.uint32)
-    assert np.array_equal(got, want_masks)
-    got_moves = d_moves[t_idx].cpu().numpy().view(np.uint16)
-    for k in range(0, len(idx), 97):
-        want = _moves_from_mask(want_masks[k])[:128]
-        assert np.array_equal(got_moves[k, :len(want)], want)
+    # EVERY call against the oracle, bit for bit (BASELINE config 2: "placements bit-exact vs move_generation.py" on
+    # the 1M x 7 sweep; reference move_generation.py:752-789): masks, counts and the ascending move lists, slab by
+    # slab so that the host never holds more than ~0.5 GB of masks.  The C oracle runs on all host threads.
+    slab = 350_000
+    threads = os.cpu_count() or 1
+    checked = 0
+    for lo in range(0, n, slab):
+        hi = min(n, lo + slab)
+        want_masks, want_n, _, _ = oracle.movegen_batch(boards[lo:hi], cur[lo:hi], alt[lo:hi], n_threads=threads)
+        got = d_mask[lo:hi].cpu().numpy().view(np.uint32)
+        if not np.array_equal(got, want_masks):
+            bad = np.nonzero((got != want_masks).any(axis=1))[0]
+            raise AssertionError(f"{len(bad)} of {hi - lo} masks differ in slab {lo}; first call {lo + int(bad[0])}")
+        assert np.array_equal(d_n[lo:hi].cpu().numpy().view(np.uint16), want_n)
+        got_moves = d_moves[lo:hi:97].cpu().numpy().view(np.uint16)
+        for k in range(0, got_moves.shape[0], 13):
+            want = _moves_from_mask(want_masks[k * 97])[:128]
+            assert np.array_equal(got_moves[k, :len(want)], want)
+        checked += hi - lo
+    assert checked == n
+    print("config 2: masks of", checked, "calls bit-exact vs the oracle,", total, "placements")
     assert total > 40 * n_boards  # sanity: tens of placements per call
 
 
@@ -315,38 +326,45 @@ def test_env_device_api_and_skip(env, oracle):
 
 
 def test_every_emitted_placement_steps_like_the_oracle(env, oracle):
-    """BASELINE config 2, second half: for EVERY placement the device enumerates on a sample of the sweep
-    workload, the device env step (lock, spin detection, line clears, all-clear, attack, b2b / combo, garbage
-    with a fixed column tape, next piece, top-out) equals the oracle's on the same state, bit for bit."""
+    """BASELINE config 2, second half ("post-clear boards bit-exact vs board.py"): for EVERY placement the device
+    enumerates on 105 000 calls of the sweep workload (~5 M placements), the device env step (lock, spin detection,
+    line clears, all-clear, attack, b2b / combo, garbage with a fixed column tape, next piece, top-out; reference
+    player.py:109-188, game.py:66-118) equals the oracle's on the same state, bit for bit."""
     from tetris_reinforcement_learning_b200 import move_generation as mgen
     seed = 20261018
-    boards, cur, alt = synth.movegen_workload(1200)            # 8400 calls, all three board families
-    n = boards.shape[0]
-    res = mgen.movegen_host(boards, cur, alt, want_mask=False, want_moves=True, moves_cap=256)
-    counts = res["n_moves"].astype(np.int64)
-    assert (counts <= 256).all() and counts.sum() > 40 * n // 7
-    base = env.game_setup_host(n, 0, seed)
-    base["turn"] = 0
-    p0 = base["players"][:, 0]
-    p0["rows"] = boards
-    p0["piece"] = cur
-    p0["held"] = alt                                            # the sweep's second piece is the hold piece
-    base["players"][:, 0] = p0
-    rep = np.repeat(np.arange(n), counts)
-    games = base[rep].copy()
-    games["game_id"] = np.arange(len(rep), dtype=np.uint32)     # one garbage-column stream per placement
-    shadow = games.copy()
-    moves = np.concatenate([res["moves"][i, :counts[i]] for i in range(n)]).astype(np.uint16)
-    assert len(moves) == len(games) > 300000 // 7
-    out = env.env_step_host(games, moves, True, seed)
-    want = oracle.env_step(shadow, moves, True, seed)
-    assert np.array_equal(out.view(np.uint8), want.view(np.uint8))
-    assert games_equal(games, shadow).all()
-    assert (out["status"] == 0).all()
+    n_boards = int(os.environ.get("TRL_STEP_BOARDS", "15000"))
+    all_boards, all_cur, all_alt = synth.movegen_workload(n_boards)    # all three board families
+    tot = dict(placements=0, clears=0, attacks=0, tspins=0, minis=0, all_clears=0, holds=0, top_outs=0)
+    slab = 10500
+    for lo in range(0, all_boards.shape[0], slab):
+        boards, cur, alt = all_boards[lo:lo + slab], all_cur[lo:lo + slab], all_alt[lo:lo + slab]
+        n = boards.shape[0]
+        res = mgen.movegen_host(boards, cur, alt, want_mask=False, want_moves=True, moves_cap=256)
+        counts = res["n_moves"].astype(np.int64)
+        assert (counts <= 256).all() and (res["status"] == 0).all()
+        base = env.game_setup_host(n, 0, seed)
+        base["turn"] = 0
+        p0 = base["players"][:, 0]
+        p0["rows"] = boards
+        p0["piece"] = cur
+        p0["held"] = alt                                            # the sweep's second piece is the hold piece
+        base["players"][:, 0] = p0
+        rep = np.repeat(np.arange(n), counts)
+        games = base[rep].copy()
+        games["game_id"] = (lo * 64 + np.arange(len(rep))).astype(np.uint32)   # one garbage-column stream per placement
+        shadow = games.copy()
+        moves = np.concatenate([res["moves"][i, :counts[i]] for i in range(n)]).astype(np.uint16)
+        assert len(moves) == len(games)
+        out = env.env_step_host(games, moves, True, seed)
+        want = oracle.env_step(shadow, moves, True, seed)
+        assert np.array_equal(out.view(np.uint8), want.view(np.uint8)), f"step outputs differ in slab {lo}"
+        assert games_equal(games, shadow).all(), f"result states differ in slab {lo}"
+        assert (out["status"] == 0).all()
+        tot["placements"] += len(moves)
+        tot["clears"] += int((out["rows_cleared"] > 0).sum()); tot["attacks"] += int((out["attack"] > 0).sum())
+        for name, bit in (("tspins", 1), ("minis", 2), ("all_clears", 4), ("holds", 8), ("top_outs", 0x10)):
+            tot[name] += int(((out["flags"] & bit) != 0).sum())
     # the sample exercises the rules: clears, spins, all-spin minis, attacks, holds, top-outs
-    print("placements", len(moves), "clears", int((out["rows_cleared"] > 0).sum()), "attacks", int((out["attack"] > 0).sum()),
-          "t-spins", int(((out["flags"] & 1) != 0).sum()), "minis", int(((out["flags"] & 2) != 0).sum()),
-          "all-clears", int(((out["flags"] & 4) != 0).sum()), "holds", int(((out["flags"] & 8) != 0).sum()),
-          "top-outs", int(((out["flags"] & 0x10) != 0).sum()))
-    assert (out["rows_cleared"] > 0).sum() > 100 and (out["attack"] > 0).sum() > 10
-    assert ((out["flags"] & 1) != 0).sum() > 0 and ((out["flags"] & 2) != 0).sum() > 0 and ((out["flags"] & 8) != 0).sum() > 1000
+    print("config 2 post-placement states:", all_boards.shape[0], "calls", tot)
+    assert tot["placements"] > 40 * all_boards.shape[0] // 7
+    assert tot["clears"] > 100 and tot["attacks"] > 10 and tot["tspins"] > 0 and tot["minis"] > 0 and tot["holds"] > 1000
