@@ -24,10 +24,51 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-NCU_DRAM_BYTES_PER_CALL = 1.0206e9 / 700000  # measured DRAM traffic of movegen_warp_kernel (profiles/r1_summary.md)
+PROFILE_JSON = ("profiles/r2_movegen_warp.json", "profiles/r1_movegen_warp_sweep2.json")   # tools/ncu_extract.py, newest first
+SCALAR_PROFILE_JSON = "profiles/r2_movegen_thread.json"   # the one-thread-per-call kernel = the scalar restatement on the GPU
 ALGO_BYTES_PER_CALL = 80 + 4 + 1448  # board + (cur, alt, pad) in, bit-packed (27,39,11) mask out
 METRIC = "placements/sec (movegen)"
 UNIT = "placements/s"
+
+
+def load_ncu_profile():
+    """Per-call ncu figures of movegen_warp_kernel from the tracked extraction of the .ncu-rep (tools/ncu_extract.py);
+    None if no profile is committed."""
+    for rel in PROFILE_JSON:
+        path = os.path.join(ROOT, rel)
+        if not os.path.exists(path):
+            continue
+        with open(path) as f:
+            d = json.load(f)
+        for l in d["launches"]:
+            if "movegen_warp_kernel" in l["kernel"] and l.get("units"):
+                m = {k: v["value"] for k, v in l["metrics"].items()}
+                warp_inst = m.get("smsp__inst_executed.sum", 0.0)
+                return {"source": f"{rel} ({d['report']}, extracted at {d['extracted_at_commit']})", "calls": l["units"],
+                        "dram_bytes_per_call": l.get("dram_bytes_per_unit"),
+                        "issue_slots_busy_pct": m.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                        "alu_pipe_pct_of_peak": m.get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                        "threads_per_warp_instruction": m.get("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                        "warp_instructions_per_call": warp_inst / l["units"] if warp_inst else None,
+                        "thread_instructions_per_call": l.get("thread_instructions_per_unit"),
+                        "kernel_ms_under_ncu": m.get("gpu__time_duration.sum"),
+                        "barrier_stall_warps_per_issue": m.get("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio")}
+    return None
+
+
+def load_scalar_profile():
+    """Thread-level instruction count per call of the scalar restatement (movegen_thread_kernel: one thread runs the
+    reference's algorithm for one call), the 'algorithmic int-ops' of SURVEY 8(d)."""
+    path = os.path.join(ROOT, SCALAR_PROFILE_JSON)
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        d = json.load(f)
+    for l in d["launches"]:
+        if "movegen_thread_kernel" in l["kernel"] and l.get("thread_instructions_per_unit"):
+            return {"source": f"{SCALAR_PROFILE_JSON} ({d['report']}, extracted at {d['extracted_at_commit']})",
+                    "thread_instructions_per_call": l["thread_instructions_per_unit"], "calls": l["units"]}
+    return None
 
 
 def load_peaks():
@@ -91,8 +132,9 @@ def make_workload(n_boards, rank):
     return synth.movegen_workload(n_boards, seed=synth.DEFAULT_SEED + 1000 * rank)
 
 
-def cpu_baseline(boards, cur, alt, target_s=12.0):
-    """The oracle port (plain C, pthreads over all host cores) on a bounded sample of the workload."""
+def cpu_baseline(boards, cur, alt, target_s=12.0, device_masks=None, device_counts=None):
+    """The oracle port (plain C, pthreads over all host cores) on a bounded sample of the workload.  The masks it
+    computes are compared with the device's masks of the same calls (parity inside the bench run)."""
     from oracle import oracle
     cores = os.cpu_count() or 1
     probe = min(boards.shape[0], 7 * 2000)
@@ -102,14 +144,103 @@ def cpu_baseline(boards, cur, alt, target_s=12.0):
     n = int(min(boards.shape[0], max(probe, probe * target_s / max(dt, 1e-3))))
     n -= n % 7
     t0 = time.perf_counter()
-    _, _, _, tot = oracle.movegen_batch(boards[:n], cur[:n], alt[:n], n_threads=cores, want_masks=True)
+    want_masks, want_n, _, tot = oracle.movegen_batch(boards[:n], cur[:n], alt[:n], n_threads=cores, want_masks=True)
     dt = time.perf_counter() - t0
-    return {"value": tot / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"first {n // 7} boards x 7 pieces ({n} calls, {tot} placements) of the same workload, "
-                      f"{dt:.1f} s, oracle/trl_oracle.c with {cores} pthreads",
-            "python_reference_per_core": 3.7e4,
-            "python_reference_note": "unmodified reference get_move_matrix measured in the build container (SURVEY §6); "
-                                     "it cannot travel to the GPU box"}
+    out = {"value": tot / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"first {n // 7} boards x 7 pieces ({n} calls, {tot} placements) of the same workload, "
+                     f"{dt:.1f} s, oracle/trl_oracle.c with {cores} pthreads",
+           "python_reference_per_core": 3.7e4,
+           "python_reference_note": "unmodified reference get_move_matrix measured in the build container (SURVEY §6); "
+                                    "it cannot travel to the GPU box"}
+    parity = None
+    if device_masks is not None:
+        mism = 0
+        for lo in range(0, n, 200_000):
+            hi = min(n, lo + 200_000)
+            got = device_masks[lo:hi].cpu().numpy().view(np.uint32)
+            mism += int((got != want_masks[lo:hi]).any(axis=1).sum())
+        if device_counts is not None:
+            mism += int((device_counts[:n].cpu().numpy().view(np.uint16) != want_n).sum())
+        parity = {"parity_checked_calls": n, "mismatches": mism,
+                  "how": "bit-packed (27,39,11) masks and counts of the device run vs oracle/trl_oracle.c on the same calls"}
+    return out, parity
+
+
+def cpu_selfplay_worker(seconds, index):
+    """One process of the CPU self-play baseline: the oracle's restatement of ai.MCTS (oracle/mcts_oracle.py, C env
+    step and placements) driving the repo's AlphaSame(10,16) on ONE CPU thread, BASELINE config 1 (MAX_ITER=160,
+    playout-cap randomisation on).  Stands in for reference ai.py:1570-1699 play_game, which cannot travel to the box.
+    Prints one JSON line."""
+    import torch
+    torch.set_num_threads(1)
+    from oracle import features_oracle, mcts_oracle, oracle
+    from tetris_reinforcement_learning_b200 import architectures as arch
+    from tetris_reinforcement_learning_b200.config import Config
+    oracle.lib()
+    torch.manual_seed(0)
+    mc = arch.AlphaSameConfig(blocks=10, filters=16)
+    net = arch.AlphaSame(mc).eval()
+    cfg = Config(visual=False, ruleset="s2", model="pytorch", model_config=mc, MAX_ITER=160, CPUCT=0.75, training=True)
+    evals = [0]
+
+    def evaluate(rec):
+        grids, extras = features_oracle.encode(rec)
+        with torch.no_grad():
+            v, logits = net.forward_packed(torch.from_numpy(grids).reshape(2, 1, 40, 10), torch.from_numpy(extras)[None])
+        evals[0] += 1
+        return float(v.reshape(-1)[0]), torch.softmax(logits[0], dim=0).numpy().reshape(27, 39, 11)
+
+    seed, gid = 20261018, 1000 + index
+    games = oracle.game_setup(1, gid, seed)
+    sims = plies = finished = 0
+    search_no = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        res = mcts_oracle.search(cfg, games, evaluate, mcts_oracle.SearchTape(seed, gid, search_no))
+        sims += res["iterations"]
+        plies += 1
+        search_no += 1
+        oracle.env_step(games, np.array([res["move"]], dtype=np.uint16), True, seed)
+        if mcts_oracle.is_terminal(games[0]) or int(games[0]["rounds"]) >= 1000:
+            finished += 1
+            gid += 10000
+            games = oracle.game_setup(1, gid, seed)
+            search_no = 0
+    dt = time.perf_counter() - t0
+    print(json.dumps({"sims": sims, "plies": plies, "games_finished": finished, "evals": evals[0], "seconds": dt}), flush=True)
+
+
+def cpu_selfplay_baseline(seconds=12.0, mean_plies=None):
+    """P = host cores single-threaded worker processes of cpu_selfplay_worker; sims/s summed over the processes."""
+    cores = os.cpu_count() or 1
+    env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-selfplay-worker", str(seconds), "--worker-index", str(i)],
+                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env) for i in range(cores)]
+    outs = []
+    for pr in procs:
+        try:
+            o, _ = pr.communicate(timeout=seconds * 6 + 180)
+            outs.append(json.loads(o.strip().splitlines()[-1]))
+        except Exception:
+            pr.kill()
+    wall = time.perf_counter() - t0
+    if not outs:
+        return {"unavailable": "no CPU self-play worker finished"}
+    sims_per_s = sum(o["sims"] / o["seconds"] for o in outs)
+    plies_per_s = sum(o["plies"] / o["seconds"] for o in outs)
+    out = {"sims_per_sec": sims_per_s, "sims_per_sec_per_core": sims_per_s / len(outs), "cores": len(outs), "kind": "port",
+           "moves_per_sec": plies_per_s, "games_finished": sum(o["games_finished"] for o in outs),
+           "sample": f"{len(outs)} single-threaded processes x {seconds:.0f} s of self-play searches (oracle/mcts_oracle.py + "
+                     "oracle/trl_oracle.c env step and placements + AlphaSame(10,16) fp32 on CPU, MAX_ITER=160 with playout-cap "
+                     f"randomisation: 400 / 80 iterations per move); wall {wall:.0f} s incl. process start",
+           "python_reference_per_core": {"sims_per_sec": 82, "games_per_hour": 29,
+                                         "note": "unmodified reference play_game in the build container (BASELINE.md §2)"}}
+    if mean_plies and mean_plies == mean_plies:
+        out["games_per_hour"] = plies_per_s / mean_plies * 3600.0
+        out["games_per_hour_note"] = (f"derived: measured moves/s / {mean_plies:.1f} plies per game (the mean game length the GPU "
+                                      "engine measured in this run); a CPU game takes minutes, none completes inside the sample")
+    return out
 
 
 def run_selfplay(args, rank, world, local_rank):
@@ -129,26 +260,59 @@ def run_selfplay(args, rank, world, local_rank):
     G = args.games
     sh = shard_for_rank(rank, world, G)
 
-    def engine(max_iter, n_games=G, **kw):
-        cfg = Config(visual=False, ruleset="s2", model="pytorch", model_config=mc, MAX_ITER=max_iter, CPUCT=0.75,
-                     training=True, use_playout_cap_randomization=False, use_dirichlet_noise=True,
-                     FpuStrategy="reduction", use_forced_playouts_and_policy_target_pruning=args.forced)
-        return SelfPlayEngine(cfg, ev, n_games, device=dev, seed=20261018, first_game_id=sh["first_game_id"],
+    def engine(max_iter, n_games=G, forced=None, evaluator=None, model_config=None, **kw):
+        cfg = Config(visual=False, ruleset="s2", model="pytorch", model_config=model_config or mc, MAX_ITER=max_iter, CPUCT=0.75,
+                     training=True, use_playout_cap_randomization=False, use_dirichlet_noise=True, FpuStrategy="reduction",
+                     use_forced_playouts_and_policy_target_pruning=args.forced if forced is None else forced)
+        return SelfPlayEngine(cfg, evaluator or ev, n_games, device=dev, seed=20261018, first_game_id=sh["first_game_id"],
                               game_id_stride=sh["game_id_stride"], feature_dtype=torch.bfloat16, **kw)
 
-    def timed(eng):
+    def timed(eng, steps=None):
+        steps = steps or args.selfplay_steps
         eng.step(12)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        eng.step(args.selfplay_steps)
+        eng.step(steps)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         return e0.elapsed_time(e1)
+
+    def extra_leg(name, steps, max_iter, forced=False, net_cfg=None, what=""):
+        """One more sims/s line: same games per GPU, another search setting or another network; max over ranks."""
+        evaluator, flops_board, net_name = None, 37.2e6 / 2, "AlphaSame(blocks=10, filters=16)"
+        if net_cfg is not None:
+            torch.manual_seed(0)
+            wide_net = arch.build_network(net_cfg).to(dev)
+            evaluator = best_evaluator(wide_net, torch.bfloat16)
+            f, b = net_cfg.filters, net_cfg.blocks
+            stem = 25 if isinstance(net_cfg, arch.AlphaSameConfig) else 9
+            flops_board = 2.0 * 400 * (stem * f + 2 * b * 9 * f * f)
+            net_name = f"{type(wide_net).__name__}(blocks={b}, filters={f})"
+        e = engine(max_iter, forced=forced, evaluator=evaluator, model_config=net_cfg)
+        fused = e.cached_eval is not None
+        t = timed(e, steps)
+        st = e.get_ctl()["status"]
+        if evaluator is not None and hasattr(evaluator, "trunk"):
+            evaluator.trunk.check()
+        del e
+        torch.cuda.empty_cache()
+        tt = torch.tensor([t], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt[0])
+        v = G * world * steps / (t * 1e-3)
+        return {"what": what, "value": v, "unit": "sims/s", "games_per_gpu": G, "n_gpus": world, "steps": steps, "max_iter": max_iter,
+                "ms_per_step": t / steps, "net": net_name + " bf16, random init", "fused_trunk": fused,
+                "forced_playouts_and_pruning": bool(forced), "status_nonzero_rank0": int((st != 0).sum()),
+                "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": load_tensor_peak(),
+                             "achieved": v / world * flops_board / 1e12, "frac": v / world * flops_board / 1e12 / load_tensor_peak(),
+                             "flops_counted": "trunk convolutions of ONE board per simulation (trunk-feature reuse); heads and policy "
+                                              "GEMM not counted"}}
 
     eng = engine(160)
     eng_flags = eng
@@ -210,6 +374,21 @@ def run_selfplay(args, rank, world, local_rank):
         mean_plies = float(np.mean(plies)) if plies else float("nan")
         del eng
         torch.cuda.empty_cache()
+    extra = {}
+    if not args.no_config4:
+        extra["config4_forced_playouts"] = extra_leg(
+            "config4", args.selfplay_steps, 160, forced=True,
+            what="BASELINE config 4: the config-3 engine with forced playouts + policy-target pruning, same games per GPU, every GPU "
+                 "count the driver runs (weak scaling)")
+    if not args.no_wide:
+        extra["config5_net"] = extra_leg(
+            "config5", 48, 800, net_cfg=arch.AlphaSameConfig(blocks=20, filters=64),
+            what="BASELINE config 5's network and search budget in the self-play engine: AlphaSame(20, 64), MAX_ITER=800, through "
+                 "csrc/trunk_wide.cu (through PyTorch / cuDNN the same step took 51 ms in round 1)")
+        extra["config_default_net"] = extra_leg(
+            "default", 96, 400, net_cfg=arch.AuxBaseResNetConfig(),
+            what="the reference's Config default (ai.py:83): AuxBaseResNet(8, 32), MAX_ITER=400, through csrc/trunk_wide.cu "
+                 "(PyTorch / cuDNN: 17 ms per step in round 1)")
     stats = torch.tensor([ms, float(G * args.selfplay_steps), float(len(samples)), ms_both or 0.0, game_ms, float(games_done)],
                          dtype=torch.float64, device=dev)
     if world > 1:
@@ -224,6 +403,7 @@ def run_selfplay(args, rank, world, local_rank):
     flops_done = (86.5e6 - 37.2e6) if reuse else 86.5e6   # with reuse one board per leaf goes through the trunk
     return {
         "_launches": launches_per_step * args.selfplay_steps,
+        **extra,
         "mcts_sims_per_sec": {
             "value": sims_per_s, "unit": "sims/s", "games_per_gpu": G, "n_gpus": world, "steps": args.selfplay_steps,
             "ms_per_step": ms / args.selfplay_steps, "max_iter": 160, "net": "AlphaSame(blocks=10, filters=16) bf16, " + ("PyTorch/cuDNN" if args.net_path == "pytorch" else
@@ -405,6 +585,13 @@ def run_ours(args, rank, world, local_rank):
     d2h_list = placements * 2 + n * (8 + 2 + 4)
     del h_moves
 
+    cpu_line, parity = None, None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        step()                      # the device masks of the timed configuration, compared call by call below
+        torch.cuda.synchronize()
+        cpu_line, parity = cpu_baseline(boards, cur, alt, device_masks=d_mask, device_counts=d_n)
     # free the sweep's buffers before the self-play leg
     del d_mask
     torch.cuda.empty_cache()
@@ -428,6 +615,33 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = load_peaks()
     achieved = ALGO_BYTES_PER_CALL * n / (kern_ms * 1e-3) / 1e9
     value = placements_all * args.steps / (total_ms * 1e-3)
+    prof, scalar = load_ncu_profile(), load_scalar_profile()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": int(prof["dram_bytes_per_call"] * n) if prof and prof.get("dram_bytes_per_call") else None,
+                "traffic_unit": "bytes per launch",
+                "traffic_source": (f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per call of a {int(prof['calls'])}-call "
+                                   f"launch, scaled to this launch's call count; {prof['source']}") if prof else None,
+                "peak_source": peak_src, "kernel": "movegen_warp_kernel",
+                "algorithmic_bytes_per_call": ALGO_BYTES_PER_CALL, "kernel_ms": kern_ms,
+                "note": "integer-issue bound, not HBM bound (SURVEY §8d): the DRAM traffic is at the algorithmic minimum; "
+                        "what binds is the ALU / XU pipes, see int_ops",
+                "ncu": prof}
+    # roofline on integer issue.  per_call = thread-level instructions of the SCALAR restatement of the
+    # algorithm (one thread per call, ncu); achieved = per_call x calls/s; peak = 148 SMs x 4 schedulers x 32 lanes x f_SM
+    f_sm = (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    peak_ops = sms * 4 * 32 * f_sm
+    calls_per_s = n / (kern_ms * 1e-3)
+    if scalar:
+        roofline["int_ops"] = {
+            "per_call": scalar["thread_instructions_per_call"], "achieved": scalar["thread_instructions_per_call"] * calls_per_s,
+            "peak": peak_ops, "unit": "thread instructions/s", "frac": scalar["thread_instructions_per_call"] * calls_per_s / peak_ops,
+            "peak_how": f"{sms} SMs x 4 issue slots x 32 lanes x {f_sm / 1e6:.0f} MHz (SM clock sampled during the timed region)",
+            "per_call_source": scalar["source"],
+            "executed_per_call": prof.get("thread_instructions_per_call") if prof else None,
+            "executed_frac": (prof["thread_instructions_per_call"] * calls_per_s / peak_ops) if prof and prof.get("thread_instructions_per_call") else None,
+            "note": "per_call = what the one-thread-per-call kernel (the reference's algorithm, scalar) executes; executed_per_call = "
+                    "what movegen_warp_kernel executes (bit-parallel passes do redundant lane work); frac is useful work / peak"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -437,16 +651,7 @@ def run_ours(args, rank, world, local_rank):
                    "boards_per_gpu": args.boards, "calls_per_step_per_gpu": n,
                    "placements_per_step_per_gpu": placements, "l2": "inputs+outputs (>10 GB/step) exceed the 126 MB L2",
                    "status_nonzero": bad_status},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": int(NCU_DRAM_BYTES_PER_CALL * n), "traffic_unit": "bytes per launch",
-                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum = 1.0206e9 B for a 700 000-call "
-                                       "launch (profiles/r1_summary.md), scaled to this launch's call count",
-                     "peak_source": peak_src, "kernel": "movegen_warp_kernel",
-                     "algorithmic_bytes_per_call": ALGO_BYTES_PER_CALL, "kernel_ms": kern_ms,
-                     "note": "integer-issue bound, not HBM bound (SURVEY §8d): the DRAM traffic is at the algorithmic minimum; "
-                             "what binds is the ALU / XU pipes",
-                     "ncu": {"issue_slots_busy_pct": 64.3, "alu_pipe_pct_of_peak": 53.8, "threads_per_warp_instruction": 21.6,
-                             "warp_instructions_per_call": 12650, "source": "profiles/r1_summary.md (r1_movegen_warp_sweep2.ncu-rep)"}},
+        "roofline": roofline,
         "e2e": {"value": placements_all / e2e_list_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_list,
                 "steps": e2e_steps, "matches_device_run": e2e_list_ok,
                 "api": "trl_movegen_host_compact: pinned host buffers in, ascending uint16 move lists (np.argwhere order, "
@@ -458,10 +663,12 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": args.steps,
         "clocks": clocks,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle
-        oracle.build()
-        line["cpu_baseline"] = cpu_baseline(boards, cur, alt)
+    if cpu_line is not None:
+        line["cpu_baseline"] = cpu_line
+        line["config"].update(parity or {})
+        if also is not None and not args.no_cpu_selfplay:
+            mp = also["selfplay_games_per_hour"].get("mean_plies_per_game")
+            line["cpu_baseline"]["selfplay"] = cpu_selfplay_baseline(args.cpu_selfplay_seconds, mp)
     if also is not None:
         line["also"] = also
         line["gpu_launches"] += also.pop("_launches", 0)
@@ -504,8 +711,18 @@ def main():
     ap.add_argument("--game-warm-steps", type=int, default=9000, help="steps before the games/h window (about one game length)")
     ap.add_argument("--game-steps", type=int, default=18000, help="steps of the games/h window (about two game lengths)")
     ap.add_argument("--net-path", default="fused", choices=["fused", "pytorch"])
-    ap.add_argument("--forced", action="store_true", help="forced playouts + policy-target pruning (config 4)")
+    ap.add_argument("--forced", action="store_true", help="forced playouts + policy-target pruning in the main self-play leg")
+    ap.add_argument("--no-config4", action="store_true", help="skip the config-4 leg (forced playouts + pruning)")
+    ap.add_argument("--no-wide", action="store_true", help="skip the wide-net legs (config 5 net, Config-default net)")
+    ap.add_argument("--no-cpu-selfplay", action="store_true")
+    ap.add_argument("--cpu-selfplay-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-selfplay-worker", type=float, default=0.0, help=argparse.SUPPRESS)
+    ap.add_argument("--worker-index", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_selfplay_worker > 0:
+        os.dup2(_REAL_STDOUT, 1)
+        cpu_selfplay_worker(args.cpu_selfplay_worker, args.worker_index)
+        return
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
     rank = int(os.environ.get("RANK", "0"))
