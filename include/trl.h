@@ -352,6 +352,11 @@ typedef struct TrlSearchBuffers {
     uint32_t* movegen_status;                /* [n_games] or NULL: TRL_ST_* bits of the uncompacted enumeration
                                                 (movegen_list == NULL); trl_search_expand folds them into
                                                 ctl.status.  The compacted enumeration writes ctl.status itself */
+    const struct TrlSearchParams* params2;   /* NULL, or a DEVICE array of two parameter sets = gating battle
+                                                (ai.py:1975-2114): the search of game g runs with
+                                                params2[(game_id ^ side to move at the root) & 1], i.e. network 1
+                                                plays player (game_id & 1) (colours alternate, ai.py:2087-2091);
+                                                the `prm` argument of the calls is then ignored             */
 } TrlSearchBuffers;
 
 int trl_sizeof_search_ctl(void);
@@ -392,6 +397,18 @@ int trl_search_expand_select_encode(const TrlSearchBuffers* buf, const TrlSearch
                                     const void* logits, int logits_stride, int dtype, void* cache_bf16,
                                     void* images_bf16, int32_t* image_dest, int32_t* n_images, void* extras_bf16,
                                     int32_t* own_row, int32_t* opp_row, int32_t* row_of, void* stream);
+
+/*
+ * Policy head on the legal moves only.  The reference computes Linear(head_in -> 11583) for every leaf
+ * (architectures.py:141) and then reads the entries of the legal moves (ai.py:411-443); this call computes exactly
+ * those: logits_legal[g][c] = bias[m] + x[g] . w[m] for the c-th legal move m of game g's selected leaf (this
+ * step's enumeration, or the list cached under the parent state), fp32.  Run it after trl_search_movegen and before
+ * trl_search_expand*, and pass logits_legal to expand with dtype = 2 and logits_stride = moves_cap (values bf16).
+ * x [n_games][k_pad] bf16 (k_pad % 8 == 0), w [>= 11583][k_pad] bf16 row-major, bias [>= 11583] bf16,
+ * logits_legal [n_games][moves_cap] f32.
+ */
+int trl_search_policy_legal(const TrlSearchBuffers* buf, const void* x_bf16, int k_pad, const void* w_bf16,
+                            const void* bias_bf16, float* logits_legal, void* stream);
 
 /* ------------------------------------------------------------------------------------ */
 /* fused convolutional trunk of the policy/value net (tcgen05 tensor cores)               */

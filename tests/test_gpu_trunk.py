@@ -182,3 +182,53 @@ def test_compact_movegen_and_fused_expand_select_are_exact():
                 assert np.array_equal(s[name], s_ref[name]), name
         assert np.sort(e, order=["game_id"]).tobytes() == e_ref.tobytes()
         assert int(c["sims"].sum()) == int(c_ref["sims"].sum())
+
+
+@pytest.mark.parametrize("family", ["alphasame16", "aux32"])
+def test_policy_head_on_legal_moves_equals_the_dense_head(family):
+    """trl_search_policy_legal computes Linear(head_in -> 11583) only at the legal moves of every leaf
+    (architectures.py:141 followed by ai.py:411-443).  Tolerance: the dense head is a bf16 GEMM with bf16 outputs,
+    the gathered one accumulates and stores fp32: |diff| <= 2^-7 |logit| + 0.02."""
+    import copy
+    import torch
+    from tetris_reinforcement_learning_b200 import architectures as arch
+    from tetris_reinforcement_learning_b200.config import Config
+    from tetris_reinforcement_learning_b200.selfplay import CTL_DTYPE, SelfPlayEngine, best_evaluator
+    torch.manual_seed(3)
+    if family == "alphasame16":
+        net = _random_net(2, 5)
+    else:
+        net = arch.AuxBaseResNet(arch.AuxBaseResNetConfig(blocks=1, filters=32)).to("cuda:0").eval()
+    ev = best_evaluator(copy.deepcopy(net))
+    cfg = Config(visual=False, ruleset="s2", model="pytorch", MAX_ITER=16, training=True, use_playout_cap_randomization=False)
+    G = 64
+    eng = SelfPlayEngine(cfg, ev, G, seed=2, feature_dtype=torch.bfloat16, max_rounds=4, use_cuda_graph=False,
+                         fuse_expand_select=False)
+    assert eng.gather_policy
+    checked = 0
+    for step in range(24):
+        eng.step(1)
+        torch.cuda.synchronize()
+        b = eng._cache_bufs
+        dense = torch.nn.functional.linear(b["x"], eng.cached_eval.w_pol, eng.cached_eval.b_pol).float().cpu().numpy()
+        got = b["logits_legal"].cpu().numpy()
+        ctl = eng.t["ctl"].cpu().numpy().view(CTL_DTYPE)
+        legal = eng.t["legal"].cpu().numpy().view(np.uint16).reshape(G, -1)
+        n_legal = eng.t["n_legal"].cpu().numpy().view(np.uint16)
+        cache = eng.t["legal_cache"].cpu().numpy().view(np.uint16).reshape(-1, eng.moves_cap)
+        cache_n = eng.t["legal_cache_n"].cpu().numpy()
+        parent = eng.t["leaf_parent"].cpu().numpy()
+        for g in range(G):
+            # iter == 0: this step finished the search and the control block already belongs to the next one
+            if ctl["leaf_kind"][g] != 0 or ctl["iter"][g] == 0:
+                continue
+            if ctl["leaf"][g] == 0:
+                moves = legal[g, :n_legal[g]]
+            else:
+                moves = cache[parent[g], :cache_n[parent[g]]]
+            want = dense[g, moves.astype(np.int64)]
+            diff = np.abs(got[g, :len(moves)] - want)
+            assert (diff <= 2.0 ** -7 * np.abs(want) + 0.02).all(), (step, g, float(diff.max()))
+            checked += len(moves)
+    assert checked > 20000
+    assert eng.status_bits() == 0

@@ -39,6 +39,7 @@ SIGNATURES = {
     "trl_sizeof_sample": (c_int, []),
     "trl_search_select": (c_int, [c_void_p, c_void_p, c_void_p]),
     "trl_search_movegen": (c_int, [c_void_p, c_void_p]),
+    "trl_search_policy_legal": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "trl_search_expand": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "trl_search_expand_select": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "trl_search_expand_select_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
@@ -117,4 +118,4 @@ class SearchBuffers(ctypes.Structure):
                                                "samples", "sample_count", "ends", "end_count",
                                                "next_game_id", "noise_override", "leaf_parent",
                                                "legal_cache", "legal_cache_n", "movegen_index", "path",
-                                               "movegen_list", "movegen_count", "movegen_status")]
+                                               "movegen_list", "movegen_count", "movegen_status", "params2")]

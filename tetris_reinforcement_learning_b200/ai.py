@@ -341,7 +341,7 @@ def make_training_set(config, interference_network, num_games, save_game=False, 
     sample list only when save_stats is False.  data_format="compact" (default: config.engine_data_format)
     keeps the samples as a compact.CompactSet and writes <n>.npz instead: same samples, same order,
     0.6 KB instead of 162 KB per saved search and no per-sample Python work."""
-    data_format = data_format or getattr(config, "engine_data_format", "json")
+    data_format = data_format or getattr(config, "engine_data_format", None) or "json"
     if data_format not in ("json", "compact"):
         raise ValueError(f"unknown data_format {data_format!r}")
     series_data, series_stats = generate_games(config, interference_network, num_games, seed=seed,
@@ -364,6 +364,18 @@ def make_training_set(config, interference_network, num_games, save_game=False, 
             out_file.write(json.dumps(averaged) + "\n")
     else:
         return series_data
+
+
+def export_training_set_json(config, set_number, out_path=None):
+    """<data_dir>/<n>.npz (compact set) -> <data_dir>/<n>.txt in the reference's format (one JSON list of 13-element
+    samples, ai.py:1822-1829), for consumers that read the reference's files."""
+    from .compact import CompactSet
+    cset = CompactSet.load(f"{config.data_dir}/{set_number}.npz")
+    out_path = out_path or f"{config.data_dir}/{set_number}.txt"
+    samples = cset.to_json_samples()
+    with open(out_path, "w") as f:
+        f.write(json.dumps(samples))
+    return out_path
 
 
 class SearchResult:
@@ -446,8 +458,10 @@ def self_play_loop(config, skip_first_set=False):
         if not skip_first_set:
             print(f"Starting training loop {it} with network version {highest_model_number(config)}")
             for _ in range(config.training_loops):
+                # compact sets by default: the JSON writer caps this call at 1.7e4 games/h against 2.5e6;
+                # training.load_data_and_train_model reads both, export_training_set_json() writes the reference's <n>.txt
                 make_training_set(training_config, challenger_infer, num_games=config.training_games,
-                                  save_game=True, save_stats=True)
+                                  save_game=True, save_stats=True, data_format=config.engine_data_format or "compact")
                 print("Finished making training set")
         else:
             skip_first_set = False

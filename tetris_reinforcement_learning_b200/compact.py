@@ -158,6 +158,39 @@ class CompactSet:
         z = np.load(path)
         return cls(z["state"].copy().view(GAME_DTYPE).reshape(-1), z["value"], z["offsets"], z["moves"], z["frac"], bool(z["augment"]))
 
+    def to_json_samples(self):
+        """The reference's sample list (13-element lists, x4 mirror variants when augmented): what make_training_set
+        writes with data_format="json" for the same games, in the same order."""
+        from .ai import _policy_to_lists, features_from_state, reflect_grid, reflect_pieces, reflect_policy_array
+        from .const import POLICY_SHAPE as shape
+        out = []
+        for i in range(self.n_searches):
+            lo, hi = int(self.offsets[i]), int(self.offsets[i + 1])
+            target = np.zeros(int(np.prod(shape)), dtype=np.float64)
+            target[self.moves[lo:hi].astype(np.int64)] = self.frac[lo:hi]
+            target = target.reshape(shape)
+            feats = features_from_state(self.state[i])
+            listify = lambda f: f.tolist() if isinstance(f, np.ndarray) else f  # noqa: E731
+            value = float(self.value[i])
+            value = int(value) if value == int(value) else value
+            variants = [(0, 0)] if not self.augment else [(0, 0), (0, 1), (1, 0), (1, 1)]
+            plain = mirrored = None
+            for a_ref, o_ref in variants:
+                d = [f.copy() if isinstance(f, np.ndarray) else f for f in feats]
+                if a_ref:
+                    d[0], d[1] = reflect_grid(d[0]), reflect_pieces(d[1])
+                if o_ref:
+                    d[5], d[6] = reflect_grid(d[5]), reflect_pieces(d[6])
+                d = [listify(f) for f in d]
+                if a_ref:
+                    mirrored = mirrored or _policy_to_lists(reflect_policy_array(target))
+                else:
+                    plain = plain or _policy_to_lists(target)
+                d.append(value)
+                d.append(mirrored if a_ref else plain)
+                out.append(d)
+        return out
+
     # ---- expansion into the tensors the JSON path yields ------------------------------------------
     def batch_tensors(self, sample_idx, device="cpu"):
         """Samples `sample_idx` (indices into the virtual JSON list: search * 4 + variant when augmented) ->

@@ -43,8 +43,10 @@ _DEFAULTS = dict(
 
 class Config:
     # B200-only knob (not a constructor argument of the reference): "json" = the reference's <n>.txt list of
-    # 13-element samples, "compact" = <n>.npz CompactSet (compact.py), 270x smaller and expanded on the training device
-    engine_data_format = "json"
+    # 13-element samples, "compact" = <n>.npz CompactSet (compact.py), 270x smaller and expanded on the training device.
+    # None = the caller's default: make_training_set writes JSON (drop-in for the reference's trainer), self_play_loop
+    # (whose trainer reads both) writes compact sets; ai.export_training_set_json turns a compact set into <n>.txt.
+    engine_data_format = None
 
     def __init__(self, **kwargs):
         unknown = set(kwargs) - set(_DEFAULTS)

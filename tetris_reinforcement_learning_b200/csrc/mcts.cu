@@ -28,7 +28,7 @@ constexpr int TRL_PATH_MAX_DEPTH = 30;
 
 static_assert(sizeof(TrlSearchCtl) == 80, "TrlSearchCtl layout");
 static_assert(sizeof(TrlSearchParams) == 160, "TrlSearchParams layout");
-static_assert(sizeof(TrlSearchBuffers) == 264, "TrlSearchBuffers layout");
+static_assert(sizeof(TrlSearchBuffers) == 272, "TrlSearchBuffers layout");
 static_assert(sizeof(TrlGameEnd) == 32, "TrlGameEnd layout");
 static_assert(sizeof(TrlSample) == 20 + 400 + 3 * 2 * TRL_SAMPLE_MOVES, "TrlSample layout");
 
@@ -271,6 +271,14 @@ __device__ void select_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
     leaf_pi = __shfl_sync(kFull, leaf_pi, 0);
 }
 
+// Gating battles (ai.py:1975-2114): two networks with their own search settings; the one that owns the side to
+// move at the root runs the search.  Colours alternate by game id (ai.py:2087-2091): network 1 plays player
+// (game_id & 1).  B.params2 = device array of the two parameter sets; the BATTLE kernels pick per game.
+__device__ __forceinline__ int battle_owner(const TrlSearchBuffers& B, int g) {
+    return (int)((B.games[g].game_id ^ (uint32_t)B.games[g].turn) & 1u);
+}
+
+template <bool BATTLE>
 __global__ void __launch_bounds__(kWarps * 32)
 search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
     __shared__ __align__(16) TrlGame s_game[kWarps];
@@ -278,7 +286,8 @@ search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
     const int g = blockIdx.x * kWarps + wib;
     if (g >= B.n_games) return;
     int si, pi;
-    select_body(B, P, g, lane, &s_game[wib], si, pi);
+    if (BATTLE) select_body(B, B.params2[battle_owner(B, g)], g, lane, &s_game[wib], si, pi);
+    else select_body(B, P, g, lane, &s_game[wib], si, pi);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -286,8 +295,14 @@ search_select_kernel(TrlSearchBuffers B, TrlSearchParams P) {
 // ---------------------------------------------------------------------------------------
 
 __device__ __forceinline__ float load_out(const void* p, size_t i, int dtype) {
-    return dtype == 0 ? reinterpret_cast<const float*>(p)[i]
-                      : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+    return dtype == 1 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i])
+                      : reinterpret_cast<const float*>(p)[i];
+}
+
+// logit of the c-th legal move: dense rows are indexed by the move, gathered rows (dtype 2, written by
+// policy_legal_kernel) by the position in the legal list
+__device__ __forceinline__ float load_logit(const void* p, size_t row_base, const uint16_t* mv, int c, int dtype) {
+    return load_out(p, row_base + (dtype == 2 ? (size_t)c : (size_t)mv[c]), dtype);
 }
 
 // End of a search (ai.py:571-648) + the per-move bookkeeping of play_game (ai.py:1611-1668).
@@ -475,7 +490,7 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
     if (kind == 2) {
         value = ctl->leaf_value;
     } else {
-        value = (double)load_out(values, (size_t)g, dtype);
+        value = (double)load_out(values, (size_t)g, dtype == 0 ? 0 : 1);   // gathered logits (dtype 2) come with bf16 values
         // legal placements: enumerated this step, or the list stored under the parent state by a sibling
         const uint16_t* mv = B.legal + (size_t)g * B.moves_cap;
         int C = (kind == 0) ? (int)B.n_legal[g] : 0;
@@ -513,9 +528,9 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int c = lane + 32 * k;
-                if (c < C) { lreg[k] = load_out(logits, lb + mv[c], dtype); mx = fmax(mx, (double)lreg[k]); }
+                if (c < C) { lreg[k] = load_logit(logits, lb, mv, c, dtype); mx = fmax(mx, (double)lreg[k]); }
             }
-            for (int c = lane + 128; c < C; c += 32) mx = fmax(mx, (double)load_out(logits, lb + mv[c], dtype));
+            for (int c = lane + 128; c < C; c += 32) mx = fmax(mx, (double)load_logit(logits, lb, mv, c, dtype));
             mx = warp_max(mx);
             const bool root_temp = (leaf == 0) && P.use_root_softmax;
             const double inv_temp = root_temp ? 1.0 / P.root_softmax_temp : 1.0;
@@ -524,7 +539,7 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
             for (int c = lane; c < C; c += 32) {
                 const int k = c >> 5;
                 const double l = (k < 4) ? (double)(k == 0 ? lreg[0] : k == 1 ? lreg[1] : k == 2 ? lreg[2] : lreg[3])
-                                         : (double)load_out(logits, lb + mv[c], dtype);
+                                         : (double)load_logit(logits, lb, mv, c, dtype);
                 double e = exp((l - mx) * inv_temp);
                 if (!(e > 0.0)) e = 1e-25;  // the reference's clamp of underflowed probabilities (ai.py:411)
                 B.prior[nb + base + c] = e;
@@ -609,6 +624,7 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
     if (ctl->iter >= ctl->max_iter) finish_search(B, P, g, lane, sgame);
 }
 
+template <bool BATTLE>
 __global__ void __launch_bounds__(kWarps * 32)
 search_expand_kernel(TrlSearchBuffers B, TrlSearchParams P, const void* __restrict__ values,
                      const void* __restrict__ logits, int logits_stride, int dtype) {
@@ -616,11 +632,13 @@ search_expand_kernel(TrlSearchBuffers B, TrlSearchParams P, const void* __restri
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int g = blockIdx.x * kWarps + wib;
     if (g >= B.n_games) return;
-    expand_body(B, P, g, lane, &s_game[wib], values, logits, logits_stride, dtype);
+    if (BATTLE) expand_body(B, B.params2[battle_owner(B, g)], g, lane, &s_game[wib], values, logits, logits_stride, dtype);
+    else expand_body(B, P, g, lane, &s_game[wib], values, logits, logits_stride, dtype);
 }
 
 // expand(t) + select(t+1): the same warp owns game g in both kernels, so running them back to back in
 // one launch is exact (a warp only reads what it wrote itself; __syncwarp orders its lanes).
+template <bool BATTLE>
 __global__ void __launch_bounds__(kWarps * 32, 7)   // 7 blocks per SM: 4096 games are resident in one wave
 search_expand_select_kernel(TrlSearchBuffers B, TrlSearchParams P, const void* __restrict__ values,
                             const void* __restrict__ logits, int logits_stride, int dtype) {
@@ -630,14 +648,22 @@ search_expand_select_kernel(TrlSearchBuffers B, TrlSearchParams P, const void* _
     trl_grid_dep_wait();
     trl_grid_dep_launch();   // the next kernel (feature encoder / trunk) may move in as our blocks retire
     if (g >= B.n_games) return;
-    expand_body(B, P, g, lane, &s_game[wib], values, logits, logits_stride, dtype);
-    __syncwarp();
     int si, pi;
-    select_body(B, P, g, lane, &s_game[wib], si, pi);
+    if (BATTLE) {
+        // the move that ends a search flips the side to move: the next search may belong to the other network
+        expand_body(B, B.params2[battle_owner(B, g)], g, lane, &s_game[wib], values, logits, logits_stride, dtype);
+        __syncwarp();
+        select_body(B, B.params2[battle_owner(B, g)], g, lane, &s_game[wib], si, pi);
+    } else {
+        expand_body(B, P, g, lane, &s_game[wib], values, logits, logits_stride, dtype);
+        __syncwarp();
+        select_body(B, P, g, lane, &s_game[wib], si, pi);
+    }
 }
 
 // ... + the feature encoding of the selected leaf (features_dev.cuh), straight from the leaf state that
 // select left in shared memory: one kernel boundary and one read of the state less per simulation.
+template <bool BATTLE>
 __global__ void __launch_bounds__(kWarps * 32, 7)
 search_expand_select_encode_kernel(TrlSearchBuffers B, TrlSearchParams P, const void* __restrict__ values,
                                    const void* __restrict__ logits, int logits_stride, int dtype, TrlEncodeArgs E) {
@@ -647,11 +673,17 @@ search_expand_select_encode_kernel(TrlSearchBuffers B, TrlSearchParams P, const 
     trl_grid_dep_wait();
     trl_grid_dep_launch();   // the next kernel (feature encoder / trunk) may move in as our blocks retire
     if (g >= B.n_games) return;
-    expand_body(B, P, g, lane, &s_game[wib], values, logits, logits_stride, dtype);
-    __syncwarp();
     int si, pi;
     int2 prow = make_int2(-1, -1);
-    select_body(B, P, g, lane, &s_game[wib], si, pi, E.row_of, &prow);
+    if (BATTLE) {
+        expand_body(B, B.params2[battle_owner(B, g)], g, lane, &s_game[wib], values, logits, logits_stride, dtype);
+        __syncwarp();
+        select_body(B, B.params2[battle_owner(B, g)], g, lane, &s_game[wib], si, pi, E.row_of, &prow);
+    } else {
+        expand_body(B, P, g, lane, &s_game[wib], values, logits, logits_stride, dtype);
+        __syncwarp();
+        select_body(B, P, g, lane, &s_game[wib], si, pi, E.row_of, &prow);
+    }
     __syncwarp();
     if (si < 0) {
         if (lane == 0) { E.own_row[g] = -1; E.opp_row[g] = -1; }
@@ -664,7 +696,85 @@ search_expand_select_encode_kernel(TrlSearchBuffers B, TrlSearchParams P, const 
     trl_encode_cached_leaf(s_game[wib], g, si, pi, pos, lane, E, inherit);
 }
 
+// ---------------------------------------------------------------------------------------
+// policy head on the legal moves only
+// ---------------------------------------------------------------------------------------
+// The reference evaluates Linear(head_in -> 11583) + softmax for every leaf (architectures.py:141, ai.py:1315-1318)
+// and then reads the ~50 entries of the legal moves (ai.py:411-443).  Here one warp per leaf computes exactly those
+// entries: logit[c] = bias[m_c] + x . W[m_c] for the leaf's legal list (this step's enumeration or the list cached
+// under the parent state, the same lookup as expand_body), fp32 accumulation, fp32 out [G][moves_cap].  The weight
+// matrix (12-38 MB) stays L2 resident; no [G, 11584] tensor exists.
+__global__ void __launch_bounds__(256)
+policy_legal_kernel(TrlSearchBuffers B, const __nv_bfloat16* __restrict__ x, int k_pad, const __nv_bfloat16* __restrict__ w,
+                    const __nv_bfloat16* __restrict__ bias, float* __restrict__ out) {
+    extern __shared__ __align__(16) uint4 s_x[];          // [8 warps][k_pad / 8]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = blockIdx.x * 8 + wib;
+    trl_grid_dep_wait();
+    if (g >= B.n_games) return;
+    const TrlSearchCtl* ctl = &B.ctl[g];
+    if (!ctl->active || ctl->leaf_kind != 0) return;
+    const uint16_t* mv = B.legal + (size_t)g * B.moves_cap;
+    int C = (int)B.n_legal[g];
+    if (B.legal_cache_n && B.movegen_index && ctl->leaf != 0) {
+        const size_t pstate = B.leaf_parent ? (size_t)B.leaf_parent[g]
+                                            : (size_t)g * B.state_cap + (size_t)B.slot[(size_t)g * B.node_cap + B.parent[(size_t)g * B.node_cap + ctl->leaf]];
+        const int cached = B.legal_cache_n[pstate];
+        if (cached >= 0) { mv = B.legal_cache + pstate * (size_t)B.moves_cap; C = cached; }
+    }
+    if (C > B.moves_cap) C = B.moves_cap;
+    const int chunks = k_pad >> 3;                        // 16-byte pieces of a row
+    uint4* sx = s_x + wib * chunks;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)g * k_pad);
+    for (int c = lane; c < chunks; c += 32) sx[c] = xr[c];
+    __syncwarp();
+    float* o = out + (size_t)g * B.moves_cap;
+    for (int c0 = 0; c0 < C; c0 += 2) {                   // two moves per pass: their loads overlap
+        const int m0 = mv[c0], m1 = (c0 + 1 < C) ? mv[c0 + 1] : m0;
+        const uint4* w0 = reinterpret_cast<const uint4*>(w + (size_t)m0 * k_pad);
+        const uint4* w1 = reinterpret_cast<const uint4*>(w + (size_t)m1 * k_pad);
+        float a0 = 0.f, a1 = 0.f;
+        for (int c = lane; c < chunks; c += 32) {
+            const uint4 xv = sx[c], u = __ldg(w0 + c), v = __ldg(w1 + c);
+            const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, us[4] = {u.x, u.y, u.z, u.w}, vs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float xl = __uint_as_float(xs[q] << 16), xh = __uint_as_float(xs[q] & 0xFFFF0000u);
+                a0 = fmaf(xl, __uint_as_float(us[q] << 16), a0); a0 = fmaf(xh, __uint_as_float(us[q] & 0xFFFF0000u), a0);
+                a1 = fmaf(xl, __uint_as_float(vs[q] << 16), a1); a1 = fmaf(xh, __uint_as_float(vs[q] & 0xFFFF0000u), a1);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            a0 += __shfl_xor_sync(kFull, a0, off);
+            a1 += __shfl_xor_sync(kFull, a1, off);
+        }
+        if (lane == 0) {
+            o[c0] = a0 + __bfloat162float(bias[m0]);
+            if (c0 + 1 < C) o[c0 + 1] = a1 + __bfloat162float(bias[m1]);
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int trl_search_policy_legal(const TrlSearchBuffers* buf, const void* x_bf16, int k_pad, const void* w_bf16,
+                                       const void* bias_bf16, float* logits_legal, void* stream) {
+    if (!buf || buf->n_games < 0 || !buf->ctl || !buf->legal || !buf->n_legal || !x_bf16 || !w_bf16 || !bias_bf16 || !logits_legal ||
+        k_pad <= 0 || (k_pad & 7))
+        return TRL_E_ARG;
+    if (buf->n_games == 0) return TRL_OK;
+    const size_t smem = (size_t)8 * (k_pad / 8) * sizeof(uint4);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        int rc = trl_check(cudaFuncSetAttribute(policy_legal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (rc) return rc;
+        configured = smem;
+    }
+    return trl_launch_ex(policy_legal_kernel, dim3((buf->n_games + 7) / 8), dim3(256), smem, (cudaStream_t)stream, true, false,
+                         *buf, (const __nv_bfloat16*)x_bf16, k_pad, (const __nv_bfloat16*)w_bf16, (const __nv_bfloat16*)bias_bf16,
+                         logits_legal);
+}
 
 extern "C" int trl_sizeof_search_ctl(void) { return (int)sizeof(TrlSearchCtl); }
 extern "C" int trl_sizeof_sample(void) { return (int)sizeof(TrlSample); }
@@ -676,10 +786,19 @@ static bool buffers_ok(const TrlSearchBuffers* b) {
            b->end_count && b->next_game_id;
 }
 
+// dtype 0 / 1: dense fp32 / bf16 rows of >= 11583 logits; dtype 2: fp32 rows of moves_cap logits of the legal moves
+// (trl_search_policy_legal); the values then are bf16 as with dtype 1
+static bool logits_ok(const TrlSearchBuffers* b, int stride, int dtype) {
+    if (dtype == 2) return stride >= b->moves_cap;
+    return (dtype == 0 || dtype == 1) && stride >= TRL_POLICY_SIZE;
+}
+
 extern "C" int trl_search_select(const TrlSearchBuffers* buf, const TrlSearchParams* prm, void* stream) {
     if (!buffers_ok(buf) || !prm) return TRL_E_ARG;
     if (buf->n_games == 0) return TRL_OK;
-    search_select_kernel<<<(buf->n_games + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(*buf, *prm);
+    const dim3 grid((buf->n_games + kWarps - 1) / kWarps);
+    if (buf->params2) search_select_kernel<true><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(*buf, *prm);
+    else search_select_kernel<false><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(*buf, *prm);
     return trl_check(cudaGetLastError());
 }
 
@@ -700,20 +819,22 @@ extern "C" int trl_search_movegen(const TrlSearchBuffers* buf, void* stream) {
 
 extern "C" int trl_search_expand(const TrlSearchBuffers* buf, const TrlSearchParams* prm, const void* values,
                                  const void* logits, int logits_stride, int dtype, void* stream) {
-    if (!buffers_ok(buf) || !prm || !values || !logits || logits_stride < TRL_POLICY_SIZE || (dtype != 0 && dtype != 1))
+    if (!buffers_ok(buf) || !prm || !values || !logits || !logits_ok(buf, logits_stride, dtype))
         return TRL_E_ARG;
     if (buf->n_games == 0) return TRL_OK;
-    search_expand_kernel<<<(buf->n_games + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(
-        *buf, *prm, values, logits, logits_stride, dtype);
+    const dim3 grid((buf->n_games + kWarps - 1) / kWarps);
+    if (buf->params2) search_expand_kernel<true><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(*buf, *prm, values, logits, logits_stride, dtype);
+    else search_expand_kernel<false><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(*buf, *prm, values, logits, logits_stride, dtype);
     return trl_check(cudaGetLastError());
 }
 
 extern "C" int trl_search_expand_select(const TrlSearchBuffers* buf, const TrlSearchParams* prm, const void* values,
                                         const void* logits, int logits_stride, int dtype, void* stream) {
-    if (!buffers_ok(buf) || !prm || !values || !logits || logits_stride < TRL_POLICY_SIZE || (dtype != 0 && dtype != 1))
+    if (!buffers_ok(buf) || !prm || !values || !logits || !logits_ok(buf, logits_stride, dtype))
         return TRL_E_ARG;
     if (buf->n_games == 0) return TRL_OK;
-    return trl_launch_ex(search_expand_select_kernel, dim3((buf->n_games + kWarps - 1) / kWarps), dim3(kWarps * 32), 0,
+    return trl_launch_ex(buf->params2 ? search_expand_select_kernel<true> : search_expand_select_kernel<false>,
+                         dim3((buf->n_games + kWarps - 1) / kWarps), dim3(kWarps * 32), 0,
                          (cudaStream_t)stream, true, false, *buf, *prm, values, logits, logits_stride, dtype);
 }
 
@@ -722,7 +843,7 @@ extern "C" int trl_search_expand_select_encode(const TrlSearchBuffers* buf, cons
                                                void* images_bf16, int32_t* image_dest, int32_t* n_images,
                                                void* extras_bf16, int32_t* own_row, int32_t* opp_row, int32_t* row_of,
                                                void* stream) {
-    if (!buffers_ok(buf) || !prm || !values || !logits || logits_stride < TRL_POLICY_SIZE || (dtype != 0 && dtype != 1) ||
+    if (!buffers_ok(buf) || !prm || !values || !logits || !logits_ok(buf, logits_stride, dtype) ||
         !buf->leaf_parent || !cache_bf16 || !images_bf16 || !image_dest || !n_images || !extras_bf16 || !own_row || !opp_row ||
         !row_of)
         return TRL_E_ARG;
@@ -731,6 +852,7 @@ extern "C" int trl_search_expand_select_encode(const TrlSearchBuffers* buf, cons
     E.cache = (__nv_bfloat16*)cache_bf16; E.images = (__nv_bfloat16*)images_bf16; E.image_dest = image_dest;
     E.n_images = n_images; E.extras = (__nv_bfloat16*)extras_bf16; E.own_row = own_row; E.opp_row = opp_row;
     E.row_of = row_of;
-    return trl_launch_ex(search_expand_select_encode_kernel, dim3((buf->n_games + kWarps - 1) / kWarps), dim3(kWarps * 32), 0,
+    return trl_launch_ex(buf->params2 ? search_expand_select_encode_kernel<true> : search_expand_select_encode_kernel<false>,
+                         dim3((buf->n_games + kWarps - 1) / kWarps), dim3(kWarps * 32), 0,
                          (cudaStream_t)stream, true, false, *buf, *prm, values, logits, logits_stride, dtype, E);
 }

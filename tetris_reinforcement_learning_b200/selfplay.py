@@ -114,7 +114,7 @@ class SelfPlayEngine:
                  feature_dtype=torch.float32, node_cap=None, sample_cap=None, restart_finished=True, save_all=None,
                  max_rounds=None, use_cuda_graph=True, overlap_movegen=True, reuse_trunk_features=True,
                  reuse_sibling_placements=True, compact_movegen=True, fuse_expand_select=True, fuse_encode=True,
-                 steps_per_graph=4, parallel_backup=True, random_openings=False):
+                 steps_per_graph=4, parallel_backup=True, random_openings=False, gather_policy=True):
         from .state import ruleset_id
         self.ruleset = ruleset_id(config.ruleset)   # 's2' (default) or 's1': attack table + all-spin rule
         if config.move_algorithm != "convolutional":
@@ -185,7 +185,9 @@ class SelfPlayEngine:
         if not parallel_backup:
             b.path = None        # the backup then walks the parent links serially
         self.buf = b
-        self._cache_bufs = self.cached_eval.make_buffers(ns, G, dev) if self.cached_eval is not None else None
+        # policy head evaluated on the legal moves only (needs the cached evaluator, which owns the head input x)
+        self.gather_policy = bool(gather_policy) and self.cached_eval is not None and getattr(self.cached_eval, "gather_policy", False)
+        self._cache_bufs = self.cached_eval.make_buffers(ns, G, dev, self.moves_cap) if self.cached_eval is not None else None
         assert self.lib.trl_sizeof_search_ctl() == CTL_DTYPE.itemsize and self.lib.trl_sizeof_sample() == SAMPLE_DTYPE.itemsize
         self._pinned, self._pinned_i = None, 0      # host staging of drain()
         self._graph = None
@@ -297,11 +299,16 @@ class SelfPlayEngine:
             stamp(9, st)
         elif mode == "trunk":
             fork_movegen()
+        def join_movegen():
+            if self.overlap_movegen and self._side is not None:
+                main.wait_stream(self._side)
+
         if self.cached_eval is not None:
             with torch.no_grad():
                 values, logits = self.cached_eval(self._cache_bufs, self.t["states"], self.t["leaf_state"], self.t["leaf_parent"], self.extras,
                                                   after_trunk=fork_movegen if mode == "heads" else (fork_movegen_tail if mode == "tail" else None),
-                                                  before_trunk=mark_encoded if mode == "tail" else None, encoded=self._encoded)
+                                                  before_trunk=mark_encoded if mode == "tail" else None, encoded=self._encoded,
+                                                  search_buffers=bp if self.gather_policy else None, join_movegen=join_movegen)
         else:
             dt = 0 if self.feature_dtype == torch.float32 else 1
             _native.check(lib.trl_encode_features(self.t["states"].data_ptr(), self.t["leaf_state"].data_ptr(), self.G,
@@ -309,18 +316,23 @@ class SelfPlayEngine:
             with torch.no_grad():
                 values, logits = self.evaluator(self.grids, self.extras)
         values = values.reshape(-1)
-        if values.dtype != logits.dtype:
+        if values.dtype != logits.dtype and not (logits.dtype == torch.float32 and logits.shape[1] == self.moves_cap
+                                                  and values.dtype == torch.bfloat16 and self.cached_eval is not None):
             values = values.to(logits.dtype)
+        gathered = logits.dim() == 2 and logits.shape[1] == self.moves_cap and logits.dtype == torch.float32 and \
+            self.cached_eval is not None and self.gather_policy     # logits of the legal moves only (trl_search_policy_legal)
         if not (values.is_contiguous() and logits.dim() == 2 and logits.shape[0] == self.G and
-                logits.shape[1] >= POLICY_SIZE and logits.stride(1) == 1):
+                (gathered or logits.shape[1] >= POLICY_SIZE) and logits.stride(1) == 1):
             raise ValueError("evaluator must return contiguous values [G] and row-major logits [G, >=11583]")
         if logits.dtype not in (torch.float32, torch.bfloat16):
             raise ValueError("evaluator outputs must be float32 or bfloat16")
+        if gathered and values.dtype != torch.bfloat16:
+            raise ValueError("gathered logits come with bfloat16 values")
         self._values, self._logits = values, logits  # keep alive (graph-owned memory when captured)
         stamp(5, st)
         if self.overlap_movegen:
             main.wait_stream(self._side)
-        ldt = 0 if logits.dtype == torch.float32 else 1
+        ldt = 2 if gathered else (0 if logits.dtype == torch.float32 else 1)
         if self.fuse_encode:
             cb = self._cache_bufs
             _native.check(lib.trl_search_expand_select_encode(

@@ -244,39 +244,139 @@ def _check_threshold(wins, games, threshold, threshold_type):
     return None
 
 
+class DualCachedEvaluator:
+    """Engine evaluator of a gating battle: two networks, each with its cached-trunk evaluator (trunk.CachedTrunkEvaluator /
+    trunk_wide.CachedWideEvaluator).  Every leaf goes through ONE network, the one that owns the running search of its
+    game (ai.py:2012-2016): the queued board images are split into two compact lists (one per network), each trunk
+    writes its own feature cache, each heads kernel skips the other network's leaves.  Same engine contract as the
+    single-network evaluators, so the whole step stays inside the engine's CUDA graph."""
+
+    overlap_mode = "heads"
+    gather_policy = True
+
+    def __init__(self, cached_1, cached_2):
+        self.c = (cached_1, cached_2)
+        self.stamp = None
+        self.engine = None          # set by battle_networks: the owner of a search is read from the engine's games
+
+    def make_buffers(self, n_states, n_leaves, device, moves_cap=512):
+        b = self.c[0].make_buffers(n_states, n_leaves, device, moves_cap)        # shared: what the encoder writes
+        subs = []
+        for c in self.c:
+            sb = c.make_buffers(n_states, n_leaves, device, moves_cap)
+            sb["images"] = torch.zeros((2 * n_leaves + 1, sb["images"].shape[1]), dtype=torch.bfloat16, device=device)   # + trash row
+            sb["dest"] = torch.zeros(2 * n_leaves + 1, dtype=torch.int32, device=device)
+            sb["opp"] = b["opp"]                   # opponent rows are the same indices in either cache
+            subs.append(sb)
+        b["subs"] = subs
+        b["k"] = torch.arange(2 * n_leaves, device=device)
+        b["rows_per_game"] = 2 * (n_states // n_leaves)
+        return b
+
+    def encode(self, b, states, leaf_state, leaf_parent, extras):
+        self.c[0].encode(b, states, leaf_state, leaf_parent, extras)
+
+    def _owner_of_games(self):
+        from .state import GAME_DTYPE
+        eng = self.engine
+        g32 = eng.t["games"].view(torch.int32).view(eng.G, GAME_DTYPE.itemsize // 4)
+        gid = g32[:, GAME_DTYPE.fields["game_id"][1] // 4]
+        turn = eng.t["games"].view(eng.G, GAME_DTYPE.itemsize)[:, GAME_DTYPE.fields["turn"][1]].to(torch.int32)
+        return (gid ^ turn) & 1                     # 0: network 1 searches (it plays player game_id & 1)
+
+    def __call__(self, b, states, leaf_state, leaf_parent, extras, after_trunk=None, before_trunk=None, encoded=False,
+                 search_buffers=None, join_movegen=None):
+        G = leaf_state.numel()
+        if not encoded:
+            self.encode(b, states, leaf_state, leaf_parent, extras)
+        owner = self._owner_of_games()                                            # [G]
+        k, n2 = b["k"], 2 * G
+        valid = k < b["count"]
+        game_of = (b["dest"].clamp(min=0) // b["rows_per_game"]).clamp(max=G - 1).long()
+        owner_k = owner[game_of]
+        for i, sb in enumerate(b["subs"]):
+            m = valid & (owner_k == i)
+            tgt = torch.where(m, torch.cumsum(m, 0) - 1, torch.full_like(k, n2))  # others land in the trash row
+            sb["images"].index_copy_(0, tgt, b["images"])
+            sb["dest"].index_copy_(0, tgt, b["dest"])
+            sb["count"].copy_(m.sum().to(torch.int32).reshape(1))
+            sb["own"].copy_(torch.where(owner == i, b["own"], torch.full_like(b["own"], -1)))
+        b["count"].zero_()                          # consumed: the next step's encoder appends from zero
+        if before_trunk is not None:
+            before_trunk()
+        for c, sb in zip(self.c, b["subs"]):
+            c.trunk_step(sb, G)
+        if after_trunk is not None:
+            after_trunk()
+        outs = []
+        for c, sb in zip(self.c, b["subs"]):
+            v = c.heads_step(sb, extras, G)
+            outs.append((v.reshape(-1), c.policy(sb, search_buffers, join_movegen)))
+        use2 = owner.bool()
+        (v1, l1), (v2, l2) = outs
+        return torch.where(use2, v2, v1), torch.where(use2[:, None], l2, l1)
+
+
 def battle_networks(NN_1, config_1, NN_2, config_2, threshold, threshold_type, games,
-                    network_1_title="Network 1", network_2_title="Network 2", screen=None, seed=None):
-    """All `games` battles run concurrently on the GPU (the reference's batched variant,
-    ai.py:2071-2114: colours alternate by game index, no early termination, post-hoc threshold).
-    Every search is evaluated by the network that owns the side to move at the ROOT."""
+                    network_1_title="Network 1", network_2_title="Network 2", screen=None, seed=None,
+                    first_game_id=0, game_id_stride=1):
+    """All `games` battles run concurrently on the GPU (the reference's batched variant, ai.py:2071-2114: network 1
+    plays player (game index & 1), no early termination, post-hoc threshold).  Every search runs with the network AND
+    the search settings (config_1 / config_2) of the side to move at the root (ai.py:2012-2016); the two configs may
+    differ in anything but the ruleset.  No random opening plies (ai.py:1588-1608 is play_game only).
+    first_game_id / game_id_stride shard the battles over ranks (ids first, first + stride, ...)."""
     from .ai import _engine_for
     import copy
-    from .selfplay import best_evaluator
+    import ctypes
+    from . import _native
+    from .selfplay import best_evaluator, search_params_from_config
     if config_1.ruleset != config_2.ruleset:
         raise NotImplementedError("Ruleset's aren't equal")
-    keys = ("MAX_ITER", "CPUCT", "DPUCT", "FpuStrategy", "FpuValue", "use_root_softmax", "RootSoftmaxTemp", "use_tanh",
-            "training", "temperature")
-    if any(getattr(config_1, k) != getattr(config_2, k) for k in keys):
-        raise NotImplementedError("battle_networks on the device path needs identical search settings for both sides")
-    dev = torch.device("cuda")
-    ev1 = best_evaluator(copy.deepcopy(NN_1).to(dev), torch.bfloat16)
-    ev2 = best_evaluator(copy.deepcopy(NN_2).to(dev), torch.bfloat16)
-    side = (torch.arange(games, device=dev) % 2).to(torch.uint8)  # 0: NN_1 plays player 0
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def as_evaluator(nn_):
+        if callable(nn_) and not isinstance(nn_, torch.nn.Module):
+            return nn_
+        return best_evaluator(copy.deepcopy(nn_).to(dev), torch.bfloat16)
+
+    ev1, ev2 = as_evaluator(NN_1), as_evaluator(NN_2)
+    both_cached = getattr(ev1, "cached", None) is not None and getattr(ev2, "cached", None) is not None
     holder = {}
-
-    def evaluator(grids, extras):
-        v1, l1 = ev1(grids, extras)
-        v2, l2 = ev2(grids, extras)
-        turn = holder["engine"].t["games"].view(games, 400)[:, 384]
-        use2 = ((turn ^ side) & 1).bool()
-        return torch.where(use2, v2.reshape(-1), v1.reshape(-1)), torch.where(use2[:, None], l2, l1)
-
-    eng = _engine_for(config_1, evaluator, games, seed=seed, restart_finished=False)
-    holder["engine"] = eng
+    if both_cached:
+        evaluator = lambda grids, extras: ev1(grids, extras)      # noqa: E731  (never called: the engine uses .cached)
+        evaluator.cached = DualCachedEvaluator(ev1.cached, ev2.cached)
+        dtype = torch.bfloat16
+    else:
+        def evaluator(grids, extras):      # generic evaluators (tests, unsupported nets): both on every leaf, then select
+            v1, l1 = ev1(grids, extras)
+            v2, l2 = ev2(grids, extras)
+            use2 = evaluator.owner().bool()
+            return torch.where(use2, v2.reshape(-1), v1.reshape(-1)), torch.where(use2[:, None], l2, l1)
+        dtype = torch.bfloat16 if isinstance(NN_1, torch.nn.Module) else torch.float32
+    # the engine is sized for the larger of the two search budgets; the per-search settings come from params2
+    big = config_1 if max(config_1.playout_iterations()[0], config_1.MAX_ITER) >= max(config_2.playout_iterations()[0], config_2.MAX_ITER) \
+        else config_2
+    eng = _engine_for(big, evaluator, games, seed=seed, restart_finished=False, dtype=dtype, first_game_id=first_game_id,
+                      game_id_stride=game_id_stride)
+    if both_cached:
+        evaluator.cached.engine = eng
+    else:
+        helper = DualCachedEvaluator(None, None)
+        helper.engine = eng
+        evaluator.owner = helper._owner_of_games
+    pair = (_native.SearchParams * 2)(search_params_from_config(config_1, eng.seed, False, game_id_stride),
+                                      search_params_from_config(config_2, eng.seed, False, game_id_stride))
+    for p in pair:
+        p.seed = eng.seed
+    params2 = torch.frombuffer(bytearray(bytes(pair)), dtype=torch.uint8).to(dev)
+    eng.buf.params2 = params2.data_ptr()
+    holder["params2"] = params2
     ends = []
+    chunk = max(8, min(config_1.MAX_ITER, config_2.MAX_ITER))
     while eng.get_ctl()["active"].any():
-        eng.step(max(8, config_1.MAX_ITER))
+        eng.step(chunk)
         ends.extend(eng.drain()[1])
+        eng.check_status(ignore=0x20)        # sample records are not read here: a full sample ring is harmless
     wins = np.zeros(2, dtype=float)
     for e in ends:
         s = int(e["game_id"]) % 2

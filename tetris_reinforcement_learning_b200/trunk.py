@@ -184,19 +184,50 @@ class CachedTrunkEvaluator:
     through the trunk; the features of the other board are the parent state's.  Outputs are
     bit-identical to the plain fused evaluator (same kernels, same per-image arithmetic)."""
 
+    gather_policy = True   # policy head on the legal moves only (trl_search_policy_legal) instead of the dense GEMM
+
     def __init__(self, packed, w_heads, use_tanh, w_pol, b_pol, k_pad):
         self.packed, self.w_heads, self.use_tanh = packed, w_heads, use_tanh
         self.w_pol, self.b_pol, self.k_pad = w_pol, b_pol, k_pad
         self.stamp = None   # profiling hook (SelfPlayEngine.enable_timeline)
 
-    def make_buffers(self, n_states, n_leaves, device):
+    def make_buffers(self, n_states, n_leaves, device, moves_cap=512):
         """Per-ENGINE buffers (the engine owns them, so they are freed with it): the feature cache
         [n_states * 2, 400] and the per-step staging of images, indices, head inputs and values."""
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)  # noqa: E731
         return {"cache": z((n_states * 2, 400), torch.bfloat16), "images": z((2 * n_leaves, 400), torch.bfloat16),
                 "dest": z(2 * n_leaves, torch.int32), "count": z(1, torch.int32),
                 "own": z(n_leaves, torch.int32), "opp": z(n_leaves, torch.int32), "rowof": z(n_states * 2, torch.int32),
-                "x": z((n_leaves, self.k_pad), torch.bfloat16), "value": z(n_leaves, torch.bfloat16)}
+                "x": z((n_leaves, self.k_pad), torch.bfloat16), "value": z(n_leaves, torch.bfloat16),
+                "logits_legal": z((n_leaves, moves_cap), torch.float32)}
+
+    def policy(self, b, search_buffers=None, join_movegen=None):
+        """Policy logits of the leaves: gathered over the legal moves (fp32 [G, moves_cap]) when the engine hands in
+        its buffers, else the dense head [G, 11584]."""
+        if self.gather_policy and search_buffers is not None:
+            if join_movegen is not None:
+                join_movegen()      # the legal lists of this step come from the forked enumeration
+            _native.check(_native.lib().trl_search_policy_legal(
+                search_buffers, b["x"].data_ptr(), self.k_pad, self.w_pol.data_ptr(), self.b_pol.data_ptr(),
+                b["logits_legal"].data_ptr(), torch.cuda.current_stream(b["x"].device).cuda_stream), "trl_search_policy_legal")
+            return b["logits_legal"]
+        return torch.nn.functional.linear(b["x"], self.w_pol, self.b_pol)
+
+    def trunk_step(self, b, G):
+        """Trunk over the queued images b["images"][: b["count"]] -> cache rows b["dest"] (resets the count)."""
+        p = self.packed
+        _native.check(_native.lib().trl_alphasame_trunk_rows_indexed(
+            b["images"].data_ptr(), b["count"].data_ptr(), 2 * G, b["dest"].data_ptr(), p["n_blocks"],
+            p["w_packed"].data_ptr(), p["consts_host"].data_ptr(), p["stem_w"].data_ptr(), b["cache"].data_ptr(),
+            torch.cuda.current_stream(b["cache"].device).cuda_stream), "trl_alphasame_trunk_rows_indexed")
+
+    def heads_step(self, b, extras, G):
+        """Opponent summary, head input b["x"] and value b["value"] of the leaves whose b["own"] row is >= 0."""
+        _native.check(_native.lib().trl_alphasame_heads_indexed(
+            b["cache"].data_ptr(), b["own"].data_ptr(), b["opp"].data_ptr(), extras.data_ptr(), G,
+            self.w_heads.data_ptr(), self.use_tanh, b["x"].data_ptr(), b["value"].data_ptr(),
+            torch.cuda.current_stream(extras.device).cuda_stream), "trl_alphasame_heads_indexed")
+        return b["value"]
 
     def encode(self, b, states, leaf_state, leaf_parent, extras):
         """Feature encoding of the selected leaves (a separate kernel; the engine normally has it done by
@@ -207,9 +238,11 @@ class CachedTrunkEvaluator:
             b["images"].data_ptr(), b["dest"].data_ptr(), b["count"].data_ptr(), extras.data_ptr(),
             b["own"].data_ptr(), b["opp"].data_ptr(), b["rowof"].data_ptr(), st), "trl_encode_features_cached")
 
-    def __call__(self, b, states, leaf_state, leaf_parent, extras, after_trunk=None, before_trunk=None, encoded=False):
+    def __call__(self, b, states, leaf_state, leaf_parent, extras, after_trunk=None, before_trunk=None, encoded=False,
+                 search_buffers=None, join_movegen=None):
         """b: make_buffers(); states uint8 [n_states*400], leaf_state / leaf_parent int32 [G], extras bf16
-        [G,105] (written here unless `encoded`) -> (values bf16 [G], logits bf16 [G, 11584])."""
+        [G,105] (written here unless `encoded`) -> (values bf16 [G], logits: bf16 [G, 11584], or fp32
+        [G, moves_cap] over the legal moves when the engine passes its search buffers)."""
         lib = _native.lib()
         dev = extras.device
         G = leaf_state.numel()
@@ -220,17 +253,10 @@ class CachedTrunkEvaluator:
         stamp(2, st)
         if before_trunk is not None:
             before_trunk()
-        p = self.packed
-        _native.check(lib.trl_alphasame_trunk_rows_indexed(
-            b["images"].data_ptr(), b["count"].data_ptr(), 2 * G, b["dest"].data_ptr(), p["n_blocks"],
-            p["w_packed"].data_ptr(), p["consts_host"].data_ptr(), p["stem_w"].data_ptr(), b["cache"].data_ptr(), st),
-            "trl_alphasame_trunk_rows_indexed")
+        self.trunk_step(b, G)
         stamp(3, st)
         if after_trunk is not None:
             after_trunk()
-        _native.check(lib.trl_alphasame_heads_indexed(
-            b["cache"].data_ptr(), b["own"].data_ptr(), b["opp"].data_ptr(), extras.data_ptr(), G,
-            self.w_heads.data_ptr(), self.use_tanh, b["x"].data_ptr(), b["value"].data_ptr(), st),
-            "trl_alphasame_heads_indexed")
+        self.heads_step(b, extras, G)
         stamp(4, st)
-        return b["value"], torch.nn.functional.linear(b["x"], self.w_pol, self.b_pol)
+        return b["value"], self.policy(b, search_buffers, join_movegen)

@@ -11,7 +11,7 @@ import torch
 
 from . import _native
 from .architectures import CELLS, SIDE_FEATS, AlphaSame, BaseResNet
-from .trunk import _fold_bn, _fold_linear_bn
+from .trunk import CachedTrunkEvaluator, _fold_bn, _fold_linear_bn
 
 WIDTHS = (32, 64)
 
@@ -185,6 +185,16 @@ class BaseResNetHeads:
         self._pad = {}
 
     def __call__(self, own, opp, extras):
+        x = self.features(own, opp, extras)
+        return self.value(x), torch.nn.functional.linear(x, self.w_pol, self.b_pol)
+
+    def value(self, x):
+        F = torch.nn.functional
+        v = F.linear(torch.relu(F.linear(x, self.w_val, self.b_val)), self.w_val2, self.b_val2).reshape(-1)
+        return torch.tanh(v) if self.tanh else torch.sigmoid(v)
+
+    def features(self, own, opp, extras):
+        """-> head input [B, k_pad] (flattened collapsed own map, own pieces / scalars, colour, zero padding)."""
         F = torch.nn.functional
         b = extras.shape[0]
         own_x, opp_x, color = extras[:, :SIDE_FEATS], extras[:, SIDE_FEATS:2 * SIDE_FEATS], extras[:, 2 * SIDE_FEATS:]
@@ -194,10 +204,7 @@ class BaseResNetHeads:
         flat = torch.relu(own[:, :4 * CELLS].reshape(b, 4, CELLS) + film[:, :, None]).reshape(b, 4 * CELLS)
         if b not in self._pad:
             self._pad[b] = torch.zeros((b, self.k_pad - self.k_in), dtype=self.dtype, device=extras.device)
-        x = torch.cat([flat, own_x, color, self._pad[b]], dim=1)
-        v = F.linear(torch.relu(F.linear(x, self.w_val, self.b_val)), self.w_val2, self.b_val2).reshape(-1)
-        value = torch.tanh(v) if self.tanh else torch.sigmoid(v)
-        return value, F.linear(x, self.w_pol, self.b_pol)
+        return torch.cat([flat, own_x, color, self._pad[b]], dim=1)
 
 
 def make_wide_evaluator(net, dtype=torch.bfloat16):
@@ -230,7 +237,7 @@ def make_wide_evaluator(net, dtype=torch.bfloat16):
             _native.check(lib.trl_alphasame_heads_indexed(
                 b["cache"].data_ptr(), b["own"].data_ptr(), b["opp"].data_ptr(), extras.data_ptr(), G,
                 w_heads.data_ptr(), use_tanh, b["x"].data_ptr(), b["value"].data_ptr(), st), "trl_alphasame_heads_indexed")
-            return b["value"], torch.nn.functional.linear(b["x"], w_pol, b_pol)
+            return b["value"]
     else:
         heads = BaseResNetHeads(net, dtype)
         k_pad = heads.k_pad
@@ -244,11 +251,13 @@ def make_wide_evaluator(net, dtype=torch.bfloat16):
             # a skipped leaf (own row < 0) reads row 0: its outputs are ignored by the search kernel
             own = b["cache"].index_select(0, b["own"].clamp(min=0))
             opp = b["cache"].index_select(0, b["opp"].clamp(min=0))
-            return heads(own, opp, extras)
+            b["x"].copy_(heads.features(own, opp, extras))
+            return heads.value(b["x"])
+        w_pol, b_pol = heads.w_pol, heads.b_pol
 
     evaluate.packed = wt.p
     evaluate.trunk = wt
-    evaluate.cached = CachedWideEvaluator(wt, heads_indexed, k_pad)
+    evaluate.cached = CachedWideEvaluator(wt, heads_indexed, k_pad, w_pol, b_pol)
     return evaluate
 
 
@@ -257,17 +266,28 @@ class CachedWideEvaluator:
     per simulation only the board the last move changed goes through the trunk (exact, include/trl.h)."""
 
     overlap_mode = "heads"     # the leaf enumeration is forked after the trunk (its CTAs own the SMs)
+    gather_policy = True       # policy head on the legal moves only (trl_search_policy_legal)
 
-    def __init__(self, wide_trunk, heads_indexed, k_pad):
+    def __init__(self, wide_trunk, heads_indexed, k_pad, w_pol, b_pol):
         self.trunk, self.heads_indexed, self.k_pad = wide_trunk, heads_indexed, k_pad
+        self.w_pol, self.b_pol = w_pol, b_pol
         self.stamp = None
 
-    def make_buffers(self, n_states, n_leaves, device):
+    policy = CachedTrunkEvaluator.policy
+
+    def make_buffers(self, n_states, n_leaves, device, moves_cap=512):
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)  # noqa: E731
         return {"cache": z((n_states * 2, self.trunk.row_elems), torch.bfloat16), "images": z((2 * n_leaves, CELLS), torch.bfloat16),
                 "dest": z(2 * n_leaves, torch.int32), "count": z(1, torch.int32),
                 "own": z(n_leaves, torch.int32), "opp": z(n_leaves, torch.int32), "rowof": z(n_states * 2, torch.int32),
-                "x": z((n_leaves, self.k_pad), torch.bfloat16), "value": z(n_leaves, torch.bfloat16)}
+                "x": z((n_leaves, self.k_pad), torch.bfloat16), "value": z(n_leaves, torch.bfloat16),
+                "logits_legal": z((n_leaves, moves_cap), torch.float32)}
+
+    def trunk_step(self, b, G):
+        self.trunk(b["images"], b["cache"], n_images=2 * G, n_images_dev=b["count"], out_row=b["dest"], pdl=True)
+
+    def heads_step(self, b, extras, G):
+        return self.heads_indexed(b, extras, G, torch.cuda.current_stream(extras.device).cuda_stream)
 
     def encode(self, b, states, leaf_state, leaf_parent, extras):
         st = torch.cuda.current_stream(extras.device).cuda_stream
@@ -276,7 +296,8 @@ class CachedWideEvaluator:
             b["images"].data_ptr(), b["dest"].data_ptr(), b["count"].data_ptr(), extras.data_ptr(),
             b["own"].data_ptr(), b["opp"].data_ptr(), b["rowof"].data_ptr(), st), "trl_encode_features_cached")
 
-    def __call__(self, b, states, leaf_state, leaf_parent, extras, after_trunk=None, before_trunk=None, encoded=False):
+    def __call__(self, b, states, leaf_state, leaf_parent, extras, after_trunk=None, before_trunk=None, encoded=False,
+                 search_buffers=None, join_movegen=None):
         G = leaf_state.numel()
         st = torch.cuda.current_stream(extras.device).cuda_stream
         if not encoded:
@@ -285,10 +306,10 @@ class CachedWideEvaluator:
         stamp(2, st)
         if before_trunk is not None:
             before_trunk()
-        self.trunk(b["images"], b["cache"], n_images=2 * G, n_images_dev=b["count"], out_row=b["dest"], pdl=True)
+        self.trunk_step(b, G)
         stamp(3, st)
         if after_trunk is not None:
             after_trunk()
-        out = self.heads_indexed(b, extras, G, st)
+        value = self.heads_step(b, extras, G)
         stamp(4, st)
-        return out
+        return value, self.policy(b, search_buffers, join_movegen)

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--games", type=int, default=256, help="self-play games per GPU")
     ap.add_argument("--battle-games", type=int, default=64, help="gating games per GPU")
     ap.add_argument("--batch-size", type=int, default=64)
+    ap.add_argument("--train-samples", type=int, default=0, help="cap on the samples per rank used for the training step (0 = all)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -48,7 +49,7 @@ def main():
 
     # ---- self-play: independent shards ----
     t0 = time.perf_counter()
-    data, stats = ai.generate_games(cfg, best, args.games, seed=20261018, first_game_id=rank, game_id_stride=world)
+    data, stats = ai.generate_games(cfg, best, args.games, seed=20261018, first_game_id=rank, game_id_stride=world, compact=True)
     torch.cuda.synchronize()
     t_play = time.perf_counter() - t0
 
@@ -57,8 +58,12 @@ def main():
     if world > 1:
         dist.all_reduce(n, op=dist.ReduceOp.MIN)
     n_common = int(n.item()) // args.batch_size * args.batch_size
+    if args.train_samples:
+        n_common = min(n_common, args.train_samples // args.batch_size * args.batch_size)
+    mem_play = torch.cuda.max_memory_allocated()
     t0 = time.perf_counter()
-    losses = training.train_network_pytorch(cfg, challenger, data[:n_common], log=False) if n_common else {}
+    import numpy as np
+    losses = training.train_network_pytorch(cfg, challenger, training._CompactSelection(data, np.arange(n_common)), log=False) if n_common else {}
     torch.cuda.synchronize()
     t_train = time.perf_counter() - t0
     flat = torch.cat([p.detach().reshape(-1).float() for p in challenger.parameters()])
@@ -74,7 +79,7 @@ def main():
     gate_cfg.training = False
     t0 = time.perf_counter()
     wins, _ = training.battle_networks(challenger.eval(), gate_cfg, best, gate_cfg, None, "moreorequal", args.battle_games,
-                                       seed=7 + rank)
+                                       seed=7, first_game_id=rank, game_id_stride=world)
     t_gate = time.perf_counter() - t0
     w = torch.tensor(wins, device="cuda", dtype=torch.float64)
     tot = torch.tensor([float(len(data)), float(args.games), t_play, t_train, t_gate], device="cuda", dtype=torch.float64)
@@ -95,7 +100,8 @@ def main():
             "replica_weight_spread_after_allreduce_training": float(spread.item()),
             "gating": {"games": total_games, "challenger_wins": float(w[0]), "best_wins": float(w[1]), "accepted": accepted,
                        "seconds": t_gate},
-            "params": int(flat.numel())}))
+            "params": int(flat.numel()),
+            "hbm_peak_bytes_selfplay_rank0": int(mem_play), "hbm_peak_bytes_total_rank0": int(torch.cuda.max_memory_allocated())}))
     if world > 1:
         dist.destroy_process_group()
 
