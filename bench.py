@@ -260,9 +260,9 @@ def run_selfplay(args, rank, world, local_rank):
     G = args.games
     sh = shard_for_rank(rank, world, G)
 
-    def engine(max_iter, n_games=G, forced=None, evaluator=None, model_config=None, **kw):
+    def engine(max_iter, n_games=G, forced=None, evaluator=None, model_config=None, playout_cap=False, **kw):
         cfg = Config(visual=False, ruleset="s2", model="pytorch", model_config=model_config or mc, MAX_ITER=max_iter, CPUCT=0.75,
-                     training=True, use_playout_cap_randomization=False, use_dirichlet_noise=True, FpuStrategy="reduction",
+                     training=True, use_playout_cap_randomization=playout_cap, use_dirichlet_noise=True, FpuStrategy="reduction",
                      use_forced_playouts_and_policy_target_pruning=args.forced if forced is None else forced)
         return SelfPlayEngine(cfg, evaluator or ev, n_games, device=dev, seed=20261018, first_game_id=sh["first_game_id"],
                               game_id_stride=sh["game_id_stride"], feature_dtype=torch.bfloat16, **kw)
@@ -282,7 +282,7 @@ def run_selfplay(args, rank, world, local_rank):
             dist.barrier()
         return e0.elapsed_time(e1)
 
-    def extra_leg(name, steps, max_iter, forced=False, net_cfg=None, what=""):
+    def extra_leg(name, steps, max_iter, forced=False, net_cfg=None, what="", playout_cap=False):
         """One more sims/s line: same games per GPU, another search setting or another network; max over ranks."""
         evaluator, flops_board, net_name = None, 37.2e6 / 2, "AlphaSame(blocks=10, filters=16)"
         if net_cfg is not None:
@@ -293,9 +293,14 @@ def run_selfplay(args, rank, world, local_rank):
             stem = 25 if isinstance(net_cfg, arch.AlphaSameConfig) else 9
             flops_board = 2.0 * 400 * (stem * f + 2 * b * 9 * f * f)
             net_name = f"{type(wide_net).__name__}(blocks={b}, filters={f})"
-        e = engine(max_iter, forced=forced, evaluator=evaluator, model_config=net_cfg)
+        torch.cuda.reset_peak_memory_stats(dev)
+        mem0 = torch.cuda.memory_allocated(dev)
+        e = engine(max_iter, forced=forced, evaluator=evaluator, model_config=net_cfg, playout_cap=playout_cap)
         fused = e.cached_eval is not None
+        arena = {"node_cap_per_game": e.node_cap, "state_cap_per_game": e.state_cap,
+                 "tree_bytes": int(sum(e.t[k].numel() * e.t[k].element_size() for k in ("prior", "value_sum", "visits", "parent", "slot", "move")))}
         t = timed(e, steps)
+        arena["hbm_peak_bytes_engine"] = int(torch.cuda.max_memory_allocated(dev) - mem0)
         st = e.get_ctl()["status"]
         if evaluator is not None and hasattr(evaluator, "trunk"):
             evaluator.trunk.check()
@@ -308,7 +313,8 @@ def run_selfplay(args, rank, world, local_rank):
         v = G * world * steps / (t * 1e-3)
         return {"what": what, "value": v, "unit": "sims/s", "games_per_gpu": G, "n_gpus": world, "steps": steps, "max_iter": max_iter,
                 "ms_per_step": t / steps, "net": net_name + " bf16, random init", "fused_trunk": fused,
-                "forced_playouts_and_pruning": bool(forced), "status_nonzero_rank0": int((st != 0).sum()),
+                "forced_playouts_and_pruning": bool(forced), "playout_cap_randomization": bool(playout_cap),
+                "status_nonzero_rank0": int((st != 0).sum()), "memory": arena,
                 "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": load_tensor_peak(),
                              "achieved": v / world * flops_board / 1e12, "frac": v / world * flops_board / 1e12 / load_tensor_peak(),
                              "flops_counted": "trunk convolutions of ONE board per simulation (trunk-feature reuse); heads and policy "
@@ -382,9 +388,10 @@ def run_selfplay(args, rank, world, local_rank):
                  "count the driver runs (weak scaling)")
     if not args.no_wide:
         extra["config5_net"] = extra_leg(
-            "config5", 48, 800, net_cfg=arch.AlphaSameConfig(blocks=20, filters=64),
-            what="BASELINE config 5's network and search budget in the self-play engine: AlphaSame(20, 64), MAX_ITER=800, through "
-                 "csrc/trunk_wide.cu (through PyTorch / cuDNN the same step took 51 ms in round 1)")
+            "config5", 48, 800, net_cfg=arch.AlphaSameConfig(blocks=20, filters=64), playout_cap=True,
+            what="BASELINE config 5's network and search budget in the self-play engine: AlphaSame(20, 64), MAX_ITER=800 with playout-cap "
+                 "randomisation (searches of 2000 / 400 iterations: the node arena is sized for 2000), through csrc/trunk_wide.cu "
+                 "(through PyTorch / cuDNN the same step took 51 ms in round 1)")
         extra["config_default_net"] = extra_leg(
             "default", 96, 400, net_cfg=arch.AuxBaseResNetConfig(),
             what="the reference's Config default (ai.py:83): AuxBaseResNet(8, 32), MAX_ITER=400, through csrc/trunk_wide.cu "

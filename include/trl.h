@@ -404,7 +404,7 @@ int trl_search_expand_select_encode(const TrlSearchBuffers* buf, const TrlSearch
  * those: logits_legal[g][c] = bias[m] + x[g] . w[m] for the c-th legal move m of game g's selected leaf (this
  * step's enumeration, or the list cached under the parent state), fp32.  Run it after trl_search_movegen and before
  * trl_search_expand*, and pass logits_legal to expand with dtype = 2 and logits_stride = moves_cap (values bf16).
- * x [n_games][k_pad] bf16 (k_pad % 8 == 0), w [>= 11583][k_pad] bf16 row-major, bias [>= 11583] bf16,
+ * x [n_games][k_pad] bf16 (k_pad % 16 == 0), w [>= 11583][k_pad] bf16 row-major, bias [>= 11583] bf16,
  * logits_legal [n_games][moves_cap] f32.
  */
 int trl_search_policy_legal(const TrlSearchBuffers* buf, const void* x_bf16, int k_pad, const void* w_bf16,

@@ -116,7 +116,8 @@ def test_trunk_feature_reuse_is_exact():
     cfg = Config(visual=False, ruleset="s2", model="pytorch", model_config=arch.AlphaSameConfig(), MAX_ITER=12, training=True)
     out = []
     for reuse in (True, False):
-        eng = SelfPlayEngine(cfg, ev, 96, seed=3, feature_dtype=torch.bfloat16, max_rounds=4, reuse_trunk_features=reuse)
+        eng = SelfPlayEngine(cfg, ev, 96, seed=3, feature_dtype=torch.bfloat16, max_rounds=4, reuse_trunk_features=reuse,
+                             gather_policy=False)   # same dense bf16 policy head on both sides: the comparison is about the trunk
         assert (eng.cached_eval is not None) == reuse
         eng.step(400)
         samples, ends = eng.drain()

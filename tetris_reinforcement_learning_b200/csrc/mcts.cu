@@ -704,6 +704,16 @@ search_expand_select_encode_kernel(TrlSearchBuffers B, TrlSearchParams P, const 
 // entries: logit[c] = bias[m_c] + x . W[m_c] for the leaf's legal list (this step's enumeration or the list cached
 // under the parent state, the same lookup as expand_body), fp32 accumulation, fp32 out [G][moves_cap].  The weight
 // matrix (12-38 MB) stays L2 resident; no [G, 11584] tensor exists.
+__device__ __forceinline__ void mma_bf16_16x8x16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// One warp per leaf.  The gathered weight rows are the A operand of warp-level MMAs (16 legal moves x 16 inputs per
+// instruction), x is broadcast into all eight B columns, so column 0 of D holds the logits; a dot product does not care
+// about the order of its terms, so the K slots of a fragment are mapped to memory such that every lane reads 16
+// contiguous bytes of its two rows per pair of MMAs.  (A CUDA-core version spent 85 instructions per move on
+// unpacking bf16 pairs; this one spends 6.)
 __global__ void __launch_bounds__(256)
 policy_legal_kernel(TrlSearchBuffers B, const __nv_bfloat16* __restrict__ x, int k_pad, const __nv_bfloat16* __restrict__ w,
                     const __nv_bfloat16* __restrict__ bias, float* __restrict__ out) {
@@ -723,35 +733,34 @@ policy_legal_kernel(TrlSearchBuffers B, const __nv_bfloat16* __restrict__ x, int
         if (cached >= 0) { mv = B.legal_cache + pstate * (size_t)B.moves_cap; C = cached; }
     }
     if (C > B.moves_cap) C = B.moves_cap;
+    if (C <= 0) return;
     const int chunks = k_pad >> 3;                        // 16-byte pieces of a row
     uint4* sx = s_x + wib * chunks;
     const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)g * k_pad);
     for (int c = lane; c < chunks; c += 32) sx[c] = xr[c];
     __syncwarp();
     float* o = out + (size_t)g * B.moves_cap;
-    for (int c0 = 0; c0 < C; c0 += 2) {                   // two moves per pass: their loads overlap
-        const int m0 = mv[c0], m1 = (c0 + 1 < C) ? mv[c0 + 1] : m0;
+    const int grp = lane >> 2, tig = lane & 3;
+    for (int t0 = 0; t0 < C; t0 += 16) {
+        const int r0 = min(t0 + grp, C - 1), r1 = min(t0 + grp + 8, C - 1);      // rows past the list repeat the last move
+        const int m0 = mv[r0], m1 = mv[r1];
         const uint4* w0 = reinterpret_cast<const uint4*>(w + (size_t)m0 * k_pad);
         const uint4* w1 = reinterpret_cast<const uint4*>(w + (size_t)m1 * k_pad);
-        float a0 = 0.f, a1 = 0.f;
-        for (int c = lane; c < chunks; c += 32) {
-            const uint4 xv = sx[c], u = __ldg(w0 + c), v = __ldg(w1 + c);
-            const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, us[4] = {u.x, u.y, u.z, u.w}, vs[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float xl = __uint_as_float(xs[q] << 16), xh = __uint_as_float(xs[q] & 0xFFFF0000u);
-                a0 = fmaf(xl, __uint_as_float(us[q] << 16), a0); a0 = fmaf(xh, __uint_as_float(us[q] & 0xFFFF0000u), a0);
-                a1 = fmaf(xl, __uint_as_float(vs[q] << 16), a1); a1 = fmaf(xh, __uint_as_float(vs[q] & 0xFFFF0000u), a1);
-            }
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        int kc = 0;                                       // in 16-byte chunks
+        for (; kc + 4 <= chunks; kc += 4) {               // 32 inputs: two MMAs from one 16-byte load per row
+            const uint4 u = __ldg(w0 + kc + tig), v = __ldg(w1 + kc + tig), xv = sx[kc + tig];
+            mma_bf16_16x8x16(d, u.x, v.x, u.y, v.y, xv.x, xv.y);
+            mma_bf16_16x8x16(d, u.z, v.z, u.w, v.w, xv.z, xv.w);
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            a0 += __shfl_xor_sync(kFull, a0, off);
-            a1 += __shfl_xor_sync(kFull, a1, off);
+        if (kc + 2 <= chunks) {                           // 16 more inputs: 8 bytes per lane
+            const uint2 u = __ldg(reinterpret_cast<const uint2*>(w0 + kc) + tig), v = __ldg(reinterpret_cast<const uint2*>(w1 + kc) + tig);
+            const uint2 xv = reinterpret_cast<const uint2*>(sx + kc)[tig];
+            mma_bf16_16x8x16(d, u.x, v.x, u.y, v.y, xv.x, xv.y);
         }
-        if (lane == 0) {
-            o[c0] = a0 + __bfloat162float(bias[m0]);
-            if (c0 + 1 < C) o[c0 + 1] = a1 + __bfloat162float(bias[m1]);
+        if (tig == 0) {                                   // column 0 of D: rows grp and grp + 8
+            if (t0 + grp < C) o[t0 + grp] = d[0] + __bfloat162float(bias[m0]);
+            if (t0 + grp + 8 < C) o[t0 + grp + 8] = d[2] + __bfloat162float(bias[m1]);
         }
     }
 }
@@ -761,7 +770,7 @@ policy_legal_kernel(TrlSearchBuffers B, const __nv_bfloat16* __restrict__ x, int
 extern "C" int trl_search_policy_legal(const TrlSearchBuffers* buf, const void* x_bf16, int k_pad, const void* w_bf16,
                                        const void* bias_bf16, float* logits_legal, void* stream) {
     if (!buf || buf->n_games < 0 || !buf->ctl || !buf->legal || !buf->n_legal || !x_bf16 || !w_bf16 || !bias_bf16 || !logits_legal ||
-        k_pad <= 0 || (k_pad & 7))
+        k_pad <= 0 || (k_pad & 15))
         return TRL_E_ARG;
     if (buf->n_games == 0) return TRL_OK;
     const size_t smem = (size_t)8 * (k_pad / 8) * sizeof(uint4);

@@ -169,6 +169,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&d)[16]) {
     for (int i = 0; i < 16; ++i) d[i] = __uint_as_float(r[i]);
 }
 
+// issue only: the registers are valid after tmem_wait_ld()
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};\n"
@@ -459,6 +469,10 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_wide_kernel(const __grid_co
                 }
             }
             // ---- layers ----
+            // An output column is published (fence.proxy.async + arrival on col_ready) when this warp has been woken for
+            // its NEXT column: by then the stores are old and the fence does not wait for them.  The next column's
+            // out_done never depends on the pending publication (it needs inputs of earlier columns only).
+            uint32_t pending_bar = 0u;
             for (int l = 0; l < L; ++l) {
                 const bool conv2 = (l & 1) != 0;
                 const bool last = (l == L - 1);
@@ -471,10 +485,12 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_wide_kernel(const __grid_co
                         const int r = q % G::kSlots;
                         const size_t off0 = ((size_t)(c * G::kKc) * kRowsBuf + slot + 1) * 16;
                         mbar_wait(out_done(r), (q / G::kSlots) & 1, kTagOutDone, q, status);
+                        if (pending_bar) { publish_global(pending_bar); pending_bar = 0u; }
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         float hacc[NOUT];
 #pragma unroll
                         for (int o = 0; o < NOUT; ++o) hacc[o] = 0.f;
+                        uint32_t acc_raw[2][16];     // two 16-channel chunks of the accumulator in flight per wait
 #pragma unroll
                         for (int ch = 0; ch < F / 16; ++ch) {
                             const size_t off = off0 + (size_t)(2 * ch) * kPlaneBytes;
@@ -485,8 +501,15 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_wide_kernel(const __grid_co
                             }
                             float d[16], kb[16];
                             const uint32_t ta = tmem_lane + (uint32_t)(r * F + 16 * ch);
-                            tmem_ld16(ta, d);
-                            tmem_st16_zero(ta);
+                            if (!(ch & 1)) {
+                                tmem_ld16_issue(ta, acc_raw[0]);
+                                tmem_ld16_issue(ta + 16u, acc_raw[1]);
+                                tmem_wait_ld();
+                                tmem_st16_zero(ta);
+                                tmem_st16_zero(ta + 16u);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) d[i] = __uint_as_float(acc_raw[ch & 1][i]);
                             load16g(cl + 16 * ch, kb);
 #pragma unroll
                             for (int i = 0; i < 16; ++i) d[i] += kb[i];
@@ -532,7 +555,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_wide_kernel(const __grid_co
                         __syncwarp();
                         if (lane == 0) mbar_arrive(out_free(r));
                         if (!last) {
-                            publish_global(col_ready(ln, c));
+                            pending_bar = col_ready(ln, c);
                         } else if (inside[ln]) {
                             const int orow = a.out_row ? a.out_row[img[ln]] : img[ln];
 #pragma unroll
@@ -545,6 +568,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_wide_kernel(const __grid_co
                     }
                 }
             }
+            if (pending_bar) publish_global(pending_bar);   // (none is left: the last layer publishes nothing)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         }
         __syncthreads();
