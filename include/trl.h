@@ -182,6 +182,13 @@ int trl_movegen_host_compact(const uint16_t* boards, const uint8_t* cur, const u
  * bit-identical outputs; the choice only trades latency against throughput. */
 void trl_movegen_select_kernel(int kernel);
 
+/* Form of the warp-cooperative kernel (csrc/movegen_warp.cu): 0 = two warps per call, one per piece
+ * type (lowest latency: the few-thousand-call batches of a self-play step), 1 = one warp per call,
+ * both piece searches back to back (highest throughput: no warp ever waits for another; the
+ * multi-million-call sweeps of move_generation.py:752-789), -1 = by batch size (default).
+ * Bit-identical outputs. */
+void trl_movegen_warp_form(int form);
+
 /* ------------------------------------------------------------------------------------ */
 /* env step                                                                              */
 /* replaces Game.make_move(move, add_bag, add_history=False)                             */

@@ -14,13 +14,20 @@ from tetris_reinforcement_learning_b200.state import (GAME_DTYPE, STEPOUT_DTYPE,
                                                       rows_to_grid, unpack_mask)
 
 
-@pytest.fixture(scope="module", params=["warp", "thread"])
+@pytest.fixture(scope="module", params=["warp", "solo", "fifo", "thread"])
 def mg(request):
-    """move_generation with one of the two bit-exact kernels forced (csrc/movegen_warp.cu, csrc/movegen.cu)."""
+    """move_generation with one of the bit-exact kernels forced: csrc/movegen_warp.cu in its two forms (two
+    warps per call / one warp per call), the same with the row-parallel closure search switched off (every
+    search through the exact FIFO form), and csrc/movegen.cu (one thread per call)."""
     from tetris_reinforcement_learning_b200 import _native, move_generation
-    _native.lib().trl_movegen_select_kernel(1 if request.param == "warp" else 0)
+    L = _native.lib()
+    L.trl_movegen_select_kernel(0 if request.param == "thread" else 1)
+    L.trl_movegen_warp_form({"warp": 0, "solo": 1, "fifo": -1, "thread": -1}[request.param])
+    assert L.trl_debug_movegen_fast_path(0 if request.param == "fifo" else 1) == 0
     yield move_generation
-    _native.lib().trl_movegen_select_kernel(-1)
+    L.trl_movegen_select_kernel(-1)
+    L.trl_movegen_warp_form(-1)
+    assert L.trl_debug_movegen_fast_path(1) == 0
 
 
 @pytest.fixture(scope="module")
@@ -116,8 +123,10 @@ def test_movegen_kernels_agree_on_adversarial_boards():
     d_c, d_a = torch.from_numpy(cur).to(dev), torch.from_numpy(alt).to(dev)
     outs = []
     try:
-        for kernel in (0, 1):
+        for kernel, form, fast in ((0, -1, 1), (1, 0, 1), (1, 1, 1), (1, -1, 0)):
             _native.lib().trl_movegen_select_kernel(kernel)
+            _native.lib().trl_movegen_warp_form(form)
+            assert _native.lib().trl_debug_movegen_fast_path(fast) == 0
             mask = torch.zeros((cur.size, MASK_WORDS), dtype=torch.int32, device=dev)
             n = torch.zeros(cur.size, dtype=torch.int16, device=dev)
             st = torch.zeros(cur.size, dtype=torch.int32, device=dev)
@@ -126,10 +135,14 @@ def test_movegen_kernels_agree_on_adversarial_boards():
             outs.append((mask, n, st))
     finally:
         _native.lib().trl_movegen_select_kernel(-1)
-    assert int((outs[0][2] != 0).sum()) == 0 and int((outs[1][2] != 0).sum()) == 0
-    assert torch.equal(outs[0][1], outs[1][1])
-    diff = (outs[0][0] != outs[1][0]).any(dim=1)
-    assert int(diff.sum()) == 0, f"{int(diff.sum())} calls differ, first {torch.nonzero(diff)[:5].flatten().tolist()}"
+        _native.lib().trl_movegen_warp_form(-1)
+        _native.lib().trl_debug_movegen_fast_path(1)
+    for o in outs:
+        assert int((o[2] != 0).sum()) == 0
+    for o in outs[1:]:
+        assert torch.equal(outs[0][1], o[1])
+        diff = (outs[0][0] != o[0]).any(dim=1)
+        assert int(diff.sum()) == 0, f"{int(diff.sum())} calls differ, first {torch.nonzero(diff)[:5].flatten().tolist()}"
     t_planes = outs[1][0][:, (23 * 39 * 11) // 32:].ne(0).any(dim=1)   # used-last-kick planes 23..26 are exercised
     assert int(t_planes.sum()) > 1000
 

@@ -84,8 +84,206 @@ __device__ __forceinline__ void flag_cell(uint32_t* fu_row, uint32_t bit, bool u
     else { atomicOr(fu_row, bit); atomicAnd(fu_row, ~(bit << 16)); }
 }
 
+// ---------------------------------------------------------------------------------------
+// Row-parallel closure search (the common case; search_piece_warp below is the exact general form).
+//
+// Everything the reference's FIFO exploration computes is a closure that does not depend on queue order
+//  — except which used-last-kick flag the LAST rotation-flagged emission of a T cell
+// carried.  So the search is run as a fix point on register-resident bit planes, lane = validity row
+// (rows 12..43; the spawn row is >= 19 and nothing above it can be entered without kicks):
+//
+//   * two rotations share a register (16 bits each, validity rows are 14 bits wide, the two spare bits
+//     stop the carries of hflood): VA/VB validity, RA/RB reached;
+//   * fill = alternate "expand along rows" (hflood, O(1)) and "fall straight down" (a segmented
+//     Hillis-Steele OR-scan over lanes, 5 shuffles, propagate masks precomputed) until nothing changes —
+//     all four rotations at once, instead of one serial row scan per queue entry;
+//   * kicks are evaluated only for edge cells reached since the previous round (move_generation.py:
+//     427-483: first valid kick wins, lane = row, bit = column, one shift/AND per kick); targets are
+//     OR-ed into per-rotation arrival planes in shared memory (for T split by the used-last-kick flag)
+//     and become the seeds of the next round's fill;
+//   * placed = reached & stuck; T: flagged = arrived & placed (every kick arrival at a stuck cell is a
+//     flagged emission, either at its pop, :384-394, or at once, :471-479).
+//
+// Returns false — and the caller runs the exact FIFO search instead — in the two cases this form cannot
+// decide: (i) a T cell received arrivals with BOTH flag values (then the order of emissions matters,
+// :671-677), (ii) something reached the two top rows of the window (a climb of more than five rows by
+// kicks; rows above the window are not represented).  Both are rare (counted in g_fast_fallbacks).
+// ---------------------------------------------------------------------------------------
+constexpr int kWin0 = 12;   // validity row of lane 0
+__constant__ int c_fast_path = 1;                 // trl_debug_movegen_fast_path(0) forces the FIFO form (tests run both)
+__device__ unsigned long long g_fast_stats[2];    // searches answered by the closure form / handed to the FIFO form
+
+__device__ __forceinline__ uint32_t shfl_up0(uint32_t x, int d, int lane) {   // lane < d receives 0
+    const uint32_t t = __shfl_up_sync(0xffffffffu, x, d);
+    return lane >= d ? t : 0u;
+}
+
+// R closed under "move one row down while the target is valid": P1..P16 are the propagate masks of
+// window lengths 1, 2, 4, 8, 16 ending at this lane's row (zero where the window leaves the lane range).
+__device__ __forceinline__ uint32_t fall_scan(uint32_t R, uint32_t P1, uint32_t P2, uint32_t P4, uint32_t P8, uint32_t P16) {
+    R |= __shfl_up_sync(0xffffffffu, R, 1) & P1;
+    R |= __shfl_up_sync(0xffffffffu, R, 2) & P2;
+    R |= __shfl_up_sync(0xffffffffu, R, 4) & P4;
+    R |= __shfl_up_sync(0xffffffffu, R, 8) & P8;
+    R |= __shfl_up_sync(0xffffffffu, R, 16) & P16;
+    return R;
+}
+
+__device__ __noinline__ bool search_piece_rows(PieceState& S, const uint16_t* rows, int type, bool via_hold, uint32_t* mask) {
+    const int lane = threadIdx.x & 31;
+    uint32_t minos[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) minos[r] = c_minos[type][r];
+    const int sx = trl_spawn_x(type);
+    if (via_hold && !trl_fits(rows, minos[0], sx, TRL_SPAWN_Y)) return true;   // player.py:37-44: no moves for this type
+
+    // validity rows of the four rotations for this lane's row (move_generation.py:490-528)
+    const int my = lane + kWin0;
+    uint32_t e[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) e[k] = trl_empty_row(rows, my - 2 + k) << 2;
+    uint32_t v[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        uint32_t acc = 0x3FFFu;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const uint32_t co = (minos[r] >> (8 * m)) & 15u, ro = (minos[r] >> (8 * m + 4)) & 15u;
+            const uint32_t ek = ro == 0 ? e[0] : (ro == 1 ? e[1] : (ro == 2 ? e[2] : e[3]));
+            acc &= ek >> co;
+        }
+        v[r] = acc;
+    }
+    // _set_starting_position (move_generation.py:164-180)
+    int hi = TRL_ROWS;
+    for (int i = lane; i < TRL_ROWS; i += 32)
+        if (rows[i] & TRL_FULL_ROW) hi = min(hi, i);
+    hi = __reduce_min_sync(0xffffffffu, hi);
+    const int slane = max(hi - (int)c_matrix_size[type], TRL_SPAWN_Y) + 2 - kWin0;   // 7..28
+    const uint32_t vs = __shfl_sync(0xffffffffu, v[0], slane);
+    if (!((vs >> (sx + 2)) & 1u)) return true;                                   // :351-352
+
+    const bool is_T = (type == P_T);
+    const uint32_t VA = v[0] | (v[1] << 16), VB = v[2] | (v[3] << 16);
+    // shared planes, row index lane + 2 (two zero rows either side): validity << 2 for the kick tests, arrivals
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        S.vv[r][lane + 2] = v[r] << 2;
+        S.fu[r][lane + 2] = 0u;
+        if (lane < 4) {
+            const int pad = lane < 2 ? lane : lane + 32;
+            S.vv[r][pad] = 0u;
+            S.fu[r][pad] = 0u;
+        }
+    }
+    // propagate masks of the fall scan
+    const uint32_t PA1 = lane >= 1 ? VA : 0u, PB1 = lane >= 1 ? VB : 0u;
+    const uint32_t PA2 = PA1 & shfl_up0(PA1, 1, lane) & (lane >= 2 ? ~0u : 0u), PB2 = PB1 & shfl_up0(PB1, 1, lane) & (lane >= 2 ? ~0u : 0u);
+    const uint32_t PA4 = PA2 & shfl_up0(PA2, 2, lane) & (lane >= 4 ? ~0u : 0u), PB4 = PB2 & shfl_up0(PB2, 2, lane) & (lane >= 4 ? ~0u : 0u);
+    const uint32_t PA8 = PA4 & shfl_up0(PA4, 4, lane) & (lane >= 8 ? ~0u : 0u), PB8 = PB4 & shfl_up0(PB4, 4, lane) & (lane >= 8 ? ~0u : 0u);
+    const uint32_t PA16 = PA8 & shfl_up0(PA8, 8, lane) & (lane >= 16 ? ~0u : 0u), PB16 = PB8 & shfl_up0(PB8, 8, lane) & (lane >= 16 ? ~0u : 0u);
+    // cells whose three neighbours (below, left, right) are all valid are no edge cells (:427-429)
+    uint32_t dA = __shfl_down_sync(0xffffffffu, VA, 1), dB = __shfl_down_sync(0xffffffffu, VB, 1);
+    if (lane == 31) { dA = 0u; dB = 0u; }
+    const uint32_t innerA = dA & (VA << 1) & (VA >> 1), innerB = dB & (VB << 1) & (VB >> 1);
+    __syncwarp();
+
+    const int tab = (type == P_I) ? 1 : 0;
+    uint32_t RA = (lane == slane) ? (1u << (sx + 2)) : 0u, RB = 0u;
+    uint32_t doneA = 0u, doneB = 0u;
+    while (true) {
+        // ---- fill to the fix point (:409-425, :485-488), all rotations at once ----
+        while (true) {
+            const uint32_t a0 = RA, b0 = RB;
+            RA = fall_scan(hflood(RA, VA), PA1, PA2, PA4, PA8, PA16);
+            RB = fall_scan(hflood(RB, VB), PB1, PB2, PB4, PB8, PB16);
+            if (!__any_sync(0xffffffffu, (RA ^ a0) | (RB ^ b0))) break;
+        }
+        if (type == P_O) break;
+        // ---- kicks of the edge cells reached since the last round (:427-483) ----
+        const uint32_t EA = RA & ~innerA, EB = RB & ~innerB;
+        const uint32_t nA = EA & ~doneA, nB = EB & ~doneB;
+        doneA = EA; doneB = EB;
+        if (!__any_sync(0xffffffffu, nA | nB)) break;
+#pragma unroll 1
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t X = (r & 2) ? nB : nA;
+            const uint32_t ne = (r & 1) ? (X >> 16) : (X & 0xFFFFu);
+            if (!__any_sync(0xffffffffu, ne)) continue;
+#pragma unroll 1
+            for (int kd = 0; kd < 3; ++kd) {
+                const int nrot = (r + kd + 1) & 3;
+                const TrlKicks& K = c_kicks[tab][r][kd];
+                const int kn = K.n;
+                const uint32_t* vt = &S.vv[nrot][lane + 2];
+                uint32_t* at = &S.fu[nrot][lane + 2];
+                uint32_t rem = ne;
+#pragma unroll 1
+                for (int ki = 0; ki < kn; ++ki) {
+                    const int kx = K.k[ki][0], ky = K.k[ki][1];
+                    const uint32_t cand = rem & (vt[-ky] >> (kx + 2));   // source bit ex <-> target bit ex + kx
+                    rem &= ~cand;
+                    if (cand) {
+                        uint32_t arr = (cand << 4) >> (4 - kx);
+                        if (is_T && kd != 1 && ki == kn - 1) arr <<= 16;   // nulk (:469)
+                        atomicOr(&at[-ky], arr);
+                    }
+                    if (!__any_sync(0xffffffffu, rem)) break;            // every edge cell has found its kick
+                }
+            }
+        }
+        __syncwarp();
+        // arrivals seed the next fill (a target is always a valid cell)
+        RA |= (S.fu[0][lane + 2] | (S.fu[0][lane + 2] >> 16)) & 0xFFFFu;
+        RA |= (S.fu[1][lane + 2] | (S.fu[1][lane + 2] >> 16)) << 16;
+        RB |= (S.fu[2][lane + 2] | (S.fu[2][lane + 2] >> 16)) & 0xFFFFu;
+        RB |= (S.fu[3][lane + 2] | (S.fu[3][lane + 2] >> 16)) << 16;
+    }
+    // rows above the window would be needed: hand over to the exact form
+    if (__any_sync(0xffffffffu, lane < 2 && (RA | RB))) return false;
+    const uint32_t placedA = RA & ~dA, placedB = RB & ~dB;
+    uint32_t fw[4] = {0u, 0u, 0u, 0u};
+    if (is_T) {
+        bool mixed = false;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            fw[r] = S.fu[r][lane + 2];
+            const uint32_t placed = ((r & 2) ? placedB : placedA) >> (16 * (r & 1)) & 0xFFFFu;
+            mixed = mixed || (fw[r] & (fw[r] >> 16) & placed);
+        }
+        if (__any_sync(0xffffffffu, mixed)) return false;   // the order of emissions decides: exact form
+    }
+    // ---- _convert_placements_to_policy (move_generation.py:650-749): lane = row ----
+    const int pbase = c_plane_base[type];
+    const int nrot_planes = c_plane_nrot[type];
+    const bool zsi = (type == P_Z || type == P_S || type == P_I);
+    if (my < TRL_MAP_H - 1) {
+#pragma unroll
+        for (int rot = 0; rot < 4; ++rot) {
+            if (type == P_O && rot > 0) break;
+            const uint32_t placed = ((rot & 2) ? placedB : placedA) >> (16 * (rot & 1)) & 0xFFFFu;
+            if (!placed) continue;
+            int row = my - 2;
+            uint32_t bits = placed;   // bit mx == policy column x + 2
+            if (zsi) {                // rot 2 -> (rot 0, row + 1); rot 3 -> (rot 1, col - 1)
+                if (rot == 2) row += 1;
+                else if (rot == 3) bits >>= 1;
+            }
+            if (!is_T) {
+                or_chunk(mask, pbase + rot % nrot_planes, row, bits & 0x7FFu);
+            } else {
+                const uint32_t f = (fw[rot] | (fw[rot] >> 16)) & placed, u = fw[rot] >> 16;
+                or_chunk(mask, pbase + rot, row, (placed & ~f) & 0x7FFu);
+                or_chunk(mask, pbase + 4 + rot, row, (f & ~u) & 0x7FFu);
+                or_chunk(mask, pbase + 8 + rot, row, (f & u) & 0x7FFu);
+            }
+        }
+    }
+    return true;
+}
+
 // One piece type of one call, executed by one converged warp.
-__device__ void search_piece_warp(PieceState& S, const uint16_t* rows, int type, bool via_hold, uint32_t* mask,
+__device__ __noinline__ void search_piece_fifo(PieceState& S, const uint16_t* rows, int type, bool via_hold, uint32_t* mask,
                                   uint32_t& status, const uint32_t (*kpack)[4][3][2]) {
     const int lane = threadIdx.x & 31;
     uint32_t minos[4];
@@ -393,6 +591,97 @@ __device__ void search_piece_warp(PieceState& S, const uint16_t* rows, int type,
     }
 }
 
+// One piece type of one call: the row-parallel closure form, or the exact FIFO form where that one cannot decide.
+__device__ __forceinline__ void search_piece_warp(PieceState& S, const uint16_t* rows, int type, bool via_hold, uint32_t* mask,
+                                                  uint32_t& status, const uint32_t (*kpack)[4][3][2]) {
+    if (c_fast_path && c_fifo_limit == kFifoCap) {
+        const bool done = search_piece_rows(S, rows, type, via_hold, mask);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_fast_stats[done ? 0 : 1], 1ull);
+        if (done) return;
+        __syncwarp();
+    }
+    search_piece_fifo(S, rows, type, via_hold, mask, status, kpack);
+}
+
+// Outputs of one call, written by ONE warp from the call's shared-memory mask: the coalesced bit-packed
+// mask, the ascending move list (= np.argwhere order, ai.py:1016-1024), the count and the status word.
+__device__ __forceinline__ void write_call_outputs(CallState& C, int i, int lane, uint32_t* __restrict__ mask_bits,
+                                                   uint16_t* __restrict__ moves, int moves_cap,
+                                                   uint16_t* __restrict__ n_moves, uint32_t* __restrict__ status,
+                                                   uint16_t* __restrict__ compact, unsigned long long compact_cap,
+                                                   unsigned long long* __restrict__ compact_total,
+                                                   unsigned long long* __restrict__ offsets) {
+    if (C.skip) {
+        if (lane == 0) {
+            if (n_moves) n_moves[i] = 0;
+            if (status) status[i] = 0;
+            if (compact) offsets[i] = 0;
+        }
+        return;
+    }
+    if (mask_bits) {
+        uint32_t* gm = mask_bits + (size_t)i * TRL_MASK_WORDS;
+        for (int w2 = lane; w2 < TRL_MASK_WORDS; w2 += 32) gm[w2] = C.mask[w2];
+    }
+    // lane owns 12 consecutive words (the last lanes fewer): counts -> prefix -> ordered writes
+    const int w0 = lane * 12;
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        const int w2 = w0 + k;
+        if (w2 < TRL_MASK_WORDS) cnt += __popc(C.mask[w2]);
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t st = C.status;
+    if (compact) {
+        unsigned long long off = 0;
+        if (lane == 0) off = atomicAdd(compact_total, (unsigned long long)total);
+        off = __shfl_sync(0xffffffffu, off, 0);
+        if (off + (unsigned long long)total > compact_cap) st |= TRL_ST_MOVES_TRUNC;
+        else {
+            uint16_t* mv = compact + off;
+            int pos = incl - cnt;
+            for (int k = 0; k < 12; ++k) {
+                const int w2 = w0 + k;
+                if (w2 >= TRL_MASK_WORDS) break;
+                uint32_t m = C.mask[w2];
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    mv[pos++] = (uint16_t)(w2 * 32 + b);
+                }
+            }
+        }
+        if (lane == 0) offsets[i] = off;
+    }
+    if (moves) {
+        uint16_t* mv = moves + (size_t)i * moves_cap;
+        int pos = incl - cnt;
+        for (int k = 0; k < 12; ++k) {
+            const int w2 = w0 + k;
+            if (w2 >= TRL_MASK_WORDS) break;
+            uint32_t m = C.mask[w2];
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                if (pos < moves_cap) mv[pos] = (uint16_t)(w2 * 32 + b);
+                ++pos;
+            }
+        }
+        if (total > moves_cap) st |= TRL_ST_MOVES_TRUNC;
+    }
+    if (lane == 0) {
+        if (n_moves) n_moves[i] = (uint16_t)total;
+        if (status) status[i] = st;
+    }
+}
+
 __global__ void __launch_bounds__(kWarps * 32)
 movegen_warp_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restrict__ cur,
                     const uint8_t* __restrict__ alt, const TrlGame* __restrict__ games,
@@ -466,77 +755,92 @@ movegen_warp_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restri
     __syncthreads();
 
     // ---- outputs: coalesced mask, ascending move list (= argwhere order), count, status ----
-    if (i < n && which == 0) {
-        if (C.skip) {
-            if (lane == 0) {
-                if (n_moves) n_moves[i] = 0;
-                if (status) status[i] = 0;
-                if (compact) offsets[i] = 0;
-            }
-            return;
+    if (i < n && which == 0)
+        write_call_outputs(C, i, lane, mask_bits, moves, moves_cap, n_moves, status, compact, compact_cap, compact_total, offsets);
+}
+
+// ---------------------------------------------------------------------------------------
+// Throughput form: ONE warp per call, both piece searches back to back on the same warp.
+//
+// In movegen_warp_kernel the two warps of a call search different piece types (an O search is a
+// fraction of a T search) and then meet at a barrier: ncu counted 4.2 of the 8 warps of a scheduler
+// parked at that barrier per issued instruction, i.e. half of the resident warps hid no latency.  For
+// multi-million-call sweeps latency of a single call is irrelevant, so here a warp owns the whole call
+// (4.5 KB of shared memory: one PieceState re-used by the two searches + the CallState), nothing in the
+// kernel waits for another warp after the kick tables are staged, and a finished warp's slot is refilled by
+// the next block instead of idling until the slowest search of a 16-warp block ends.
+// ---------------------------------------------------------------------------------------
+constexpr int kSoloWarps = 4;
+
+struct SoloState {
+    PieceState P;
+    CallState C;
+};
+
+__global__ void __launch_bounds__(kSoloWarps * 32, 8)
+movegen_solo_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restrict__ cur,
+                    const uint8_t* __restrict__ alt, const TrlGame* __restrict__ games,
+                    const int32_t* __restrict__ index, int n, uint32_t* __restrict__ mask_bits,
+                    uint16_t* __restrict__ moves, int moves_cap, uint16_t* __restrict__ n_moves,
+                    uint32_t* __restrict__ status, uint16_t* __restrict__ compact, unsigned long long compact_cap,
+                    unsigned long long* __restrict__ compact_total, unsigned long long* __restrict__ offsets) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ uint32_t s_kpack[2][4][3][2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    SoloState& S = reinterpret_cast<SoloState*>(smem_raw)[warp];
+    CallState& C = S.C;
+    if (tid < 24) {
+        const int t = tid / 12, r = (tid / 3) % 4, kd = tid % 3;
+        const TrlKicks& K = c_kicks[t][r][kd];
+        uint32_t px = 0, py = 0;
+        for (int ki = 0; ki < K.n; ++ki) {
+            px |= (uint32_t)(K.k[ki][0] + 2) << (4 * ki);
+            py |= (uint32_t)(K.k[ki][1] + 2) << (4 * ki);
         }
-        if (mask_bits) {
-            uint32_t* gm = mask_bits + (size_t)i * TRL_MASK_WORDS;
-            for (int w2 = lane; w2 < TRL_MASK_WORDS; w2 += 32) gm[w2] = C.mask[w2];
-        }
-        // lane owns 12 consecutive words (the last lanes fewer): counts -> prefix -> ordered writes
-        const int w0 = lane * 12;
-        int cnt = 0;
-#pragma unroll
-        for (int k = 0; k < 12; ++k) {
-            const int w2 = w0 + k;
-            if (w2 < TRL_MASK_WORDS) cnt += __popc(C.mask[w2]);
-        }
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        uint32_t st = C.status;
-        if (compact) {
-            unsigned long long off = 0;
-            if (lane == 0) off = atomicAdd(compact_total, (unsigned long long)total);
-            off = __shfl_sync(0xffffffffu, off, 0);
-            if (off + (unsigned long long)total > compact_cap) st |= TRL_ST_MOVES_TRUNC;
+        s_kpack[t][r][kd][0] = px;
+        s_kpack[t][r][kd][1] = py;
+    }
+    const int i = blockIdx.x * kSoloWarps + warp;
+    int c = TRL_NONE, a = TRL_NONE, skip = 0;
+    if (i < n) {
+        for (int w2 = lane; w2 < TRL_MASK_WORDS + 2; w2 += 32) C.mask[w2] = 0u;
+        if (games) {
+            const int gi = index ? index[i] : i;
+            if (gi < 0) skip = 1;
             else {
-                uint16_t* mv = compact + off;
-                int pos = incl - cnt;
-                for (int k = 0; k < 12; ++k) {
-                    const int w2 = w0 + k;
-                    if (w2 >= TRL_MASK_WORDS) break;
-                    uint32_t m = C.mask[w2];
-                    while (m) {
-                        const int b = __ffs(m) - 1;
-                        m &= m - 1;
-                        mv[pos++] = (uint16_t)(w2 * 32 + b);
-                    }
-                }
+                const TrlPlayer& p = games[gi].players[games[gi].turn & 1];
+                for (int r = lane; r < TRL_ROWS; r += 32) C.rows[r] = p.rows[r];
+                c = p.piece;
+                a = (p.held != TRL_NONE) ? p.held : (p.qlen > 0 ? p.queue[0] : TRL_NONE);
             }
-            if (lane == 0) offsets[i] = off;
+        } else {
+            for (int r = lane; r < TRL_ROWS; r += 32) C.rows[r] = boards[(size_t)i * TRL_ROWS + r];
+            c = cur[i];
+            a = alt[i];
         }
-        if (moves) {
-            uint16_t* mv = moves + (size_t)i * moves_cap;
-            int pos = incl - cnt;
-            for (int k = 0; k < 12; ++k) {
-                const int w2 = w0 + k;
-                if (w2 >= TRL_MASK_WORDS) break;
-                uint32_t m = C.mask[w2];
-                while (m) {
-                    const int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    if (pos < moves_cap) mv[pos] = (uint16_t)(w2 * 32 + b);
-                    ++pos;
-                }
-            }
-            if (total > moves_cap) st |= TRL_ST_MOVES_TRUNC;
-        }
+        if (c > 6 && c != TRL_NONE) c = TRL_NONE;
+        if (a > 6 && a != TRL_NONE) a = TRL_NONE;
         if (lane == 0) {
-            if (n_moves) n_moves[i] = (uint16_t)total;
-            if (status) status[i] = st;
+            C.skip = skip;
+            C.status = (!skip && c == TRL_NONE && a == TRL_NONE) ? TRL_ST_NO_PIECE : 0u;
         }
     }
+    __syncthreads();   // kick tables staged; the only block-wide barrier
+    if (i >= n) return;
+    if (!skip) {
+        uint32_t st = 0;
+        // the current piece, then the hold-or-next piece (de-duplicated, move_generation.py:103-105)
+        for (int which = 0; which < 2; ++which) {
+            const int type = which ? a : c;
+            if (type == TRL_NONE || (which && a == c)) continue;
+            search_piece_warp(S.P, C.rows, type, which != 0, C.mask, st, &s_kpack[type == P_I ? 1 : 0]);
+            __syncwarp();
+        }
+        st = __reduce_or_sync(0xffffffffu, st);
+        if (st && lane == 0) C.status |= st;
+        __syncwarp();
+    }
+    write_call_outputs(C, i, lane, mask_bits, moves, moves_cap, n_moves, status, compact, compact_cap, compact_total, offsets);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -675,6 +979,22 @@ movegen_list_kernel(const TrlGame* __restrict__ games, const int32_t* __restrict
 static int g_list_rounds = 1;
 extern "C" void trl_search_movegen_rounds(int rounds) { g_list_rounds = rounds < 1 ? 1 : (rounds > 16 ? 16 : rounds); }
 
+extern "C" int trl_debug_movegen_fast_path(int on) {
+    const int v = on ? 1 : 0;
+    return trl_check(cudaMemcpyToSymbol(c_fast_path, &v, sizeof(int)));
+}
+
+// answered[0] = piece searches answered by the row-parallel closure form, answered[1] = handed to the FIFO
+// form, since the last call (the counters are reset)
+extern "C" int trl_debug_movegen_fast_stats(uint64_t* answered) {
+    if (!answered) return TRL_E_ARG;
+    unsigned long long h[2] = {0, 0}, z[2] = {0, 0};
+    int rc = trl_check(cudaMemcpyFromSymbol(h, g_fast_stats, sizeof(h)));
+    if (!rc) rc = trl_check(cudaMemcpyToSymbol(g_fast_stats, z, sizeof(z)));
+    answered[0] = h[0]; answered[1] = h[1];
+    return rc;
+}
+
 extern "C" int trl_debug_movegen_fifo_limit(int limit) {
     if (limit < 1 || limit > kFifoCap) limit = kFifoCap;
     return trl_check(cudaMemcpyToSymbol(c_fifo_limit, &limit, sizeof(int)));
@@ -698,12 +1018,35 @@ int trl_launch_movegen_listed(const TrlGame* games, const int32_t* index, const 
     return trl_check(cudaGetLastError());
 }
 
+// Which of the two warp-cooperative kernels runs: -1 automatic (by batch size), 0 = two warps per call
+// (latency form), 1 = one warp per call (throughput form).  Tests force both.
+static int g_solo = -1;
+extern "C" void trl_movegen_warp_form(int form) { g_solo = form; }
+
 // Launch the warp-cooperative kernel (same argument contract as movegen.cu's launch_movegen).
 int trl_launch_movegen_warp(const uint16_t* boards, const uint8_t* cur, const uint8_t* alt, const TrlGame* games,
                             const int32_t* index, int n, uint32_t* mask_bits, uint16_t* moves, int moves_cap,
                             uint16_t* n_moves, uint32_t* status, cudaStream_t stream, uint16_t* compact,
                             unsigned long long compact_cap, unsigned long long* compact_total,
                             unsigned long long* offsets) {
+    // one warp per call once every SM is full of warps anyway (148 SMs x 32 resident warps = 4736 calls
+    // in flight): below that the two-warp form halves the latency of a batch
+    const bool solo = g_solo < 0 ? (n >= 3 * 4736) : (g_solo == 1);
+    if (solo) {
+        const size_t smem = sizeof(SoloState) * kSoloWarps;
+        static bool configured = false;
+        if (!configured) {
+            int rc = trl_check(cudaFuncSetAttribute(movegen_solo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (!rc) rc = trl_check(cudaFuncSetAttribute(movegen_solo_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            if (rc) return rc;
+            configured = true;
+        }
+        const int blocks = (n + kSoloWarps - 1) / kSoloWarps;
+        movegen_solo_kernel<<<blocks, kSoloWarps * 32, smem, stream>>>(boards, cur, alt, games, index, n, mask_bits, moves,
+                                                                      moves_cap, n_moves, status, compact, compact_cap,
+                                                                      compact_total, offsets);
+        return trl_check(cudaGetLastError());
+    }
     const size_t smem = sizeof(PieceState) * kWarps + sizeof(CallState) * kCallsPerBlock;
     static bool configured = false;
     if (!configured) {
