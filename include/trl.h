@@ -182,9 +182,10 @@ int trl_movegen_host_compact(const uint16_t* boards, const uint8_t* cur, const u
  * bit-identical outputs; the choice only trades latency against throughput. */
 void trl_movegen_select_kernel(int kernel);
 
-/* Form of the warp-cooperative kernel (csrc/movegen_warp.cu): 0 = two warps per call, one per piece
+/* Form of the warp-cooperative enumeration (csrc/movegen_warp.cu): 0 = two warps per call, one per piece
  * type (lowest latency: the few-thousand-call batches of a self-play step), 1 = one warp per call,
- * both piece searches back to back (highest throughput: no warp ever waits for another; the
+ * both piece searches back to back, 2 = two passes: a small kernel with the row-parallel closure search
+ * alone, then the exact FIFO search for the calls it could not decide (highest throughput: the
  * multi-million-call sweeps of move_generation.py:752-789), -1 = by batch size (default).
  * Bit-identical outputs. */
 void trl_movegen_warp_form(int form);

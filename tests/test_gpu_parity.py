@@ -14,15 +14,15 @@ from tetris_reinforcement_learning_b200.state import (GAME_DTYPE, STEPOUT_DTYPE,
                                                       rows_to_grid, unpack_mask)
 
 
-@pytest.fixture(scope="module", params=["warp", "solo", "fifo", "thread"])
+@pytest.fixture(scope="module", params=["warp", "solo", "rows", "fifo", "thread"])
 def mg(request):
-    """move_generation with one of the bit-exact kernels forced: csrc/movegen_warp.cu in its two forms (two
-    warps per call / one warp per call), the same with the row-parallel closure search switched off (every
+    """move_generation with one of the bit-exact kernels forced: csrc/movegen_warp.cu in its three forms (two
+    warps per call / one warp per call / closure-search kernel + exact clean-up pass), the same with the row-parallel closure search switched off (every
     search through the exact FIFO form), and csrc/movegen.cu (one thread per call)."""
     from tetris_reinforcement_learning_b200 import _native, move_generation
     L = _native.lib()
     L.trl_movegen_select_kernel(0 if request.param == "thread" else 1)
-    L.trl_movegen_warp_form({"warp": 0, "solo": 1, "fifo": -1, "thread": -1}[request.param])
+    L.trl_movegen_warp_form({"warp": 0, "solo": 1, "rows": 2, "fifo": -1, "thread": -1}[request.param])
     assert L.trl_debug_movegen_fast_path(0 if request.param == "fifo" else 1) == 0
     yield move_generation
     L.trl_movegen_select_kernel(-1)
@@ -123,7 +123,7 @@ def test_movegen_kernels_agree_on_adversarial_boards():
     d_c, d_a = torch.from_numpy(cur).to(dev), torch.from_numpy(alt).to(dev)
     outs = []
     try:
-        for kernel, form, fast in ((0, -1, 1), (1, 0, 1), (1, 1, 1), (1, -1, 0)):
+        for kernel, form, fast in ((0, -1, 1), (1, 0, 1), (1, 1, 1), (1, 2, 1), (1, -1, 0)):
             _native.lib().trl_movegen_select_kernel(kernel)
             _native.lib().trl_movegen_warp_form(form)
             assert _native.lib().trl_debug_movegen_fast_path(fast) == 0

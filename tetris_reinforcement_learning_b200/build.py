@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
     """Compile every .cu under csrc/ for sm_100a into one shared library."""
     if not force and not needs_build():
         return SO
-    cmd = [NVCC] + FLAGS + ["-o", SO] + sources()
+    cmd = [NVCC] + FLAGS + os.environ.get("TRL_NVCC_EXTRA", "").split() + ["-o", SO] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(PKG, "build.log"), "w") as f:

@@ -50,7 +50,7 @@ struct PieceState {
 };
 
 struct CallState {
-    uint32_t mask[TRL_MASK_WORDS + 2];
+    alignas(16) uint32_t mask[TRL_MASK_WORDS + 2];   // 364 words = 91 x 16 B
     uint16_t rows[TRL_ROWS];
     int cur, alt, skip;
     uint32_t status;
@@ -105,21 +105,27 @@ __device__ __forceinline__ void flag_cell(uint32_t* fu_row, uint32_t bit, bool u
 //     flagged emission, either at its pop, :384-394, or at once, :471-479).
 //
 // Returns false — and the caller runs the exact FIFO search instead — in the two cases this form cannot
-// decide: (i) a T cell received arrivals with BOTH flag values (then the order of emissions matters,
-// :671-677), (ii) something reached the two top rows of the window (a climb of more than five rows by
-// kicks; rows above the window are not represented).  Both are rare (counted in g_fast_fallbacks).
+// decide: (i) a stuck T cell received arrivals with BOTH flag values (then the order of emissions matters,
+// :671-677; a level-by-level ordering argument — rounds of this search are levels of the reference's queue —
+// was tried and decides under 14 % of these cases: the two flags nearly always meet inside one level),
+// (ii) something reached the two top rows of the window (a climb of more than five rows by kicks; rows
+// above the window are not represented).  Counted in g_fast_stats: 24 % of the T searches, 0 of the others,
+// on the BASELINE config-2 boards.
 // ---------------------------------------------------------------------------------------
 constexpr int kWin0 = 12;   // validity row of lane 0
+constexpr int kWinRows = 36;                      // lane + 2, two zero rows either side
 __constant__ int c_fast_path = 1;                 // trl_debug_movegen_fast_path(0) forces the FIFO form (tests run both)
-__device__ unsigned long long g_fast_stats[2];    // searches answered by the closure form / handed to the FIFO form
-
-__device__ __forceinline__ uint32_t shfl_up0(uint32_t x, int d, int lane) {   // lane < d receives 0
-    const uint32_t t = __shfl_up_sync(0xffffffffu, x, d);
-    return lane >= d ? t : 0u;
-}
+__device__ unsigned long long g_fast_stats[8];    // [0] searches answered by the closure form, [1] handed to the FIFO form;
+                                                  // with -DTRL_MOVEGEN_STATS also [2] rounds, [3] fill iterations, [4] (rotation, direction) passes, [5] kick tests
+#ifdef TRL_MOVEGEN_STATS
+#define TRL_STAT(i) (++stat_##i)
+#else
+#define TRL_STAT(i) ((void)0)
+#endif
 
 // R closed under "move one row down while the target is valid": P1..P16 are the propagate masks of
-// window lengths 1, 2, 4, 8, 16 ending at this lane's row (zero where the window leaves the lane range).
+// window lengths 1, 2, 4, 8, 16 ending at this lane's row (zero where the window leaves the lane range,
+// which also cancels the value a lane < d gets back from its own shuffle).
 __device__ __forceinline__ uint32_t fall_scan(uint32_t R, uint32_t P1, uint32_t P2, uint32_t P4, uint32_t P8, uint32_t P16) {
     R |= __shfl_up_sync(0xffffffffu, R, 1) & P1;
     R |= __shfl_up_sync(0xffffffffu, R, 2) & P2;
@@ -129,59 +135,71 @@ __device__ __forceinline__ uint32_t fall_scan(uint32_t R, uint32_t P1, uint32_t 
     return R;
 }
 
-__device__ __noinline__ bool search_piece_rows(PieceState& S, const uint16_t* rows, int type, bool via_hold, uint32_t* mask) {
-    const int lane = threadIdx.x & 31;
-    uint32_t minos[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) minos[r] = c_minos[type][r];
-    const int sx = trl_spawn_x(type);
-    if (via_hold && !trl_fits(rows, minos[0], sx, TRL_SPAWN_Y)) return true;   // player.py:37-44: no moves for this type
+// hflood with the bit-reversed `open` precomputed (it is loop invariant in the closure search)
+__device__ __forceinline__ uint32_t hflood_r(uint32_t seed, uint32_t open, uint32_t ropen) {
+    const uint32_t up = ((open + seed) ^ open) & open;
+    const uint32_t dn = __brev(((ropen + __brev(seed)) ^ ropen) & ropen);
+    return up | dn | seed;
+}
 
+// first board row with a block (40 when the board is empty); rows in shared memory, executed by a whole warp
+__device__ __forceinline__ int first_block_row(const uint16_t* rows, int lane) {
+    const uint32_t b0 = __ballot_sync(0xffffffffu, (rows[lane] & TRL_FULL_ROW) != 0);
+    const uint32_t b1 = __ballot_sync(0xffffffffu, lane < TRL_ROWS - 32 && (rows[(lane & 7) + 32] & TRL_FULL_ROW) != 0);
+    return b0 ? (__ffs(b0) - 1) : (b1 ? 31 + __ffs(b1) : TRL_ROWS);
+}
+
+// St: anything with uint32_t vv[4][>= kWinRows], fu[4][>= kWinRows] in shared memory.  The loops are kept
+// rolled on purpose: the kernels that call this are bound by instruction fetch, not by loop overhead.
+template <class St>
+__device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, int hi, int type, bool via_hold, uint32_t* mask) {
+    const int lane = threadIdx.x & 31;
+    const int sx = trl_spawn_x(type);
+    const bool is_T = (type == P_T);
     // validity rows of the four rotations for this lane's row (move_generation.py:490-528)
     const int my = lane + kWin0;
     uint32_t e[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) e[k] = trl_empty_row(rows, my - 2 + k) << 2;
-    uint32_t v[4];
-#pragma unroll
+    uint32_t VA = 0u, VB = 0u;
+#pragma unroll 1
     for (int r = 0; r < 4; ++r) {
+        const uint32_t m4 = c_minos[type][r];
         uint32_t acc = 0x3FFFu;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-            const uint32_t co = (minos[r] >> (8 * m)) & 15u, ro = (minos[r] >> (8 * m + 4)) & 15u;
+            const uint32_t co = (m4 >> (8 * m)) & 15u, ro = (m4 >> (8 * m + 4)) & 15u;
             const uint32_t ek = ro == 0 ? e[0] : (ro == 1 ? e[1] : (ro == 2 ? e[2] : e[3]));
             acc &= ek >> co;
         }
-        v[r] = acc;
-    }
-    // _set_starting_position (move_generation.py:164-180)
-    int hi = TRL_ROWS;
-    for (int i = lane; i < TRL_ROWS; i += 32)
-        if (rows[i] & TRL_FULL_ROW) hi = min(hi, i);
-    hi = __reduce_min_sync(0xffffffffu, hi);
-    const int slane = max(hi - (int)c_matrix_size[type], TRL_SPAWN_Y) + 2 - kWin0;   // 7..28
-    const uint32_t vs = __shfl_sync(0xffffffffu, v[0], slane);
-    if (!((vs >> (sx + 2)) & 1u)) return true;                                   // :351-352
-
-    const bool is_T = (type == P_T);
-    const uint32_t VA = v[0] | (v[1] << 16), VB = v[2] | (v[3] << 16);
-    // shared planes, row index lane + 2 (two zero rows either side): validity << 2 for the kick tests, arrivals
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        S.vv[r][lane + 2] = v[r] << 2;
+        // shared planes, row index lane + 2: validity << 2 for the kick tests, arrivals (T: low half = flag
+        // clear, high half = used-last-kick)
+        S.vv[r][lane + 2] = acc << 2;
         S.fu[r][lane + 2] = 0u;
         if (lane < 4) {
             const int pad = lane < 2 ? lane : lane + 32;
             S.vv[r][pad] = 0u;
             S.fu[r][pad] = 0u;
         }
+        const uint32_t sh = acc << (16 * (r & 1));
+        if (r & 2) VB |= sh; else VA |= sh;
     }
+    // Player.hold_piece -> create_piece spawn test (player.py:37-44, move_generation.py:112-121): the spawn
+    // cell (sx, 17) is validity row 19 = lane 7 of rotation 0
+    const uint32_t v_spawn = __shfl_sync(0xffffffffu, VA, TRL_SPAWN_Y + 2 - kWin0);
+    if (via_hold && !((v_spawn >> (sx + 2)) & 1u)) return true;
+    // _set_starting_position (move_generation.py:164-180)
+    const int slane = max(hi - (int)c_matrix_size[type], TRL_SPAWN_Y) + 2 - kWin0;   // 7..28
+    const uint32_t vs = __shfl_sync(0xffffffffu, VA, slane);
+    if (!((vs >> (sx + 2)) & 1u)) return true;                                   // :351-352
+
     // propagate masks of the fall scan
     const uint32_t PA1 = lane >= 1 ? VA : 0u, PB1 = lane >= 1 ? VB : 0u;
-    const uint32_t PA2 = PA1 & shfl_up0(PA1, 1, lane) & (lane >= 2 ? ~0u : 0u), PB2 = PB1 & shfl_up0(PB1, 1, lane) & (lane >= 2 ? ~0u : 0u);
-    const uint32_t PA4 = PA2 & shfl_up0(PA2, 2, lane) & (lane >= 4 ? ~0u : 0u), PB4 = PB2 & shfl_up0(PB2, 2, lane) & (lane >= 4 ? ~0u : 0u);
-    const uint32_t PA8 = PA4 & shfl_up0(PA4, 4, lane) & (lane >= 8 ? ~0u : 0u), PB8 = PB4 & shfl_up0(PB4, 4, lane) & (lane >= 8 ? ~0u : 0u);
-    const uint32_t PA16 = PA8 & shfl_up0(PA8, 8, lane) & (lane >= 16 ? ~0u : 0u), PB16 = PB8 & shfl_up0(PB8, 8, lane) & (lane >= 16 ? ~0u : 0u);
+    const uint32_t PA2 = PA1 & __shfl_up_sync(0xffffffffu, PA1, 1), PB2 = PB1 & __shfl_up_sync(0xffffffffu, PB1, 1);
+    const uint32_t PA4 = PA2 & __shfl_up_sync(0xffffffffu, PA2, 2), PB4 = PB2 & __shfl_up_sync(0xffffffffu, PB2, 2);
+    const uint32_t PA8 = PA4 & __shfl_up_sync(0xffffffffu, PA4, 4), PB8 = PB4 & __shfl_up_sync(0xffffffffu, PB4, 4);
+    const uint32_t PA16 = PA8 & __shfl_up_sync(0xffffffffu, PA8, 8), PB16 = PB8 & __shfl_up_sync(0xffffffffu, PB8, 8);
+    const uint32_t rVA = __brev(VA), rVB = __brev(VB);
     // cells whose three neighbours (below, left, right) are all valid are no edge cells (:427-429)
     uint32_t dA = __shfl_down_sync(0xffffffffu, VA, 1), dB = __shfl_down_sync(0xffffffffu, VB, 1);
     if (lane == 31) { dA = 0u; dB = 0u; }
@@ -191,12 +209,19 @@ __device__ __noinline__ bool search_piece_rows(PieceState& S, const uint16_t* ro
     const int tab = (type == P_I) ? 1 : 0;
     uint32_t RA = (lane == slane) ? (1u << (sx + 2)) : 0u, RB = 0u;
     uint32_t doneA = 0u, doneB = 0u;
+    uint32_t a0A = 0u, a0B = 0u;   // arrivals by the in-place kick (0, 0): same lane, never the last kick
+#ifdef TRL_MOVEGEN_STATS
+    unsigned stat_2 = 0, stat_3 = 0, stat_4 = 0, stat_5 = 0;
+#endif
     while (true) {
+        TRL_STAT(2);
         // ---- fill to the fix point (:409-425, :485-488), all rotations at once ----
         while (true) {
-            const uint32_t a0 = RA, b0 = RB;
-            RA = fall_scan(hflood(RA, VA), PA1, PA2, PA4, PA8, PA16);
-            RB = fall_scan(hflood(RB, VB), PB1, PB2, PB4, PB8, PB16);
+            TRL_STAT(3);
+            // a set closed along rows to which the fall scan adds nothing is closed under both
+            const uint32_t a0 = hflood_r(RA, VA, rVA), b0 = hflood_r(RB, VB, rVB);
+            RA = fall_scan(a0, PA1, PA2, PA4, PA8, PA16);
+            RB = fall_scan(b0, PB1, PB2, PB4, PB8, PB16);
             if (!__any_sync(0xffffffffu, (RA ^ a0) | (RB ^ b0))) break;
         }
         if (type == P_O) break;
@@ -212,14 +237,22 @@ __device__ __noinline__ bool search_piece_rows(PieceState& S, const uint16_t* ro
             if (!__any_sync(0xffffffffu, ne)) continue;
 #pragma unroll 1
             for (int kd = 0; kd < 3; ++kd) {
+                TRL_STAT(4);
                 const int nrot = (r + kd + 1) & 3;
+                // kick 0 is (0, 0) in every list (const.py:191-235): target = same cell of the new rotation
+                const uint32_t Vn = ((nrot & 2) ? VB : VA) >> (16 * (nrot & 1));
+                const uint32_t c0 = ne & Vn;
+                const uint32_t c0s = c0 << (16 * (nrot & 1));
+                if (nrot & 2) a0B |= c0s; else a0A |= c0s;
+                uint32_t rem = ne & ~c0;
+                if (!__any_sync(0xffffffffu, rem)) continue;
                 const TrlKicks& K = c_kicks[tab][r][kd];
                 const int kn = K.n;
                 const uint32_t* vt = &S.vv[nrot][lane + 2];
                 uint32_t* at = &S.fu[nrot][lane + 2];
-                uint32_t rem = ne;
 #pragma unroll 1
-                for (int ki = 0; ki < kn; ++ki) {
+                for (int ki = 1; ki < kn; ++ki) {
+                    TRL_STAT(5);
                     const int kx = K.k[ki][0], ky = K.k[ki][1];
                     const uint32_t cand = rem & (vt[-ky] >> (kx + 2));   // source bit ex <-> target bit ex + kx
                     rem &= ~cand;
@@ -233,23 +266,30 @@ __device__ __noinline__ bool search_piece_rows(PieceState& S, const uint16_t* ro
             }
         }
         __syncwarp();
-        // arrivals seed the next fill (a target is always a valid cell)
-        RA |= (S.fu[0][lane + 2] | (S.fu[0][lane + 2] >> 16)) & 0xFFFFu;
-        RA |= (S.fu[1][lane + 2] | (S.fu[1][lane + 2] >> 16)) << 16;
-        RB |= (S.fu[2][lane + 2] | (S.fu[2][lane + 2] >> 16)) & 0xFFFFu;
-        RB |= (S.fu[3][lane + 2] | (S.fu[3][lane + 2] >> 16)) << 16;
+        // arrivals seed the next fill (a target is always a valid cell; T: low half = flag clear, high = set)
+        {
+            const uint32_t f0 = S.fu[0][lane + 2], f1 = S.fu[1][lane + 2], f2 = S.fu[2][lane + 2], f3 = S.fu[3][lane + 2];
+            RA |= a0A | ((f0 | (f0 >> 16)) & 0xFFFFu) | ((f1 | (f1 >> 16)) << 16);
+            RB |= a0B | ((f2 | (f2 >> 16)) & 0xFFFFu) | ((f3 | (f3 >> 16)) << 16);
+        }
     }
+#ifdef TRL_MOVEGEN_STATS
+    if (lane == 0) {
+        atomicAdd(&g_fast_stats[2], (unsigned long long)stat_2); atomicAdd(&g_fast_stats[3], (unsigned long long)stat_3);
+        atomicAdd(&g_fast_stats[4], (unsigned long long)stat_4); atomicAdd(&g_fast_stats[5], (unsigned long long)stat_5);
+    }
+#endif
     // rows above the window would be needed: hand over to the exact form
     if (__any_sync(0xffffffffu, lane < 2 && (RA | RB))) return false;
     const uint32_t placedA = RA & ~dA, placedB = RB & ~dB;
-    uint32_t fw[4] = {0u, 0u, 0u, 0u};
     if (is_T) {
         bool mixed = false;
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < 4; ++r) {
-            fw[r] = S.fu[r][lane + 2];
-            const uint32_t placed = ((r & 2) ? placedB : placedA) >> (16 * (r & 1)) & 0xFFFFu;
-            mixed = mixed || (fw[r] & (fw[r] >> 16) & placed);
+            const uint32_t fw = S.fu[r][lane + 2];
+            const uint32_t sel = ((r & 2) ? placedB : placedA) >> (16 * (r & 1));
+            const uint32_t a0 = ((r & 2) ? a0B : a0A) >> (16 * (r & 1));
+            mixed = mixed || ((fw | a0) & (fw >> 16) & sel & 0xFFFFu);
         }
         if (__any_sync(0xffffffffu, mixed)) return false;   // the order of emissions decides: exact form
     }
@@ -258,10 +298,10 @@ __device__ __noinline__ bool search_piece_rows(PieceState& S, const uint16_t* ro
     const int nrot_planes = c_plane_nrot[type];
     const bool zsi = (type == P_Z || type == P_S || type == P_I);
     if (my < TRL_MAP_H - 1) {
-#pragma unroll
-        for (int rot = 0; rot < 4; ++rot) {
-            if (type == P_O && rot > 0) break;
-            const uint32_t placed = ((rot & 2) ? placedB : placedA) >> (16 * (rot & 1)) & 0xFFFFu;
+        const int n_rot = (type == P_O) ? 1 : 4;
+#pragma unroll 1
+        for (int rot = 0; rot < n_rot; ++rot) {
+            const uint32_t placed = (((rot & 2) ? placedB : placedA) >> (16 * (rot & 1))) & 0xFFFFu;
             if (!placed) continue;
             int row = my - 2;
             uint32_t bits = placed;   // bit mx == policy column x + 2
@@ -272,7 +312,9 @@ __device__ __noinline__ bool search_piece_rows(PieceState& S, const uint16_t* ro
             if (!is_T) {
                 or_chunk(mask, pbase + rot % nrot_planes, row, bits & 0x7FFu);
             } else {
-                const uint32_t f = (fw[rot] | (fw[rot] >> 16)) & placed, u = fw[rot] >> 16;
+                const uint32_t fw = S.fu[rot][lane + 2];
+                const uint32_t a0 = (((rot & 2) ? a0B : a0A) >> (16 * (rot & 1))) & 0xFFFFu;
+                const uint32_t f = (fw | (fw >> 16) | a0) & placed, u = fw >> 16;
                 or_chunk(mask, pbase + rot, row, (placed & ~f) & 0x7FFu);
                 or_chunk(mask, pbase + 4 + rot, row, (f & ~u) & 0x7FFu);
                 or_chunk(mask, pbase + 8 + rot, row, (f & u) & 0x7FFu);
@@ -280,6 +322,11 @@ __device__ __noinline__ bool search_piece_rows(PieceState& S, const uint16_t* ro
         }
     }
     return true;
+}
+
+// out-of-line copy for the kernels that also carry the FIFO form
+__device__ __noinline__ bool search_piece_rows_call(PieceState& S, const uint16_t* rows, int type, bool via_hold, uint32_t* mask) {
+    return search_piece_rows(S, rows, first_block_row(rows, threadIdx.x & 31), type, via_hold, mask);
 }
 
 // One piece type of one call, executed by one converged warp.
@@ -593,9 +640,9 @@ __device__ __noinline__ void search_piece_fifo(PieceState& S, const uint16_t* ro
 
 // One piece type of one call: the row-parallel closure form, or the exact FIFO form where that one cannot decide.
 __device__ __forceinline__ void search_piece_warp(PieceState& S, const uint16_t* rows, int type, bool via_hold, uint32_t* mask,
-                                                  uint32_t& status, const uint32_t (*kpack)[4][3][2]) {
-    if (c_fast_path && c_fifo_limit == kFifoCap) {
-        const bool done = search_piece_rows(S, rows, type, via_hold, mask);
+                                                  uint32_t& status, const uint32_t (*kpack)[4][3][2], bool exact_only = false) {
+    if (!exact_only && c_fast_path && c_fifo_limit == kFifoCap) {
+        const bool done = search_piece_rows_call(S, rows, type, via_hold, mask);
         if ((threadIdx.x & 31) == 0) atomicAdd(&g_fast_stats[done ? 0 : 1], 1ull);
         if (done) return;
         __syncwarp();
@@ -603,8 +650,26 @@ __device__ __forceinline__ void search_piece_warp(PieceState& S, const uint16_t*
     search_piece_fifo(S, rows, type, via_hold, mask, status, kpack);
 }
 
+// Ascending move list (= np.argwhere order, ai.py:1016-1024) of a shared-memory mask: lane owns the 12
+// consecutive words from w0 and writes from position `pos` (its exclusive prefix count).  Kept out of line
+// and rolled: it runs once per call and must not crowd the search loops out of the instruction cache.
+__device__ __noinline__ void write_move_list(const uint32_t* mask, int w0, int pos, uint16_t* mv, int cap) {
+#pragma unroll 1
+    for (int k = 0; k < 12; ++k) {
+        const int w2 = w0 + k;
+        if (w2 >= TRL_MASK_WORDS) break;
+        uint32_t m = mask[w2];
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            if (pos < cap) mv[pos] = (uint16_t)(w2 * 32 + b);
+            ++pos;
+        }
+    }
+}
+
 // Outputs of one call, written by ONE warp from the call's shared-memory mask: the coalesced bit-packed
-// mask, the ascending move list (= np.argwhere order, ai.py:1016-1024), the count and the status word.
+// mask, the ascending move list, the count and the status word.
 __device__ __forceinline__ void write_call_outputs(CallState& C, int i, int lane, uint32_t* __restrict__ mask_bits,
                                                    uint16_t* __restrict__ moves, int moves_cap,
                                                    uint16_t* __restrict__ n_moves, uint32_t* __restrict__ status,
@@ -619,17 +684,16 @@ __device__ __forceinline__ void write_call_outputs(CallState& C, int i, int lane
         }
         return;
     }
-    if (mask_bits) {
-        uint32_t* gm = mask_bits + (size_t)i * TRL_MASK_WORDS;
-        for (int w2 = lane; w2 < TRL_MASK_WORDS; w2 += 32) gm[w2] = C.mask[w2];
-    }
     // lane owns 12 consecutive words (the last lanes fewer): counts -> prefix -> ordered writes
     const int w0 = lane * 12;
     int cnt = 0;
-#pragma unroll
+    uint32_t* gm = mask_bits ? mask_bits + (size_t)i * TRL_MASK_WORDS : nullptr;
+#pragma unroll 1
     for (int k = 0; k < 12; ++k) {
         const int w2 = w0 + k;
         if (w2 < TRL_MASK_WORDS) cnt += __popc(C.mask[w2]);
+        const int w3 = k * 32 + lane;                       // coalesced copy of the mask
+        if (gm && w3 < TRL_MASK_WORDS) gm[w3] = C.mask[w3];
     }
     int incl = cnt;
 #pragma unroll
@@ -644,41 +708,52 @@ __device__ __forceinline__ void write_call_outputs(CallState& C, int i, int lane
         if (lane == 0) off = atomicAdd(compact_total, (unsigned long long)total);
         off = __shfl_sync(0xffffffffu, off, 0);
         if (off + (unsigned long long)total > compact_cap) st |= TRL_ST_MOVES_TRUNC;
-        else {
-            uint16_t* mv = compact + off;
-            int pos = incl - cnt;
-            for (int k = 0; k < 12; ++k) {
-                const int w2 = w0 + k;
-                if (w2 >= TRL_MASK_WORDS) break;
-                uint32_t m = C.mask[w2];
-                while (m) {
-                    const int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    mv[pos++] = (uint16_t)(w2 * 32 + b);
-                }
-            }
-        }
+        else write_move_list(C.mask, w0, incl - cnt, compact + off, 0x7fffffff);
         if (lane == 0) offsets[i] = off;
     }
     if (moves) {
-        uint16_t* mv = moves + (size_t)i * moves_cap;
-        int pos = incl - cnt;
-        for (int k = 0; k < 12; ++k) {
-            const int w2 = w0 + k;
-            if (w2 >= TRL_MASK_WORDS) break;
-            uint32_t m = C.mask[w2];
-            while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                if (pos < moves_cap) mv[pos] = (uint16_t)(w2 * 32 + b);
-                ++pos;
-            }
-        }
+        write_move_list(C.mask, w0, incl - cnt, moves + (size_t)i * moves_cap, moves_cap);
         if (total > moves_cap) st |= TRL_ST_MOVES_TRUNC;
     }
     if (lane == 0) {
         if (n_moves) n_moves[i] = (uint16_t)total;
         if (status) status[i] = st;
+    }
+}
+
+// Zero the call's mask with one warp: 91 128-bit stores.
+__device__ __forceinline__ void zero_mask(CallState& C, int lane) {
+    static_assert((TRL_MASK_WORDS + 2) % 4 == 0, "mask is a whole number of 16-byte words");
+    uint4* m4 = reinterpret_cast<uint4*>(C.mask);
+#pragma unroll
+    for (int k = lane; k < (TRL_MASK_WORDS + 2) / 4; k += 32) m4[k] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// Stage one call into the warp's CallState: zeroed mask, board rows, piece types (c, a) and the skip flag.
+__device__ __forceinline__ void stage_call(CallState& C, int i, int lane, const uint16_t* __restrict__ boards,
+                                           const uint8_t* __restrict__ cur, const uint8_t* __restrict__ alt,
+                                           const TrlGame* __restrict__ games, const int32_t* __restrict__ index,
+                                           int& c, int& a, int& skip) {
+    c = TRL_NONE; a = TRL_NONE; skip = 0;
+    if (games) {
+        const int gi = index ? index[i] : i;
+        if (gi < 0) skip = 1;
+        else {
+            const TrlPlayer& p = games[gi].players[games[gi].turn & 1];
+            for (int r = lane; r < TRL_ROWS; r += 32) C.rows[r] = p.rows[r];
+            c = p.piece;
+            a = (p.held != TRL_NONE) ? p.held : (p.qlen > 0 ? p.queue[0] : TRL_NONE);
+        }
+    } else {
+        for (int r = lane; r < TRL_ROWS; r += 32) C.rows[r] = boards[(size_t)i * TRL_ROWS + r];
+        c = cur[i];
+        a = alt[i];
+    }
+    if (c > 6 && c != TRL_NONE) c = TRL_NONE;
+    if (a > 6 && a != TRL_NONE) a = TRL_NONE;
+    if (lane == 0) {
+        C.cur = c; C.alt = a; C.skip = skip;
+        C.status = (!skip && c == TRL_NONE && a == TRL_NONE) ? TRL_ST_NO_PIECE : 0u;
     }
 }
 
@@ -692,14 +767,16 @@ movegen_warp_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restri
                     // compact[offsets[i] .. offsets[i] + n_moves[i]) (segments are handed out with an atomic
                     // bump allocator, so their order in the buffer is arbitrary; each list is ascending)
                     uint16_t* __restrict__ compact, unsigned long long compact_cap,
-                    unsigned long long* __restrict__ compact_total, unsigned long long* __restrict__ offsets) {
+                    unsigned long long* __restrict__ compact_total, unsigned long long* __restrict__ offsets,
+                    // clean-up mode (second pass of the throughput form): only the calls call_list[0 .. *call_count),
+                    // every search through the exact FIFO form, a fixed grid striding over the list
+                    const int32_t* __restrict__ call_list, const uint32_t* __restrict__ call_count) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     PieceState* ps = reinterpret_cast<PieceState*>(smem_raw);
     CallState* cs = reinterpret_cast<CallState*>(smem_raw + sizeof(PieceState) * kWarps);
     __shared__ uint32_t s_kpack[2][4][3][2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int slot = warp >> 1, which = warp & 1;
-    const int i = blockIdx.x * kCallsPerBlock + slot;
     CallState& C = cs[slot];
 
     if (tid < 24) {   // kick offsets packed 4 bits each (+2) so a lane can index them by kick number
@@ -713,50 +790,38 @@ movegen_warp_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restri
         s_kpack[t][r][kd][0] = px;
         s_kpack[t][r][kd][1] = py;
     }
-    // ---- stage the call: board rows, piece types, zeroed mask (both warps of the call) ----
-    if (i < n) {
-        for (int w2 = which * 32 + lane; w2 < TRL_MASK_WORDS + 2; w2 += 64) C.mask[w2] = 0u;
-        if (which == 0) {
-            int c = TRL_NONE, a = TRL_NONE, skip = 0;
-            if (games) {
-                const int gi = index ? index[i] : i;
-                if (gi < 0) skip = 1;
-                else {
-                    const TrlPlayer& p = games[gi].players[games[gi].turn & 1];
-                    for (int r = lane; r < TRL_ROWS; r += 32) C.rows[r] = p.rows[r];
-                    c = p.piece;
-                    a = (p.held != TRL_NONE) ? p.held : (p.qlen > 0 ? p.queue[0] : TRL_NONE);
-                }
-            } else {
-                for (int r = lane; r < TRL_ROWS; r += 32) C.rows[r] = boards[(size_t)i * TRL_ROWS + r];
-                c = cur[i];
-                a = alt[i];
-            }
-            if (c > 6 && c != TRL_NONE) c = TRL_NONE;
-            if (a > 6 && a != TRL_NONE) a = TRL_NONE;
-            if (lane == 0) {
-                C.cur = c; C.alt = a; C.skip = skip;
-                C.status = (!skip && c == TRL_NONE && a == TRL_NONE) ? TRL_ST_NO_PIECE : 0u;
+    const int n_items = call_list ? (int)call_count[0] : n;
+    for (int base = blockIdx.x * kCallsPerBlock; base < n_items; base += gridDim.x * kCallsPerBlock) {
+        const int j = base + slot;
+        const bool live = j < n_items;
+        const int i = live ? (call_list ? call_list[j] : j) : 0;
+        // ---- stage the call: board rows, piece types, zeroed mask (both warps of the call) ----
+        if (live) {
+            for (int w2 = which * 32 + lane; w2 < TRL_MASK_WORDS + 2; w2 += 64) C.mask[w2] = 0u;
+            if (which == 0) {
+                int c, a, skip;
+                stage_call(C, i, lane, boards, cur, alt, games, index, c, a, skip);
             }
         }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    if (i < n && !C.skip) {
-        const int c = C.cur, a = C.alt;
-        uint32_t st = 0;
-        // warp 0 of the call: the current piece; warp 1: the hold-or-next piece (de-duplicated, :103-105)
-        const int type = which ? a : c;
-        if (type != TRL_NONE && !(which && a == c))
-            search_piece_warp(ps[warp], C.rows, type, which != 0, C.mask, st, &s_kpack[type == P_I ? 1 : 0]);
-        st = __reduce_or_sync(0xffffffffu, st);
-        if (st && lane == 0) atomicOr(&C.status, st);
-    }
-    __syncthreads();
+        if (live && !C.skip) {
+            const int c = C.cur, a = C.alt;
+            uint32_t st = 0;
+            // warp 0 of the call: the current piece; warp 1: the hold-or-next piece (de-duplicated, :103-105)
+            const int type = which ? a : c;
+            if (type != TRL_NONE && !(which && a == c))
+                search_piece_warp(ps[warp], C.rows, type, which != 0, C.mask, st, &s_kpack[type == P_I ? 1 : 0], call_list != nullptr);
+            st = __reduce_or_sync(0xffffffffu, st);
+            if (st && lane == 0) atomicOr(&C.status, st);
+        }
+        __syncthreads();
 
-    // ---- outputs: coalesced mask, ascending move list (= argwhere order), count, status ----
-    if (i < n && which == 0)
-        write_call_outputs(C, i, lane, mask_bits, moves, moves_cap, n_moves, status, compact, compact_cap, compact_total, offsets);
+        // ---- outputs: coalesced mask, ascending move list (= argwhere order), count, status ----
+        if (live && which == 0)
+            write_call_outputs(C, i, lane, mask_bits, moves, moves_cap, n_moves, status, compact, compact_cap, compact_total, offsets);
+        __syncthreads();   // the slot is staged again by the next trip
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -783,7 +848,10 @@ movegen_solo_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restri
                     const int32_t* __restrict__ index, int n, uint32_t* __restrict__ mask_bits,
                     uint16_t* __restrict__ moves, int moves_cap, uint16_t* __restrict__ n_moves,
                     uint32_t* __restrict__ status, uint16_t* __restrict__ compact, unsigned long long compact_cap,
-                    unsigned long long* __restrict__ compact_total, unsigned long long* __restrict__ offsets) {
+                    unsigned long long* __restrict__ compact_total, unsigned long long* __restrict__ offsets,
+                    // clean-up mode (second pass of the two-pass form): only the calls call_list[0 .. *call_count),
+                    // T searches straight through the exact FIFO form, a fixed grid striding over the list
+                    const int32_t* __restrict__ call_list, const uint32_t* __restrict__ call_count) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint32_t s_kpack[2][4][3][2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -800,45 +868,91 @@ movegen_solo_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restri
         s_kpack[t][r][kd][0] = px;
         s_kpack[t][r][kd][1] = py;
     }
-    const int i = blockIdx.x * kSoloWarps + warp;
-    int c = TRL_NONE, a = TRL_NONE, skip = 0;
-    if (i < n) {
-        for (int w2 = lane; w2 < TRL_MASK_WORDS + 2; w2 += 32) C.mask[w2] = 0u;
-        if (games) {
-            const int gi = index ? index[i] : i;
-            if (gi < 0) skip = 1;
-            else {
-                const TrlPlayer& p = games[gi].players[games[gi].turn & 1];
-                for (int r = lane; r < TRL_ROWS; r += 32) C.rows[r] = p.rows[r];
-                c = p.piece;
-                a = (p.held != TRL_NONE) ? p.held : (p.qlen > 0 ? p.queue[0] : TRL_NONE);
-            }
-        } else {
-            for (int r = lane; r < TRL_ROWS; r += 32) C.rows[r] = boards[(size_t)i * TRL_ROWS + r];
-            c = cur[i];
-            a = alt[i];
-        }
-        if (c > 6 && c != TRL_NONE) c = TRL_NONE;
-        if (a > 6 && a != TRL_NONE) a = TRL_NONE;
-        if (lane == 0) {
-            C.skip = skip;
-            C.status = (!skip && c == TRL_NONE && a == TRL_NONE) ? TRL_ST_NO_PIECE : 0u;
-        }
-    }
     __syncthreads();   // kick tables staged; the only block-wide barrier
-    if (i >= n) return;
-    if (!skip) {
-        uint32_t st = 0;
-        // the current piece, then the hold-or-next piece (de-duplicated, move_generation.py:103-105)
-        for (int which = 0; which < 2; ++which) {
-            const int type = which ? a : c;
-            if (type == TRL_NONE || (which && a == c)) continue;
-            search_piece_warp(S.P, C.rows, type, which != 0, C.mask, st, &s_kpack[type == P_I ? 1 : 0]);
+    const int n_items = call_list ? (int)call_count[0] : n;
+#pragma unroll 1
+    for (int j = blockIdx.x * kSoloWarps + warp; j < n_items; j += gridDim.x * kSoloWarps) {
+        const int i = call_list ? call_list[j] : j;
+        int c, a, skip;
+        zero_mask(C, lane);
+        stage_call(C, i, lane, boards, cur, alt, games, index, c, a, skip);
+        __syncwarp();
+        if (!skip) {
+            uint32_t st = 0;
+            // the current piece, then the hold-or-next piece (de-duplicated, move_generation.py:103-105)
+#pragma unroll 1
+            for (int which = 0; which < 2; ++which) {
+                const int type = which ? a : c;
+                if (type == TRL_NONE || (which && a == c)) continue;
+                search_piece_warp(S.P, C.rows, type, which != 0, C.mask, st, &s_kpack[type == P_I ? 1 : 0],
+                                  call_list != nullptr && type == P_T);
+                __syncwarp();
+            }
+            st = __reduce_or_sync(0xffffffffu, st);
+            if (st && lane == 0) C.status |= st;
             __syncwarp();
         }
-        st = __reduce_or_sync(0xffffffffu, st);
-        if (st && lane == 0) C.status |= st;
+        write_call_outputs(C, i, lane, mask_bits, moves, moves_cap, n_moves, status, compact, compact_cap, compact_total, offsets);
         __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Throughput form, two passes: the row-parallel closure search alone in a small kernel, then the exact
+// FIFO search for the few calls it could not decide.
+//
+// movegen_rows_kernel carries no FIFO code: 40 registers instead of 64 (48 resident warps per SM instead
+// of 32), 2.8 KB of shared memory per warp, and a loop nest small enough to stay in the instruction caches
+// (the one-kernel forms lose a quarter of their issue slots to instruction fetch).  A call one of whose
+// piece searches returns "undecided" (mixed T-spin flags on a cell, or a climb out of the row window) is
+// appended to a list and produces no output here; movegen_solo_kernel in clean-up mode then handles
+// exactly those calls (T searches straight through the FIFO form).
+// ---------------------------------------------------------------------------------------
+constexpr int kRowsWarps = 4;
+
+struct RowsState {
+    uint32_t vv[4][kWinRows];
+    uint32_t fu[4][kWinRows];
+};
+
+struct RowsWarp {
+    RowsState P;
+    CallState C;
+};
+
+__global__ void __launch_bounds__(kRowsWarps * 32, 12)
+movegen_rows_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restrict__ cur,
+                    const uint8_t* __restrict__ alt, const TrlGame* __restrict__ games,
+                    const int32_t* __restrict__ index, int n, uint32_t* __restrict__ mask_bits,
+                    uint16_t* __restrict__ moves, int moves_cap, uint16_t* __restrict__ n_moves,
+                    uint32_t* __restrict__ status, uint16_t* __restrict__ compact, unsigned long long compact_cap,
+                    unsigned long long* __restrict__ compact_total, unsigned long long* __restrict__ offsets,
+                    int32_t* __restrict__ undecided, uint32_t* __restrict__ undecided_count) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    RowsWarp& S = reinterpret_cast<RowsWarp*>(smem_raw)[warp];
+    CallState& C = S.C;
+    const int i = blockIdx.x * kRowsWarps + warp;
+    if (i >= n) return;
+    int c, a, skip;
+    zero_mask(C, lane);
+    stage_call(C, i, lane, boards, cur, alt, games, index, c, a, skip);
+    __syncwarp();
+    if (!skip) {
+        const int hi = first_block_row(C.rows, lane);
+        bool ok = true;
+        // the current piece, then the hold-or-next piece (de-duplicated, move_generation.py:103-105)
+#pragma unroll 1
+        for (int which = 0; which < 2 && ok; ++which) {
+            const int type = which ? a : c;
+            if (type == TRL_NONE || (which && a == c)) continue;
+            ok = search_piece_rows(S.P, C.rows, hi, type, which != 0, C.mask);
+            __syncwarp();
+        }
+        if (!ok) {
+            if (lane == 0) undecided[atomicAdd(undecided_count, 1u)] = i;
+            return;
+        }
     }
     write_call_outputs(C, i, lane, mask_bits, moves, moves_cap, n_moves, status, compact, compact_cap, compact_total, offsets);
 }
@@ -988,10 +1102,13 @@ extern "C" int trl_debug_movegen_fast_path(int on) {
 // form, since the last call (the counters are reset)
 extern "C" int trl_debug_movegen_fast_stats(uint64_t* answered) {
     if (!answered) return TRL_E_ARG;
-    unsigned long long h[2] = {0, 0}, z[2] = {0, 0};
+    unsigned long long h[8] = {0}, z[8] = {0};
     int rc = trl_check(cudaMemcpyFromSymbol(h, g_fast_stats, sizeof(h)));
     if (!rc) rc = trl_check(cudaMemcpyToSymbol(g_fast_stats, z, sizeof(z)));
     answered[0] = h[0]; answered[1] = h[1];
+#ifdef TRL_MOVEGEN_STATS
+    for (int k = 2; k < 8; ++k) answered[k] = h[k];   // instrumented builds: the caller passes 8 words
+#endif
     return rc;
 }
 
@@ -1018,45 +1135,90 @@ int trl_launch_movegen_listed(const TrlGame* games, const int32_t* index, const 
     return trl_check(cudaGetLastError());
 }
 
-// Which of the two warp-cooperative kernels runs: -1 automatic (by batch size), 0 = two warps per call
-// (latency form), 1 = one warp per call (throughput form).  Tests force both.
-static int g_solo = -1;
-extern "C" void trl_movegen_warp_form(int form) { g_solo = form; }
+// Which form of the warp-cooperative enumeration runs: -1 automatic (by batch size), 0 = two warps per call
+// (latency form), 1 = one warp per call, 2 = two passes (closure-search kernel + exact clean-up; the
+// throughput form).  Tests force all of them.
+static int g_form = -1;
+extern "C" void trl_movegen_warp_form(int form) { g_form = form; }
 
-// Launch the warp-cooperative kernel (same argument contract as movegen.cu's launch_movegen).
+// per-stream scratch of the two-pass form: [0] = undecided count, [16..] = undecided call indices
+struct TwoPassScratch { cudaStream_t stream; uint32_t* buf; size_t cap; bool used; };
+static TwoPassScratch g_scratch[8];
+
+static uint32_t* two_pass_scratch(cudaStream_t stream, int n) {
+    TwoPassScratch* slot = nullptr;
+    for (auto& e : g_scratch) if (e.used && e.stream == stream) { slot = &e; break; }
+    if (!slot) for (auto& e : g_scratch) if (!e.used) { slot = &e; e.used = true; e.stream = stream; e.buf = nullptr; e.cap = 0; break; }
+    if (!slot) return nullptr;
+    const size_t need = (size_t)n + 16;
+    if (slot->cap < need) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
+        if (slot->buf) { cudaStreamSynchronize(stream); cudaFree(slot->buf); slot->buf = nullptr; slot->cap = 0; }
+        if (cudaMalloc(&slot->buf, need * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        slot->cap = need;
+    }
+    return slot->buf;
+}
+
+// Launch the warp-cooperative enumeration (same argument contract as movegen.cu's launch_movegen).
 int trl_launch_movegen_warp(const uint16_t* boards, const uint8_t* cur, const uint8_t* alt, const TrlGame* games,
                             const int32_t* index, int n, uint32_t* mask_bits, uint16_t* moves, int moves_cap,
                             uint16_t* n_moves, uint32_t* status, cudaStream_t stream, uint16_t* compact,
                             unsigned long long compact_cap, unsigned long long* compact_total,
                             unsigned long long* offsets) {
-    // one warp per call once every SM is full of warps anyway (148 SMs x 32 resident warps = 4736 calls
-    // in flight): below that the two-warp form halves the latency of a batch
-    const bool solo = g_solo < 0 ? (n >= 3 * 4736) : (g_solo == 1);
-    if (solo) {
-        const size_t smem = sizeof(SoloState) * kSoloWarps;
-        static bool configured = false;
-        if (!configured) {
-            int rc = trl_check(cudaFuncSetAttribute(movegen_solo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            if (!rc) rc = trl_check(cudaFuncSetAttribute(movegen_solo_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            if (rc) return rc;
-            configured = true;
-        }
-        const int blocks = (n + kSoloWarps - 1) / kSoloWarps;
-        movegen_solo_kernel<<<blocks, kSoloWarps * 32, smem, stream>>>(boards, cur, alt, games, index, n, mask_bits, moves,
-                                                                      moves_cap, n_moves, status, compact, compact_cap,
-                                                                      compact_total, offsets);
-        return trl_check(cudaGetLastError());
-    }
-    const size_t smem = sizeof(PieceState) * kWarps + sizeof(CallState) * kCallsPerBlock;
+    static int n_sm = 0;
     static bool configured = false;
+    const size_t smem_warp = sizeof(PieceState) * kWarps + sizeof(CallState) * kCallsPerBlock;
+    const size_t smem_solo = sizeof(SoloState) * kSoloWarps;
+    const size_t smem_rows = sizeof(RowsWarp) * kRowsWarps;
     if (!configured) {
-        int rc = trl_check(cudaFuncSetAttribute(movegen_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dev = 0;
+        int rc = trl_check(cudaGetDevice(&dev));
+        if (!rc) rc = trl_check(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        if (!rc) rc = trl_check(cudaFuncSetAttribute(movegen_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_warp));
+        if (!rc) rc = trl_check(cudaFuncSetAttribute(movegen_solo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solo));
+        if (!rc) rc = trl_check(cudaFuncSetAttribute(movegen_solo_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        if (!rc) rc = trl_check(cudaFuncSetAttribute(movegen_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+        if (!rc) rc = trl_check(cudaFuncSetAttribute(movegen_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         if (rc) return rc;
         configured = true;
     }
+    // the throughput forms once every SM is full of warps anyway (148 SMs x 32 resident warps = 4736 calls
+    // in flight): below that the two-warp form halves the latency of a batch
+    int form = g_form < 0 ? (n >= 3 * 4736 ? 2 : 0) : g_form;
+    int fast = 1, limit = kFifoCap;
+    if (form == 2) {   // the debug switches (FIFO form only / lowered FIFO capacity) are served by the one-kernel forms
+        if (cudaMemcpyFromSymbol(&fast, c_fast_path, sizeof(int)) != cudaSuccess ||
+            cudaMemcpyFromSymbol(&limit, c_fifo_limit, sizeof(int)) != cudaSuccess) { cudaGetLastError(); form = 1; }
+        if (!fast || limit != kFifoCap) form = 1;
+    }
+    uint32_t* scratch = form == 2 ? two_pass_scratch(stream, n) : nullptr;
+    if (form == 2 && !scratch) form = 1;
+    if (form == 2) {
+        int rc = trl_check(cudaMemsetAsync(scratch, 0, sizeof(uint32_t), stream));
+        if (rc) return rc;
+        movegen_rows_kernel<<<(n + kRowsWarps - 1) / kRowsWarps, kRowsWarps * 32, smem_rows, stream>>>(
+            boards, cur, alt, games, index, n, mask_bits, moves, moves_cap, n_moves, status, compact, compact_cap,
+            compact_total, offsets, (int32_t*)(scratch + 16), scratch);
+        rc = trl_check(cudaGetLastError());
+        if (rc) return rc;
+        const int blocks = min(8 * n_sm, (n + kSoloWarps - 1) / kSoloWarps);
+        movegen_solo_kernel<<<blocks, kSoloWarps * 32, smem_solo, stream>>>(
+            boards, cur, alt, games, index, n, mask_bits, moves, moves_cap, n_moves, status, compact, compact_cap,
+            compact_total, offsets, (const int32_t*)(scratch + 16), scratch);
+        return trl_check(cudaGetLastError());
+    }
+    if (form == 1) {
+        const int blocks = (n + kSoloWarps - 1) / kSoloWarps;
+        movegen_solo_kernel<<<blocks, kSoloWarps * 32, smem_solo, stream>>>(boards, cur, alt, games, index, n, mask_bits, moves,
+                                                                           moves_cap, n_moves, status, compact, compact_cap,
+                                                                           compact_total, offsets, nullptr, nullptr);
+        return trl_check(cudaGetLastError());
+    }
     const int blocks = (n + kCallsPerBlock - 1) / kCallsPerBlock;
-    movegen_warp_kernel<<<blocks, kWarps * 32, smem, stream>>>(boards, cur, alt, games, index, n, mask_bits, moves,
-                                                              moves_cap, n_moves, status, compact, compact_cap,
-                                                              compact_total, offsets);
+    movegen_warp_kernel<<<blocks, kWarps * 32, smem_warp, stream>>>(boards, cur, alt, games, index, n, mask_bits, moves,
+                                                                   moves_cap, n_moves, status, compact, compact_cap,
+                                                                   compact_total, offsets, nullptr, nullptr);
     return trl_check(cudaGetLastError());
 }

@@ -18,7 +18,7 @@ for n_boards in (586, nb):   # 586 x 7 = 4102 calls: the size of one self-play s
     d_boards = torch.from_numpy(boards.view(np.int16)).to(dev)
     d_cur, d_alt = torch.from_numpy(cur).to(dev), torch.from_numpy(alt).to(dev)
     res = {}
-    for name, k, form in (("thread", 0, -1), ("warp", 1, 0), ("solo", 1, 1)):
+    for name, k, form in (("thread", 0, -1), ("warp", 1, 0), ("solo", 1, 1), ("rows", 1, 2)):
         L.trl_movegen_select_kernel(k)
         L.trl_movegen_warp_form(form)
         for want_mask in (True, False):
@@ -39,13 +39,13 @@ for n_boards in (586, nb):   # 586 x 7 = 4102 calls: the size of one self-play s
             tot = int(d_n.to(torch.int64).sum())
             if k == 1:
                 import ctypes
-                st2 = (ctypes.c_uint64 * 2)()
+                st2 = (ctypes.c_uint64 * 8)()
                 L.trl_debug_movegen_fast_stats(st2)
                 print(f"    closure form answered {st2[0]} piece searches, FIFO form {st2[1]} ({100.0 * st2[1] / max(st2[0] + st2[1], 1):.3f} %)")
             print(f"n_calls={n:8d} kernel={name:6s} out={'mask' if want_mask else 'list'}: {ms * 1e3:9.1f} us  "
                   f"{tot / ms / 1e6:8.1f} G placements/s  status!=0: {int((d_st != 0).sum())}")
             res[(name, want_mask)] = (d_n.clone(), None if d_mask is None else d_mask.clone())
-    for other in ("warp", "solo"):
+    for other in ("warp", "solo", "rows"):
         print(f"  thread vs {other}: counts equal:", bool((res[("thread", True)][0] == res[(other, True)][0]).all()),
               " masks equal:", bool((res[("thread", True)][1] == res[(other, True)][1]).all()))
 L.trl_movegen_select_kernel(-1)
