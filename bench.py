@@ -24,7 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-PROFILE_JSON = ("profiles/r2_movegen_warp.json", "profiles/r1_movegen_warp_sweep2.json")   # tools/ncu_extract.py, newest first
+PROFILE_JSON = ("profiles/r2_movegen_rows.json",)   # tools/ncu_extract.py of the two-pass throughput form
 SCALAR_PROFILE_JSON = "profiles/r2_movegen_thread.json"   # the one-thread-per-call kernel = the scalar restatement on the GPU
 ALGO_BYTES_PER_CALL = 80 + 4 + 1448  # board + (cur, alt, pad) in, bit-packed (27,39,11) mask out
 METRIC = "placements/sec (movegen)"
@@ -32,27 +32,45 @@ UNIT = "placements/s"
 
 
 def load_ncu_profile():
-    """Per-call ncu figures of movegen_warp_kernel from the tracked extraction of the .ncu-rep (tools/ncu_extract.py);
-    None if no profile is committed."""
+    """Per-call ncu figures of the sweep's kernels from the tracked extraction of the .ncu-rep (tools/ncu_extract.py):
+    movegen_rows_kernel (the dominant kernel: closure search) and movegen_solo_kernel in clean-up mode (the calls
+    whose T-spin flags the closure search cannot decide).  None if no profile is committed."""
     for rel in PROFILE_JSON:
         path = os.path.join(ROOT, rel)
         if not os.path.exists(path):
             continue
         with open(path) as f:
             d = json.load(f)
+        out = {"source": f"{rel} ({d['report']}, extracted at {d['extracted_at_commit']})", "kernels": {}}
         for l in d["launches"]:
-            if "movegen_warp_kernel" in l["kernel"] and l.get("units"):
-                m = {k: v["value"] for k, v in l["metrics"].items()}
-                warp_inst = m.get("smsp__inst_executed.sum", 0.0)
-                return {"source": f"{rel} ({d['report']}, extracted at {d['extracted_at_commit']})", "calls": l["units"],
-                        "dram_bytes_per_call": l.get("dram_bytes_per_unit"),
-                        "issue_slots_busy_pct": m.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-                        "alu_pipe_pct_of_peak": m.get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
-                        "threads_per_warp_instruction": m.get("smsp__thread_inst_executed_per_inst_executed.ratio"),
-                        "warp_instructions_per_call": warp_inst / l["units"] if warp_inst else None,
-                        "thread_instructions_per_call": l.get("thread_instructions_per_unit"),
-                        "kernel_ms_under_ncu": m.get("gpu__time_duration.sum"),
-                        "barrier_stall_warps_per_issue": m.get("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio")}
+            if not l.get("units"):
+                continue
+            m = {k: v["value"] for k, v in l["metrics"].items()}
+            warp_inst = m.get("smsp__inst_executed.sum", 0.0)
+            name = "movegen_rows_kernel" if "movegen_rows_kernel" in l["kernel"] else (
+                "movegen_solo_kernel(clean-up)" if "movegen_solo_kernel" in l["kernel"] else None)
+            if name is None:
+                continue
+            out["calls"] = l["units"]
+            out["kernels"][name] = {
+                "dram_bytes_per_call": l.get("dram_bytes_per_unit"),
+                "issue_slots_busy_pct": m.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "alu_pipe_pct_of_peak": m.get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                "threads_per_warp_instruction": m.get("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                "warp_instructions_per_call": warp_inst / l["units"] if warp_inst else None,
+                "thread_instructions_per_call": l.get("thread_instructions_per_unit"),
+                "registers_per_thread": m.get("launch__registers_per_thread"),
+                "achieved_warps_per_sm_pct": m.get("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                "kernel_ms_under_ncu": m.get("gpu__time_duration.sum"),
+                "no_instruction_stall_warps_per_issue": m.get("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio"),
+                "barrier_stall_warps_per_issue": m.get("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio")}
+        if "movegen_rows_kernel" in out["kernels"]:
+            ks = out["kernels"]
+            tot = sum(k["kernel_ms_under_ncu"] or 0.0 for k in ks.values())
+            out["dominant_kernel_share_of_step"] = (ks["movegen_rows_kernel"]["kernel_ms_under_ncu"] or 0.0) / tot if tot else None
+            out["dram_bytes_per_call"] = sum(k["dram_bytes_per_call"] or 0.0 for k in ks.values())
+            out["thread_instructions_per_call"] = sum(k["thread_instructions_per_call"] or 0.0 for k in ks.values())
+            return out
     return None
 
 
@@ -628,10 +646,12 @@ def run_ours(args, rank, world, local_rank):
                 "traffic_unit": "bytes per launch",
                 "traffic_source": (f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per call of a {int(prof['calls'])}-call "
                                    f"launch, scaled to this launch's call count; {prof['source']}") if prof else None,
-                "peak_source": peak_src, "kernel": "movegen_warp_kernel",
+                "peak_source": peak_src, "kernel": "movegen_rows_kernel",
                 "algorithmic_bytes_per_call": ALGO_BYTES_PER_CALL, "kernel_ms": kern_ms,
+                "kernel_ms_how": "CUDA events around one sweep = movegen_rows_kernel + movegen_solo_kernel in clean-up mode (two launches "
+                                 "inside the library call); `achieved` divides by this whole time, the dominant kernel's share is ncu.dominant_kernel_share_of_step",
                 "note": "integer-issue bound, not HBM bound (SURVEY §8d): the DRAM traffic is at the algorithmic minimum; "
-                        "what binds is the ALU / XU pipes, see int_ops",
+                        "what binds is the issue rate (85 % of the issue slots busy in the dominant kernel), see int_ops",
                 "ncu": prof}
     # roofline on integer issue.  per_call = thread-level instructions of the SCALAR restatement of the
     # algorithm (one thread per call, ncu); achieved = per_call x calls/s; peak = 148 SMs x 4 schedulers x 32 lanes x f_SM
@@ -648,7 +668,7 @@ def run_ours(args, rank, world, local_rank):
             "executed_per_call": prof.get("thread_instructions_per_call") if prof else None,
             "executed_frac": (prof["thread_instructions_per_call"] * calls_per_s / peak_ops) if prof and prof.get("thread_instructions_per_call") else None,
             "note": "per_call = what the one-thread-per-call kernel (the reference's algorithm, scalar) executes; executed_per_call = "
-                    "what movegen_warp_kernel executes (bit-parallel passes do redundant lane work); frac is useful work / peak"}
+                    "what the two kernels of the sweep execute (row-parallel bit planes do redundant lane work); frac is useful work / peak"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -667,7 +687,7 @@ def run_ours(args, rank, world, local_rank):
                                         "h2d_bytes_per_step": n_mask * (80 + 2), "d2h_bytes_per_step": d2h, "matches_device_run": e2e_ok,
                                         "api": "trl_movegen_host: the same enumeration returned as bit-packed (27,39,11) masks "
                                                "(1448 B per call): bound by PCIe / host memory, does not scale with the GPU count"}},
-        "gpu_launches": args.steps,
+        "gpu_launches": 2 * args.steps,   # movegen_rows_kernel + movegen_solo_kernel (clean-up) per sweep
         "clocks": clocks,
     }
     if cpu_line is not None:

@@ -709,17 +709,30 @@ __device__ __forceinline__ void mma_bf16_16x8x16(float (&d)[4], uint32_t a0, uin
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// One warp per leaf.  The gathered weight rows are the A operand of warp-level MMAs (16 legal moves x 16 inputs per
-// instruction), x is broadcast into all eight B columns, so column 0 of D holds the logits; a dot product does not care
-// about the order of its terms, so the K slots of a fragment are mapped to memory such that every lane reads 16
-// contiguous bytes of its two rows per pair of MMAs.  (A CUDA-core version spent 85 instructions per move on
-// unpacking bf16 pairs; this one spends 6.)
+// 256-bit read-only global load (sm_100a: LDG.E.ENL2.256).
+__device__ __forceinline__ void ldg256(uint32_t (&r)[8], const void* p) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+
+// Four warps per leaf, each taking every fourth tile of 16 legal moves.  The gathered weight rows are the A operand
+// of warp-level MMAs (16 legal moves x 16 inputs per instruction), x is broadcast into all eight B columns, so column
+// 0 of D holds the logits; a dot product does not care about the order of its terms, so the K slots of a fragment are
+// mapped to memory such that every lane reads 32 contiguous bytes of its two rows per four MMAs.  (A CUDA-core
+// version spent 85 instructions per move on unpacking bf16 pairs; this one spends 6.)
+//
+// What binds is the L1 wavefront queue of the gather (the weight matrix is L2 resident, 216 MB of rows per 4096-leaf
+// step): measured 36 us for 4096 leaves with one or four warps per leaf, with 128-bit or 256-bit loads, with x staged
+// in shared memory or read through L1 — about 22 B/clk/SM.  Staging the rows in shared memory with cp.async (32 lanes
+// along one row per instruction, double buffered) was slower (71 us: LDGSTS costs 8 cycles per instruction and leaves
+// 12 warps per SM).  Left: TMA bulk copies of whole rows, which bypass L1 (bound by L2 at about 18 us).
+constexpr int kPolicyWarpsPerLeaf = 4;
+
 __global__ void __launch_bounds__(256)
 policy_legal_kernel(TrlSearchBuffers B, const __nv_bfloat16* __restrict__ x, int k_pad, const __nv_bfloat16* __restrict__ w,
                     const __nv_bfloat16* __restrict__ bias, float* __restrict__ out) {
-    extern __shared__ __align__(16) uint4 s_x[];          // [8 warps][k_pad / 8]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int g = blockIdx.x * 8 + wib;
+    const int g = blockIdx.x * (8 / kPolicyWarpsPerLeaf) + wib / kPolicyWarpsPerLeaf, sub = wib % kPolicyWarpsPerLeaf;
     trl_grid_dep_wait();
     if (g >= B.n_games) return;
     const TrlSearchCtl* ctl = &B.ctl[g];
@@ -733,29 +746,34 @@ policy_legal_kernel(TrlSearchBuffers B, const __nv_bfloat16* __restrict__ x, int
         if (cached >= 0) { mv = B.legal_cache + pstate * (size_t)B.moves_cap; C = cached; }
     }
     if (C > B.moves_cap) C = B.moves_cap;
-    if (C <= 0) return;
     const int chunks = k_pad >> 3;                        // 16-byte pieces of a row
-    uint4* sx = s_x + wib * chunks;
     const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)g * k_pad);
-    for (int c = lane; c < chunks; c += 32) sx[c] = xr[c];
-    __syncwarp();
     float* o = out + (size_t)g * B.moves_cap;
     const int grp = lane >> 2, tig = lane & 3;
-    for (int t0 = 0; t0 < C; t0 += 16) {
+    for (int t0 = 16 * sub; t0 < C; t0 += 16 * kPolicyWarpsPerLeaf) {
         const int r0 = min(t0 + grp, C - 1), r1 = min(t0 + grp + 8, C - 1);      // rows past the list repeat the last move
         const int m0 = mv[r0], m1 = mv[r1];
         const uint4* w0 = reinterpret_cast<const uint4*>(w + (size_t)m0 * k_pad);
         const uint4* w1 = reinterpret_cast<const uint4*>(w + (size_t)m1 * k_pad);
         float d[4] = {0.f, 0.f, 0.f, 0.f};
         int kc = 0;                                       // in 16-byte chunks
+#pragma unroll 2
+        for (; kc + 8 <= chunks; kc += 8) {               // 64 inputs: four MMAs from one 32-byte load per row
+            uint32_t u[8], v[8], xv[8];
+            ldg256(u, w0 + kc + 2 * tig);
+            ldg256(v, w1 + kc + 2 * tig);
+            ldg256(xv, xr + kc + 2 * tig);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_bf16_16x8x16(d, u[2 * j], v[2 * j], u[2 * j + 1], v[2 * j + 1], xv[2 * j], xv[2 * j + 1]);
+        }
         for (; kc + 4 <= chunks; kc += 4) {               // 32 inputs: two MMAs from one 16-byte load per row
-            const uint4 u = __ldg(w0 + kc + tig), v = __ldg(w1 + kc + tig), xv = sx[kc + tig];
+            const uint4 u = __ldg(w0 + kc + tig), v = __ldg(w1 + kc + tig), xv = __ldg(xr + kc + tig);
             mma_bf16_16x8x16(d, u.x, v.x, u.y, v.y, xv.x, xv.y);
             mma_bf16_16x8x16(d, u.z, v.z, u.w, v.w, xv.z, xv.w);
         }
         if (kc + 2 <= chunks) {                           // 16 more inputs: 8 bytes per lane
             const uint2 u = __ldg(reinterpret_cast<const uint2*>(w0 + kc) + tig), v = __ldg(reinterpret_cast<const uint2*>(w1 + kc) + tig);
-            const uint2 xv = reinterpret_cast<const uint2*>(sx + kc)[tig];
+            const uint2 xv = __ldg(reinterpret_cast<const uint2*>(xr + kc) + tig);
             mma_bf16_16x8x16(d, u.x, v.x, u.y, v.y, xv.x, xv.y);
         }
         if (tig == 0) {                                   // column 0 of D: rows grp and grp + 8
@@ -773,16 +791,10 @@ extern "C" int trl_search_policy_legal(const TrlSearchBuffers* buf, const void* 
         k_pad <= 0 || (k_pad & 15))
         return TRL_E_ARG;
     if (buf->n_games == 0) return TRL_OK;
-    const size_t smem = (size_t)8 * (k_pad / 8) * sizeof(uint4);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        int rc = trl_check(cudaFuncSetAttribute(policy_legal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (rc) return rc;
-        configured = smem;
-    }
-    return trl_launch_ex(policy_legal_kernel, dim3((buf->n_games + 7) / 8), dim3(256), smem, (cudaStream_t)stream, true, false,
-                         *buf, (const __nv_bfloat16*)x_bf16, k_pad, (const __nv_bfloat16*)w_bf16, (const __nv_bfloat16*)bias_bf16,
-                         logits_legal);
+    const int leaves_per_block = 8 / kPolicyWarpsPerLeaf;
+    return trl_launch_ex(policy_legal_kernel, dim3((buf->n_games + leaves_per_block - 1) / leaves_per_block), dim3(256), 0,
+                         (cudaStream_t)stream, true, false, *buf, (const __nv_bfloat16*)x_bf16, k_pad, (const __nv_bfloat16*)w_bf16,
+                         (const __nv_bfloat16*)bias_bf16, logits_legal);
 }
 
 extern "C" int trl_sizeof_search_ctl(void) { return (int)sizeof(TrlSearchCtl); }

@@ -45,6 +45,7 @@ def main():
     ap.add_argument("out")
     ap.add_argument("--kernel", default=".*")
     ap.add_argument("--units-per-block", type=float, default=0.0, help="e.g. 8 movegen calls per block: adds per-unit figures")
+    ap.add_argument("--units", type=float, default=0.0, help="units (e.g. movegen calls) every captured launch worked on, when the grid does not tell")
     ap.add_argument("--note", default="")
     args = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", args.rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
@@ -72,8 +73,8 @@ def main():
                     u = "byte" if "byte" in u else "ms"
                 m[base] = {"value": v, "unit": u}
         rec = {"kernel": re.sub(r"\(.*", "", name), "grid": r[col["Grid Size"]], "block": r[col["Block Size"]], "metrics": m}
-        if args.units_per_block and "launch__grid_size" in m:
-            n = m["launch__grid_size"]["value"] * args.units_per_block
+        if args.units or (args.units_per_block and "launch__grid_size" in m):
+            n = args.units or m["launch__grid_size"]["value"] * args.units_per_block
             rec["units"] = n
             if "sm__inst_executed.sum" in m:
                 rec["warp_instructions_per_unit"] = m["sm__inst_executed.sum"]["value"] / n

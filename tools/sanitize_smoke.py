@@ -13,10 +13,20 @@ from tetris_reinforcement_learning_b200.selfplay import SelfPlayEngine  # noqa: 
 
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
 if what in ("movegen", "all"):
+    from tetris_reinforcement_learning_b200 import _native
     boards, cur, alt = synth.movegen_workload(40, seed=3, caves=True)
-    res = move_generation.movegen_host(boards, cur, alt, want_mask=True, want_moves=True)
-    res2 = move_generation.movegen_host_compact(boards, cur, alt)
-    print("movegen ok", int(res["n_moves"].sum()), res2["total"])
+    # every form of the warp-cooperative enumeration (two warps per call / one warp per call / closure-search
+    # kernel + clean-up pass), then every search through the exact FIFO form, then the one-thread kernel
+    for kernel, form, fast in ((1, 0, 1), (1, 1, 1), (1, 2, 1), (1, 0, 0), (0, -1, 1)):
+        _native.lib().trl_movegen_select_kernel(kernel)
+        _native.lib().trl_movegen_warp_form(form)
+        _native.lib().trl_debug_movegen_fast_path(fast)
+        res = move_generation.movegen_host(boards, cur, alt, want_mask=True, want_moves=True)
+        res2 = move_generation.movegen_host_compact(boards, cur, alt)
+        print("movegen ok", (kernel, form, fast), int(res["n_moves"].sum()), res2["total"])
+    _native.lib().trl_movegen_select_kernel(-1)
+    _native.lib().trl_movegen_warp_form(-1)
+    _native.lib().trl_debug_movegen_fast_path(1)
 if what in ("trunk", "all"):
     torch.manual_seed(0)
     net = arch.AlphaSame(arch.AlphaSameConfig(blocks=2)).to("cuda:0").eval()
