@@ -9,7 +9,7 @@ static thread_local char g_err[256] = "";
 static std::mutex g_ws_mutex;
 static void* g_ws_ptr[TRL_WS_SLOTS] = {};
 static size_t g_ws_size[TRL_WS_SLOTS] = {};
-static cudaStream_t g_host_stream[2] = {nullptr, nullptr};
+static cudaStream_t g_host_stream[TRL_HOST_STREAMS] = {};
 
 int trl_check(cudaError_t e) {
     if (e == cudaSuccess) return TRL_OK;
@@ -33,7 +33,7 @@ void* trl_workspace(int slot, size_t bytes) {
 
 cudaStream_t trl_host_stream(int which) {
     std::lock_guard<std::mutex> lock(g_ws_mutex);
-    which &= 1;
+    which &= TRL_HOST_STREAMS - 1;
     if (!g_host_stream[which]) {
         if (trl_check(cudaStreamCreateWithFlags(&g_host_stream[which], cudaStreamNonBlocking)) != TRL_OK) return nullptr;
     }

@@ -291,25 +291,25 @@ extern "C" int trl_movegen_host(const uint16_t* boards, const uint8_t* cur, cons
                                 uint32_t* status) {
     if (n < 0 || !boards || !cur || !alt || (moves && moves_cap <= 0)) return TRL_E_ARG;
     if (n == 0) return TRL_OK;
-    // Chunked and double-buffered over two streams: with pinned host buffers the H2D / D2H
-    // copies of one chunk overlap the kernel of the other; the staging workspace stays bounded
-    // for multi-million-call sweeps.
+    // Chunked over a ring of TRL_HOST_STREAMS streams: with pinned host buffers the H2D / D2H copies of one chunk
+    // overlap the kernels of the others; the staging workspace stays bounded for multi-million-call sweeps.
     const int chunk = 1 << 17;
     const size_t per = TRL_ROWS * 2 + 2 + TRL_MASK_WORDS * 4 + (moves ? (size_t)moves_cap * 2 : 0) + 2 + 4;
     const int cmax = n < chunk ? n : chunk;
-    const size_t half = (per * (size_t)cmax + 255) & ~(size_t)255;
-    char* ws = (char*)trl_workspace(TRL_WS_HOST_STAGE, 2 * half);
+    const size_t part = (per * (size_t)cmax + 255) & ~(size_t)255;
+    char* ws = (char*)trl_workspace(TRL_WS_HOST_STAGE, TRL_HOST_STREAMS * part);
     if (!ws) return TRL_E_NOMEM;
-    cudaStream_t st[2] = {trl_host_stream(0), trl_host_stream(1)};
-    if (!st[0] || !st[1]) return TRL_E_CUDA;
+    cudaStream_t st[TRL_HOST_STREAMS];
+    for (int k = 0; k < TRL_HOST_STREAMS; ++k) if (!(st[k] = trl_host_stream(k))) return TRL_E_CUDA;
     int rc = TRL_OK;
     int c = 0;
     for (int off = 0; off < n && !rc; off += chunk, ++c) {
         const int m = (n - off < chunk) ? n - off : chunk;
-        cudaStream_t s = st[c & 1];
-        rc = trl_check(cudaStreamSynchronize(s));  // this half's previous chunk has fully drained
+        const int h = c % TRL_HOST_STREAMS;
+        cudaStream_t s = st[h];
+        rc = trl_check(cudaStreamSynchronize(s));  // this part's previous chunk has fully drained
         if (rc) break;
-        char* p = ws + (size_t)(c & 1) * half;
+        char* p = ws + (size_t)h * part;
         uint32_t* d_mask = (uint32_t*)p;  p += (size_t)m * TRL_MASK_WORDS * 4;
         uint32_t* d_status = (uint32_t*)p; p += (size_t)m * 4;
         uint16_t* d_boards = (uint16_t*)p; p += (size_t)m * TRL_ROWS * 2;
@@ -327,9 +327,11 @@ extern "C" int trl_movegen_host(const uint16_t* boards, const uint8_t* cur, cons
         if (!rc && n_moves) rc = trl_check(cudaMemcpyAsync(n_moves + off, d_nm, (size_t)m * 2, cudaMemcpyDeviceToHost, s));
         if (!rc && status) rc = trl_check(cudaMemcpyAsync(status + off, d_status, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
     }
-    int rc0 = trl_check(cudaStreamSynchronize(st[0]));
-    int rc1 = trl_check(cudaStreamSynchronize(st[1]));
-    return rc ? rc : (rc0 ? rc0 : rc1);
+    for (int k = 0; k < TRL_HOST_STREAMS; ++k) {
+        const int r = trl_check(cudaStreamSynchronize(st[k]));
+        if (!rc) rc = r;
+    }
+    return rc;
 }
 
 // Host entry point with COMPACT output: the ascending move lists of all calls packed back to back
@@ -346,18 +348,20 @@ extern "C" int trl_movegen_host_compact(const uint16_t* boards, const uint8_t* c
     const size_t list_cap = (size_t)chunk * 160;   // per-chunk staging: 160 placements per call on average (x 2 B)
     const size_t per = TRL_ROWS * 2 + 2 + 8 + 2 + 4;
     const int cmax = n < chunk ? n : chunk;
-    const size_t half = ((per * (size_t)cmax + list_cap * 2 + 64) + 255) & ~(size_t)255;
-    char* ws = (char*)trl_workspace(TRL_WS_HOST_STAGE, 2 * half);
+    const size_t part = ((per * (size_t)cmax + list_cap * 2 + 64) + 255) & ~(size_t)255;
+    char* ws = (char*)trl_workspace(TRL_WS_HOST_STAGE, TRL_HOST_STREAMS * part);
     if (!ws) return TRL_E_NOMEM;
-    cudaStream_t st[2] = {trl_host_stream(0), trl_host_stream(1)};
-    if (!st[0] || !st[1]) return TRL_E_CUDA;
+    cudaStream_t st[TRL_HOST_STREAMS];
+    for (int k = 0; k < TRL_HOST_STREAMS; ++k) if (!(st[k] = trl_host_stream(k))) return TRL_E_CUDA;
     static unsigned long long* h_total = nullptr;   // pinned: the per-chunk totals come back through it
-    if (!h_total && trl_check(cudaMallocHost(&h_total, 2 * sizeof(unsigned long long))) != TRL_OK) return TRL_E_CUDA;
-    struct Pending { int off, m; unsigned long long* d_total; uint16_t* d_list; unsigned long long* d_offs;
-                     uint16_t* d_nm; uint32_t* d_status; bool live; } pend[2] = {};
+    if (!h_total && trl_check(cudaMallocHost(&h_total, TRL_HOST_STREAMS * sizeof(unsigned long long))) != TRL_OK) return TRL_E_CUDA;
+    struct Pending { int off, m; uint16_t* d_list; bool live; } pend[TRL_HOST_STREAMS] = {};
     uint64_t base = 0;
     int rc = TRL_OK;
-    auto drain = [&](int h) -> int {   // chunk of half h: wait for its kernel + total, then fetch exactly `total` moves
+    // A ring of TRL_HOST_STREAMS chunks in flight: the H2D copies, the two kernels and the small D2H copies (offsets,
+    // counts, status, total) of a chunk are queued at once; its move list is fetched when the part is needed again
+    // (three chunks later), with exactly `total` entries, at its place in the caller's buffer.
+    auto drain = [&](int h) -> int {
         Pending& p = pend[h];
         if (!p.live) return TRL_OK;
         p.live = false;
@@ -366,22 +370,18 @@ extern "C" int trl_movegen_host_compact(const uint16_t* boards, const uint8_t* c
         const unsigned long long total = h_total[h];
         if (total > list_cap || base + total > capacity) return TRL_E_ARG;   // staging / caller buffer too small
         r = trl_check(cudaMemcpyAsync(moves_compact + base, p.d_list, (size_t)total * 2, cudaMemcpyDeviceToHost, st[h]));
-        if (!r) r = trl_check(cudaMemcpyAsync(offsets + p.off, p.d_offs, (size_t)p.m * 8, cudaMemcpyDeviceToHost, st[h]));
-        if (!r) r = trl_check(cudaMemcpyAsync(n_moves + p.off, p.d_nm, (size_t)p.m * 2, cudaMemcpyDeviceToHost, st[h]));
-        if (!r && status) r = trl_check(cudaMemcpyAsync(status + p.off, p.d_status, (size_t)p.m * 4, cudaMemcpyDeviceToHost, st[h]));
-        if (!r) r = trl_check(cudaStreamSynchronize(st[h]));
         if (r) return r;
-        for (int k = 0; k < p.m; ++k) offsets[p.off + k] += base;   // chunk-local -> global
+        for (int k = 0; k < p.m; ++k) offsets[p.off + k] += base;   // chunk-local -> global (under the copy)
         base += total;
-        return TRL_OK;
+        return trl_check(cudaStreamSynchronize(st[h]));
     };
     int c = 0;
     for (int off = 0; off < n && !rc; off += chunk, ++c) {
-        const int h = c & 1;
-        rc = drain(h);   // this half's previous chunk
+        const int h = c % TRL_HOST_STREAMS;
+        rc = drain(h);   // this part's previous chunk (chunks are drained in submission order, so `base` grows in chunk order)
         if (rc) break;
         const int m = (n - off < chunk) ? n - off : chunk;
-        char* p = ws + (size_t)h * half;
+        char* p = ws + (size_t)h * part;
         unsigned long long* d_total = (unsigned long long*)p; p += 64;
         unsigned long long* d_offs = (unsigned long long*)p; p += (size_t)m * 8;
         uint32_t* d_status = (uint32_t*)p; p += (size_t)m * 4;
@@ -398,11 +398,14 @@ extern "C" int trl_movegen_host_compact(const uint16_t* boards, const uint8_t* c
         if (!rc) rc = trl_launch_movegen_warp(d_boards, d_cur, d_alt, nullptr, nullptr, m, nullptr, nullptr, 0, d_nm, d_status, s,
                                               d_list, list_cap, d_total, d_offs);
         if (!rc) rc = trl_check(cudaMemcpyAsync(&h_total[h], d_total, 8, cudaMemcpyDeviceToHost, s));
-        if (!rc) pend[h] = {off, m, d_total, d_list, d_offs, d_nm, d_status, true};
+        if (!rc) rc = trl_check(cudaMemcpyAsync(offsets + off, d_offs, (size_t)m * 8, cudaMemcpyDeviceToHost, s));
+        if (!rc) rc = trl_check(cudaMemcpyAsync(n_moves + off, d_nm, (size_t)m * 2, cudaMemcpyDeviceToHost, s));
+        if (!rc && status) rc = trl_check(cudaMemcpyAsync(status + off, d_status, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+        if (!rc) pend[h] = {off, m, d_list, true};
     }
-    // drain in submission order so that `base` grows in chunk order
-    if (!rc) rc = drain(c & 1);
-    if (!rc) rc = drain((c + 1) & 1);
+    // the chunks still in flight, oldest first
+    for (int k = 0; k < TRL_HOST_STREAMS && !rc; ++k) rc = drain((c + k) % TRL_HOST_STREAMS);
+    if (rc) for (int k = 0; k < TRL_HOST_STREAMS; ++k) cudaStreamSynchronize(st[k]);
     *total_out = base;
     return rc;
 }

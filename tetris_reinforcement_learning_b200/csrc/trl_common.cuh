@@ -12,7 +12,8 @@ int trl_check(cudaError_t e);
 enum TrlWorkspaceSlot { TRL_WS_MOVEGEN_MASK = 0, TRL_WS_HOST_STAGE = 1, TRL_WS_TRUNK_COUNTER = 2, TRL_WS_TRUNK_COUNTER_TAPS = 3, TRL_WS_TRUNK_COUNTER_WIDE = 4, TRL_WS_SLOTS = 5 };
 void* trl_workspace(int slot, size_t bytes);
 
-// Streams (0 or 1) used by the *_host entry points (created on first use, non-blocking).
+// Streams (0 .. TRL_HOST_STREAMS - 1) used by the *_host entry points (created on first use, non-blocking).
+#define TRL_HOST_STREAMS 4
 cudaStream_t trl_host_stream(int which = 0);
 
 // Programmatic dependent launch (PDL).  A kernel launched with the attribute may become resident and run
