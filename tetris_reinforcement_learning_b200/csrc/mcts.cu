@@ -32,6 +32,15 @@ static_assert(sizeof(TrlSearchBuffers) == 272, "TrlSearchBuffers layout");
 static_assert(sizeof(TrlGameEnd) == 32, "TrlGameEnd layout");
 static_assert(sizeof(TrlSample) == 20 + 400 + 3 * 2 * TRL_SAMPLE_MOVES, "TrlSample layout");
 
+// Phase trace of the per-step kernel (builds with -DTRL_SEARCH_TRACE only; tools/search_trace.py): lane 0 of every
+// game's warp stamps clock64() into g_search_trace[game][phase].
+#ifdef TRL_SEARCH_TRACE
+__device__ long long* g_search_trace = nullptr;
+#define TRL_TRACE(g, lane, phase) do { if ((lane) == 0 && g_search_trace) g_search_trace[(size_t)(g) * 16 + (phase)] = clock64(); } while (0)
+#else
+#define TRL_TRACE(g, lane, phase) ((void)0)
+#endif
+
 __device__ __forceinline__ double negate_value(double v, bool tanh_mode) { return tanh_mode ? -v : 1.0 - v; }
 
 // Uniform double in [0,1): purpose 3 = playout-cap coin, 4 = move choice.
@@ -211,6 +220,7 @@ __device__ void select_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
     }
 
     if (path && lane == 0) path[0] = depth <= TRL_PATH_MAX_DEPTH ? depth : -1;
+    TRL_TRACE(g, lane, 9);   // selection walk
 
     // ---- materialise the leaf (ai.py:398-403) ----
     int s = s_leaf;
@@ -225,6 +235,7 @@ __device__ void select_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
         if (path && lane == 0 && depth <= TRL_PATH_MAX_DEPTH) path[32 + depth] = s;
         copy_game(sg, reinterpret_cast<const uint32_t*>(&B.states[sb + ps]), lane);
         __syncwarp();
+        TRL_TRACE(g, lane, 10);   // parent state in shared memory
         if (lane == 0) {
             trl_env_step_scalar(sgame, (int)B.move[nb + node], false, P.seed, 1u + ctl->search_no, &ctl->garbage_ctr);
             if (B.slot[nb + node] < 0) {
@@ -235,6 +246,7 @@ __device__ void select_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
             }
         }
         __syncwarp();
+        TRL_TRACE(g, lane, 11);   // env step
         copy_game(reinterpret_cast<uint32_t*>(&B.states[sb + s]), sg, lane);
     } else {
         copy_game(sg, reinterpret_cast<const uint32_t*>(&B.states[sb]), lane);
@@ -269,6 +281,7 @@ __device__ void select_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
     }
     leaf_si = __shfl_sync(kFull, leaf_si, 0);
     leaf_pi = __shfl_sync(kFull, leaf_pi, 0);
+    TRL_TRACE(g, lane, 12);   // leaf classified, work list entry
 }
 
 // Gating battles (ai.py:1975-2114): two networks with their own search settings; the one that owns the side to
@@ -486,6 +499,7 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
     if (pdepth >= 0 && path[1 + pdepth] != leaf) pdepth = -1;
     const int ls = pdepth >= 0 ? path[32 + pdepth] : B.slot[nb + leaf];
 
+    TRL_TRACE(g, lane, 1);   // control block and path loaded
     double value;
     if (kind == 2) {
         value = ctl->leaf_value;
@@ -518,6 +532,7 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
             C = 0;
             if (lane == 0) ctl->status |= TRL_ST_ARENA_FULL;
         }
+        TRL_TRACE(g, lane, 2);   // legal list located (cache lookup / store)
         if (C > 0) {
             // priors over the legal moves (ai.py:411-443).  softmax over all 11583 logits followed
             // by renormalisation over the legal ones == softmax over the legal logits.
@@ -532,6 +547,7 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
             }
             for (int c = lane + 128; c < C; c += 32) mx = fmax(mx, (double)load_logit(logits, lb, mv, c, dtype));
             mx = warp_max(mx);
+            TRL_TRACE(g, lane, 3);   // logits gathered
             const bool root_temp = (leaf == 0) && P.use_root_softmax;
             const double inv_temp = root_temp ? 1.0 / P.root_softmax_temp : 1.0;
             const int base = ctl->n_nodes;
@@ -546,6 +562,7 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
                 sum += e;
             }
             sum = warp_sum(sum);
+            TRL_TRACE(g, lane, 4);   // exp + first prior store
             const bool noisy = P.training && !ctl->fast && P.use_noise && leaf == 0;  // ai.py:482-499
             double alpha = P.dirichlet_alpha;
             if (noisy && P.use_dirichlet_s) alpha *= P.dirichlet_s / (double)C;
@@ -571,6 +588,7 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
         }
     }
     __syncwarp();
+    TRL_TRACE(g, lane, 5);   // children created
 
     // ---- backup (ai.py:511-533) ----
     if (pdepth >= 0) {
@@ -602,6 +620,7 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
         ctl->sims += 1;
     }
     __syncwarp();
+    TRL_TRACE(g, lane, 6);   // backup
 
     // ---- FPU refresh of the played-out node's unvisited siblings (ai.py:542-565) ----
     if (leaf != 0 && P.fpu_reduction) {
@@ -620,8 +639,10 @@ __device__ void expand_body(const TrlSearchBuffers& B, const TrlSearchParams& P,
         }
     }
     __syncwarp();
+    TRL_TRACE(g, lane, 7);   // FPU refresh
 
     if (ctl->iter >= ctl->max_iter) finish_search(B, P, g, lane, sgame);
+    TRL_TRACE(g, lane, 8);   // (end of search: move choice, record, real move)
 }
 
 template <bool BATTLE>
@@ -673,6 +694,7 @@ search_expand_select_encode_kernel(TrlSearchBuffers B, TrlSearchParams P, const 
     trl_grid_dep_wait();
     trl_grid_dep_launch();   // the next kernel (feature encoder / trunk) may move in as our blocks retire
     if (g >= B.n_games) return;
+    TRL_TRACE(g, lane, 0);
     int si, pi;
     int2 prow = make_int2(-1, -1);
     if (BATTLE) {
@@ -694,6 +716,7 @@ search_expand_select_encode_kernel(TrlSearchBuffers B, TrlSearchParams P, const 
     pos = __shfl_sync(kFull, pos, 0);
     const int inherit = (pi >= 0) ? ((s_game[wib].turn & 1) ? prow.y : prow.x) : -1;   // parent's cache row of the side to move
     trl_encode_cached_leaf(s_game[wib], g, si, pi, pos, lane, E, inherit);
+    TRL_TRACE(g, lane, 13);   // features encoded
 }
 
 // ---------------------------------------------------------------------------------------
@@ -795,6 +818,16 @@ extern "C" int trl_search_policy_legal(const TrlSearchBuffers* buf, const void* 
     return trl_launch_ex(policy_legal_kernel, dim3((buf->n_games + leaves_per_block - 1) / leaves_per_block), dim3(256), 0,
                          (cudaStream_t)stream, true, false, *buf, (const __nv_bfloat16*)x_bf16, k_pad, (const __nv_bfloat16*)w_bf16,
                          (const __nv_bfloat16*)bias_bf16, logits_legal);
+}
+
+// instrumented builds (-DTRL_SEARCH_TRACE): [n_games][16] clock64 stamps of the per-step kernel, or NULL to stop
+extern "C" int trl_debug_search_trace(long long* device_buffer) {
+#ifdef TRL_SEARCH_TRACE
+    return trl_check(cudaMemcpyToSymbol(g_search_trace, &device_buffer, sizeof(device_buffer)));
+#else
+    (void)device_buffer;
+    return TRL_E_ARG;
+#endif
 }
 
 extern "C" int trl_sizeof_search_ctl(void) { return (int)sizeof(TrlSearchCtl); }

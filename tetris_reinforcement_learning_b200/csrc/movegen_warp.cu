@@ -149,9 +149,52 @@ __device__ __forceinline__ int first_block_row(const uint16_t* rows, int lane) {
     return b0 ? (__ffs(b0) - 1) : (b1 ? 31 + __ffs(b1) : TRL_ROWS);
 }
 
+// Compile-time copy of the wall-kick table of the six non-I pieces (c_kicks[0], const.py:191-212) for the
+// specialised kick passes: with the kick offsets as immediates a kick test is LDS + SHF + 2 LOP3 + vote.
+struct KickList { int n; int k[6][2]; };
+constexpr KickList kWallKicks[4][3] = {
+    {{5, {{0, 0}, {-1, 0}, {-1, 1}, {0, -2}, {-1, -2}, {0, 0}}}, {6, {{0, 0}, {0, 1}, {1, 1}, {-1, 1}, {1, 0}, {-1, 0}}}, {5, {{0, 0}, {1, 0}, {1, 1}, {0, -2}, {1, -2}, {0, 0}}}},
+    {{5, {{0, 0}, {1, 0}, {1, -1}, {0, 2}, {1, 2}, {0, 0}}}, {6, {{0, 0}, {1, 0}, {1, 2}, {1, 1}, {0, 2}, {0, 1}}}, {5, {{0, 0}, {1, 0}, {1, -1}, {0, 2}, {1, 2}, {0, 0}}}},
+    {{5, {{0, 0}, {1, 0}, {1, 1}, {0, -2}, {1, -2}, {0, 0}}}, {6, {{0, 0}, {0, -1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}}}, {5, {{0, 0}, {-1, 0}, {-1, 1}, {0, -2}, {-1, -2}, {0, 0}}}},
+    {{5, {{0, 0}, {-1, 0}, {-1, -1}, {0, 2}, {-1, 2}, {0, 0}}}, {6, {{0, 0}, {-1, 0}, {-1, 2}, {-1, 1}, {0, 2}, {0, 1}}}, {5, {{0, 0}, {-1, 0}, {-1, -1}, {0, 2}, {-1, 2}, {0, 0}}}},
+};
+
+// One (source rotation R, direction KD) pass over the new edge cells `ne` of this lane's row, non-I pieces.
+template <int R, int KD, class St>
+__device__ __forceinline__ void kick_pass_wall(St& S, int lane, uint32_t ne, uint32_t VA, uint32_t VB, uint32_t& a0A, uint32_t& a0B, bool is_T) {
+    constexpr int nrot = (R + KD + 1) & 3;
+    constexpr KickList K = kWallKicks[R][KD];
+    // kick 0 is (0, 0) in every list (const.py:191-235): target = same cell of the new rotation
+    const uint32_t Vn = ((nrot & 2) ? VB : VA) >> (16 * (nrot & 1));
+    const uint32_t c0 = ne & Vn;
+    if (nrot & 2) a0B |= c0 << (16 * (nrot & 1)); else a0A |= c0 << (16 * (nrot & 1));
+    uint32_t rem = ne & ~c0;
+    if (!__any_sync(0xffffffffu, rem)) return;
+#pragma unroll
+    for (int ki = 1; ki < K.n; ++ki) {
+        const int kx = K.k[ki][0], ky = K.k[ki][1];
+        const uint32_t cand = rem & (S.vv[nrot][lane + 2 - ky] >> (kx + 2));   // source bit ex <-> target bit ex + kx
+        rem &= ~cand;
+        if (cand) {
+            uint32_t arr = kx >= 0 ? (cand << kx) : (cand >> -kx);
+            if (KD != 1 && ki == K.n - 1 && is_T) arr <<= 16;                  // nulk (:469)
+            atomicOr(&S.fu[nrot][lane + 2 - ky], arr);
+        }
+        if (ki + 1 < K.n && !__any_sync(0xffffffffu, rem)) return;              // every edge cell has found its kick
+    }
+}
+
+template <int R, class St>
+__device__ __forceinline__ void kick_passes_wall(St& S, int lane, uint32_t ne, uint32_t VA, uint32_t VB, uint32_t& a0A, uint32_t& a0B, bool is_T) {
+    kick_pass_wall<R, 0>(S, lane, ne, VA, VB, a0A, a0B, is_T);
+    kick_pass_wall<R, 1>(S, lane, ne, VA, VB, a0A, a0B, is_T);
+    kick_pass_wall<R, 2>(S, lane, ne, VA, VB, a0A, a0B, is_T);
+}
+
 // St: anything with uint32_t vv[4][>= kWinRows], fu[4][>= kWinRows] in shared memory.  The loops are kept
 // rolled on purpose: the kernels that call this are bound by instruction fetch, not by loop overhead.
-template <class St>
+// SPECIAL: kick passes of the non-I pieces with compile-time tables (the closure kernel; costs 11 KB of code).
+template <bool SPECIAL, class St>
 __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, int hi, int type, bool via_hold, uint32_t* mask) {
     const int lane = threadIdx.x & 31;
     const int sx = trl_spawn_x(type);
@@ -235,6 +278,15 @@ __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, i
             const uint32_t X = (r & 2) ? nB : nA;
             const uint32_t ne = (r & 1) ? (X >> 16) : (X & 0xFFFFu);
             if (!__any_sync(0xffffffffu, ne)) continue;
+            if (SPECIAL && tab == 0) {
+                switch (r) {
+                    case 0: kick_passes_wall<0>(S, lane, ne, VA, VB, a0A, a0B, is_T); break;
+                    case 1: kick_passes_wall<1>(S, lane, ne, VA, VB, a0A, a0B, is_T); break;
+                    case 2: kick_passes_wall<2>(S, lane, ne, VA, VB, a0A, a0B, is_T); break;
+                    default: kick_passes_wall<3>(S, lane, ne, VA, VB, a0A, a0B, is_T); break;
+                }
+                continue;
+            }
 #pragma unroll 1
             for (int kd = 0; kd < 3; ++kd) {
                 TRL_STAT(4);
@@ -326,7 +378,7 @@ __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, i
 
 // out-of-line copy for the kernels that also carry the FIFO form
 __device__ __noinline__ bool search_piece_rows_call(PieceState& S, const uint16_t* rows, int type, bool via_hold, uint32_t* mask) {
-    return search_piece_rows(S, rows, first_block_row(rows, threadIdx.x & 31), type, via_hold, mask);
+    return search_piece_rows<false>(S, rows, first_block_row(rows, threadIdx.x & 31), type, via_hold, mask);
 }
 
 // One piece type of one call, executed by one converged warp.
@@ -901,14 +953,23 @@ movegen_solo_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restri
 // Throughput form, two passes: the row-parallel closure search alone in a small kernel, then the exact
 // FIFO search for the few calls it could not decide.
 //
-// movegen_rows_kernel carries no FIFO code: 40 registers instead of 64 (48 resident warps per SM instead
+// movegen_rows_kernel carries no FIFO code: 48 registers instead of 64 (40 resident warps per SM instead
 // of 32), 2.8 KB of shared memory per warp, and a loop nest small enough to stay in the instruction caches
 // (the one-kernel forms lose a quarter of their issue slots to instruction fetch).  A call one of whose
 // piece searches returns "undecided" (mixed T-spin flags on a cell, or a climb out of the row window) is
 // appended to a list and produces no output here; movegen_solo_kernel in clean-up mode then handles
 // exactly those calls (T searches straight through the FIFO form).
 // ---------------------------------------------------------------------------------------
-constexpr int kRowsWarps = 4;
+#ifndef TRL_ROWS_SPECIAL
+#define TRL_ROWS_SPECIAL 1
+#endif
+#ifndef TRL_ROWS_WARPS
+#define TRL_ROWS_WARPS 4
+#endif
+#ifndef TRL_ROWS_MIN_BLOCKS
+#define TRL_ROWS_MIN_BLOCKS 10
+#endif
+constexpr int kRowsWarps = TRL_ROWS_WARPS;
 
 struct RowsState {
     uint32_t vv[4][kWinRows];
@@ -920,7 +981,7 @@ struct RowsWarp {
     CallState C;
 };
 
-__global__ void __launch_bounds__(kRowsWarps * 32, 12)
+__global__ void __launch_bounds__(kRowsWarps * 32, TRL_ROWS_MIN_BLOCKS)
 movegen_rows_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restrict__ cur,
                     const uint8_t* __restrict__ alt, const TrlGame* __restrict__ games,
                     const int32_t* __restrict__ index, int n, uint32_t* __restrict__ mask_bits,
@@ -946,7 +1007,7 @@ movegen_rows_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restri
         for (int which = 0; which < 2 && ok; ++which) {
             const int type = which ? a : c;
             if (type == TRL_NONE || (which && a == c)) continue;
-            ok = search_piece_rows(S.P, C.rows, hi, type, which != 0, C.mask);
+            ok = search_piece_rows<TRL_ROWS_SPECIAL != 0>(S.P, C.rows, hi, type, which != 0, C.mask);
             __syncwarp();
         }
         if (!ok) {

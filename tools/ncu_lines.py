@@ -22,7 +22,7 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def sass_lines(so, cubin_hint, kernel):
+def sass_lines(so, cubin_hint, kernel, want_len=-1):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
     out = []
@@ -31,7 +31,8 @@ def sass_lines(so, cubin_hint, kernel):
         if cubin_hint and not base.startswith(cubin_hint + "."):
             continue
         txt = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout
-        cur_fn, line, rows = None, None, []
+        cur_fn, line = None, None
+        fns = collections.OrderedDict()
         for ln in txt.splitlines():
             m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
             if m:
@@ -42,9 +43,10 @@ def sass_lines(so, cubin_hint, kernel):
                 line = (os.path.basename(m.group(1)), int(m.group(2)))
                 continue
             if cur_fn and kernel in cur_fn and re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S", ln):
-                rows.append((line, ln.split("*/", 1)[1].strip().rstrip(";")))
-        if rows:
-            out = rows
+                fns.setdefault(cur_fn, []).append((line, ln.split("*/", 1)[1].strip().rstrip(";")))
+        if fns:
+            # template instantiations: the one whose length matches the report, else the first
+            out = next((v for v in fns.values() if len(v) == want_len), next(iter(fns.values())))
             break
     return out
 
@@ -61,11 +63,15 @@ def main():
     raw = subprocess.run(["ncu", "-i", args.rep, "--page", "source", "--csv", "-k", "regex:" + args.kernel],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
-    hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    # the page lists every captured launch: "Kernel Name" row, header row, one row per SASS instruction
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    pick = next((i for i in starts if re.search(args.kernel, rows[i][1])), starts[0] if starts else -1)
+    end = next((i for i in starts if i > pick), len(rows))
+    hdr_i = next(i for i in range(pick, end) if rows[i] and rows[i][0] == "Address")
     hdr = rows[hdr_i]
     col = {h: i for i, h in enumerate(hdr)}
-    inst = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
-    sass = sass_lines(args.so, args.cubin, args.kernel)
+    inst = [r for r in rows[hdr_i + 1:end] if len(r) == len(hdr)]
+    sass = sass_lines(args.so, args.cubin, args.kernel, len(inst))
     if len(sass) != len(inst):
         print(f"warning: {len(sass)} SASS instructions in the .so vs {len(inst)} in the report (different build?)")
     n = min(len(sass), len(inst))
