@@ -25,7 +25,10 @@ void* trl_workspace(int slot, size_t bytes) {
     if (g_ws_ptr[slot]) { cudaFree(g_ws_ptr[slot]); g_ws_ptr[slot] = nullptr; g_ws_size[slot] = 0; }
     void* p = nullptr;
     if (trl_check(cudaMalloc(&p, bytes)) != TRL_OK) return nullptr;
-    if (trl_check(cudaMemset(p, 0, bytes)) != TRL_OK) { cudaFree(p); return nullptr; }   // counters start at zero
+    // counters start at zero.  cudaMemset runs on the legacy default stream, which the library's non-blocking
+    // streams do not wait for: without the synchronisation the memset can land AFTER the first H2D copy into
+    // the new buffer (seen as wrong answers for the first calls after a re-allocation).
+    if (trl_check(cudaMemset(p, 0, bytes)) != TRL_OK || trl_check(cudaDeviceSynchronize()) != TRL_OK) { cudaFree(p); return nullptr; }
     g_ws_ptr[slot] = p;
     g_ws_size[slot] = bytes;
     return p;

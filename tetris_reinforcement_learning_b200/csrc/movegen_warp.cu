@@ -254,7 +254,7 @@ __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, i
     uint32_t doneA = 0u, doneB = 0u;
     uint32_t a0A = 0u, a0B = 0u;   // arrivals by the in-place kick (0, 0): same lane, never the last kick
 #ifdef TRL_MOVEGEN_STATS
-    unsigned stat_2 = 0, stat_3 = 0, stat_4 = 0, stat_5 = 0;
+    unsigned stat_2 = 0, stat_3 = 0, stat_4 = 0, stat_5 = 0, stat_6 = 0, stat_7 = 0;
 #endif
     while (true) {
         TRL_STAT(2);
@@ -321,6 +321,14 @@ __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, i
         // arrivals seed the next fill (a target is always a valid cell; T: low half = flag clear, high = set)
         {
             const uint32_t f0 = S.fu[0][lane + 2], f1 = S.fu[1][lane + 2], f2 = S.fu[2][lane + 2], f3 = S.fu[3][lane + 2];
+#ifdef TRL_MOVEGEN_STATS
+            if (is_T && stat_2 == 1) {   // mixed flags on a stuck cell after the first round of kicks?
+                const uint32_t stA = VA & ~dA, stB = VB & ~dB;
+                const uint32_t mA = (((f0 | a0A) & (f0 >> 16)) & 0xFFFFu) | ((((f1 << 16) | a0A) & f1) & 0xFFFF0000u);
+                const uint32_t mB = (((f2 | a0B) & (f2 >> 16)) & 0xFFFFu) | ((((f3 << 16) | a0B) & f3) & 0xFFFF0000u);
+                if (__any_sync(0xffffffffu, (mA & stA) | (mB & stB))) stat_6 = 1;
+            }
+#endif
             RA |= a0A | ((f0 | (f0 >> 16)) & 0xFFFFu) | ((f1 | (f1 >> 16)) << 16);
             RB |= a0B | ((f2 | (f2 >> 16)) & 0xFFFFu) | ((f3 | (f3 >> 16)) << 16);
         }
@@ -329,6 +337,7 @@ __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, i
     if (lane == 0) {
         atomicAdd(&g_fast_stats[2], (unsigned long long)stat_2); atomicAdd(&g_fast_stats[3], (unsigned long long)stat_3);
         atomicAdd(&g_fast_stats[4], (unsigned long long)stat_4); atomicAdd(&g_fast_stats[5], (unsigned long long)stat_5);
+        atomicAdd(&g_fast_stats[6], (unsigned long long)stat_6);
     }
 #endif
     // rows above the window would be needed: hand over to the exact form
@@ -1154,8 +1163,13 @@ movegen_list_kernel(const TrlGame* __restrict__ games, const int32_t* __restrict
 static int g_list_rounds = 1;
 extern "C" void trl_search_movegen_rounds(int rounds) { g_list_rounds = rounds < 1 ? 1 : (rounds > 16 ? 16 : rounds); }
 
+// host-side shadows of the two debug switches (the launcher must not read device symbols: that would be a
+// synchronous copy on the legacy stream at every launch)
+static int g_fast_path_host = 1, g_fifo_limit_host = kFifoCap;
+
 extern "C" int trl_debug_movegen_fast_path(int on) {
     const int v = on ? 1 : 0;
+    g_fast_path_host = v;
     return trl_check(cudaMemcpyToSymbol(c_fast_path, &v, sizeof(int)));
 }
 
@@ -1175,6 +1189,7 @@ extern "C" int trl_debug_movegen_fast_stats(uint64_t* answered) {
 
 extern "C" int trl_debug_movegen_fifo_limit(int limit) {
     if (limit < 1 || limit > kFifoCap) limit = kFifoCap;
+    g_fifo_limit_host = limit;
     return trl_check(cudaMemcpyToSymbol(c_fifo_limit, &limit, sizeof(int)));
 }
 
@@ -1248,12 +1263,8 @@ int trl_launch_movegen_warp(const uint16_t* boards, const uint8_t* cur, const ui
     // the throughput forms once every SM is full of warps anyway (148 SMs x 32 resident warps = 4736 calls
     // in flight): below that the two-warp form halves the latency of a batch
     int form = g_form < 0 ? (n >= 3 * 4736 ? 2 : 0) : g_form;
-    int fast = 1, limit = kFifoCap;
-    if (form == 2) {   // the debug switches (FIFO form only / lowered FIFO capacity) are served by the one-kernel forms
-        if (cudaMemcpyFromSymbol(&fast, c_fast_path, sizeof(int)) != cudaSuccess ||
-            cudaMemcpyFromSymbol(&limit, c_fifo_limit, sizeof(int)) != cudaSuccess) { cudaGetLastError(); form = 1; }
-        if (!fast || limit != kFifoCap) form = 1;
-    }
+    // the debug switches (FIFO form only / lowered FIFO capacity) are served by the one-kernel forms
+    if (form == 2 && (!g_fast_path_host || g_fifo_limit_host != kFifoCap)) form = 1;
     uint32_t* scratch = form == 2 ? two_pass_scratch(stream, n) : nullptr;
     if (form == 2 && !scratch) form = 1;
     if (form == 2) {

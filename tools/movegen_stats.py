@@ -3,7 +3,7 @@ import numpy as np, torch
 sys.path.insert(0, os.getcwd())
 from tetris_reinforcement_learning_b200 import _native, move_generation, synth
 from tetris_reinforcement_learning_b200.const import MASK_WORDS
-L=_native.lib()
+L=_native.lib(); L.trl_movegen_warp_form(1)
 dev=torch.device("cuda:0")
 boards,cur,alt=synth.movegen_workload(20000)
 n=boards.shape[0]
@@ -21,4 +21,4 @@ for t in range(7):
     d_c2=torch.from_numpy(c).to(dev)
     move_generation.movegen_device(d_b,d_c2,d_c2,d_mask,None,d_n,d_st); torch.cuda.synchronize()
     L.trl_debug_movegen_fast_stats(st); s=[int(x) for x in st]; tot=s[0]+s[1]
-    print("piece",t,"searches",tot,"fallback %.3f%%"%(100*s[1]/tot),"rounds %.2f fill iters %.2f kd passes %.2f kick tests %.2f"%(s[2]/tot,s[3]/tot,s[4]/tot,s[5]/tot), "placements/search %.1f"%(float(d_n.to(torch.int64).sum())/n))
+    print("piece",t,"searches",tot,"fallback %.3f%%"%(100*s[1]/tot),"rounds %.2f fill iters %.2f kd passes %.2f kick tests %.2f"%(s[2]/tot,s[3]/tot,s[4]/tot,s[5]/tot), "placements/search %.1f"%(float(d_n.to(torch.int64).sum())/n), "mixed after round 1: %.3f%% of searches"%(100*s[6]/tot))
