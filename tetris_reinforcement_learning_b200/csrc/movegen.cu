@@ -286,6 +286,10 @@ int trl_movegen_indexed(const TrlGame* games, const int32_t* index, int n, uint1
     return launch_movegen(nullptr, nullptr, nullptr, games, index, n, nullptr, moves, moves_cap, n_moves, status, stream);
 }
 
+#ifndef TRL_HOST_CHUNK_LOG2
+#define TRL_HOST_CHUNK_LOG2 17   // calls per staging chunk of the *_host entry points
+#endif
+
 extern "C" int trl_movegen_host(const uint16_t* boards, const uint8_t* cur, const uint8_t* alt, int n,
                                 uint32_t* mask_bits, uint16_t* moves, int moves_cap, uint16_t* n_moves,
                                 uint32_t* status) {
@@ -293,7 +297,7 @@ extern "C" int trl_movegen_host(const uint16_t* boards, const uint8_t* cur, cons
     if (n == 0) return TRL_OK;
     // Chunked over a ring of TRL_HOST_STREAMS streams: with pinned host buffers the H2D / D2H copies of one chunk
     // overlap the kernels of the others; the staging workspace stays bounded for multi-million-call sweeps.
-    const int chunk = 1 << 17;
+    const int chunk = 1 << TRL_HOST_CHUNK_LOG2;
     const size_t per = TRL_ROWS * 2 + 2 + TRL_MASK_WORDS * 4 + (moves ? (size_t)moves_cap * 2 : 0) + 2 + 4;
     const int cmax = n < chunk ? n : chunk;
     const size_t part = (per * (size_t)cmax + 255) & ~(size_t)255;
@@ -344,7 +348,7 @@ extern "C" int trl_movegen_host_compact(const uint16_t* boards, const uint8_t* c
     if (n < 0 || !boards || !cur || !alt || !moves_compact || !offsets || !n_moves || !total_out) return TRL_E_ARG;
     *total_out = 0;
     if (n == 0) return TRL_OK;
-    const int chunk = 1 << 17;
+    const int chunk = 1 << TRL_HOST_CHUNK_LOG2;
     const size_t list_cap = (size_t)chunk * 160;   // per-chunk staging: 160 placements per call on average (x 2 B)
     const size_t per = TRL_ROWS * 2 + 2 + 8 + 2 + 4;
     const int cmax = n < chunk ? n : chunk;

@@ -46,6 +46,10 @@ def main():
         grids = (torch.rand((n, 1, 40, 10), device=dev) < 0.35).to(torch.bfloat16)
         wt = trunk_wide.WideTrunk(trunk_wide.pack_wide_trunk(net), dev)
         out = torch.empty((n, wt.row_elems), dtype=torch.bfloat16, device=dev)
+        from tetris_reinforcement_learning_b200 import _native
+        _native.lib().trl_debug_trunk_wide_l2_window(0)           # A/B: without the persisting-L2 window over the scratch
+        best0, _ = timed(lambda: wt(grids, out, n_images=n))
+        _native.lib().trl_debug_trunk_wide_l2_window(1)
         best, med = timed(lambda: wt(grids, out, n_images=n))
         wt.check()
         net16 = net.to(torch.bfloat16)
@@ -55,7 +59,7 @@ def main():
             net16 = net16.to(memory_format=torch.channels_last)
         with torch.no_grad():
             tb, tm = timed(lambda: ref(g2), reps=3, warm=1)
-        print(json.dumps({"net": f"{family}({blocks},{f})", "boards": n, "fused_ms_best": round(best, 3), "fused_ms_median": round(med, 3),
+        print(json.dumps({"net": f"{family}({blocks},{f})", "boards": n, "fused_ms_best": round(best, 3), "fused_ms_median": round(med, 3), "fused_ms_best_without_l2_window": round(best0, 3),
                           "fused_tflops": round(flops / best / 1e9, 1), "cudnn_ms_best": round(tb, 3), "speedup": round(tb / best, 1)}), flush=True)
 
 
