@@ -117,6 +117,13 @@ constexpr int kWinRows = 36;                      // lane + 2, two zero rows eit
 __constant__ int c_fast_path = 1;                 // trl_debug_movegen_fast_path(0) forces the FIFO form (tests run both)
 __device__ unsigned long long g_fast_stats[8];    // [0] searches answered by the closure form, [1] handed to the FIFO form;
                                                   // with -DTRL_MOVEGEN_STATS also [2] rounds, [3] fill iterations, [4] (rotation, direction) passes, [5] kick tests
+#ifdef TRL_T_TRACE
+// research build: per T search, the arrival planes of every (round, target rotation, direction) pass
+// (tools/t_order_study.py): [search][8 rounds][4 target rotations][3 directions][32 lanes] then [4][32] placed planes
+__device__ uint32_t* g_t_trace = nullptr;
+__device__ unsigned int g_t_trace_n = 0, g_t_trace_cap = 0;
+constexpr int kTTraceWords = 8 * 4 * 3 * 32 + 4 * 32 + 32;   // ... then the board (rows l | rows l+32 << 16)
+#endif
 #ifdef TRL_MOVEGEN_STATS
 #define TRL_STAT(i) (++stat_##i)
 #else
@@ -249,6 +256,19 @@ __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, i
     const uint32_t innerA = dA & (VA << 1) & (VA >> 1), innerB = dB & (VB << 1) & (VB >> 1);
     __syncwarp();
 
+#ifdef TRL_T_TRACE
+    uint32_t* ttrace = nullptr;
+    int tround = 0;
+    if (is_T && g_t_trace) {
+        unsigned slot_i = 0;
+        if (lane == 0) slot_i = atomicAdd(&g_t_trace_n, 1u);
+        slot_i = __shfl_sync(0xffffffffu, slot_i, 0);
+        if (slot_i < g_t_trace_cap) {
+            ttrace = g_t_trace + (size_t)slot_i * kTTraceWords;
+            for (int k = lane; k < kTTraceWords; k += 32) ttrace[k] = 0u;
+        }
+    }
+#endif
     const int tab = (type == P_I) ? 1 : 0;
     uint32_t RA = (lane == slane) ? (1u << (sx + 2)) : 0u, RB = 0u;
     uint32_t doneA = 0u, doneB = 0u;
@@ -291,6 +311,23 @@ __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, i
             for (int kd = 0; kd < 3; ++kd) {
                 TRL_STAT(4);
                 const int nrot = (r + kd + 1) & 3;
+#ifdef TRL_T_TRACE
+                uint32_t t_saved = 0u, t_a0A = a0A, t_a0B = a0B;
+                if (ttrace) { t_saved = S.fu[nrot][lane + 2]; S.fu[nrot][lane + 2] = 0u; a0A = 0u; a0B = 0u; __syncwarp(); }
+                struct TraceEnd {   // runs at every exit of this pass (continue / fall through)
+                    St& S; uint32_t* tt; int nrot, kd, lane, round; uint32_t saved, sA, sB; uint32_t &a0A, &a0B;
+                    __device__ ~TraceEnd() {
+                        if (!tt) return;
+                        __syncwarp();
+                        const uint32_t d = S.fu[nrot][lane + 2];
+                        const uint32_t k0 = (((nrot & 2) ? a0B : a0A) >> (16 * (nrot & 1))) & 0xFFFFu;
+                        if (round < 8) tt[((round * 4 + nrot) * 3 + kd) * 32 + lane] |= d | k0;
+                        S.fu[nrot][lane + 2] = saved | d;
+                        a0A |= sA; a0B |= sB;
+                        __syncwarp();
+                    }
+                } trace_end{S, ttrace, nrot, kd, lane, tround, t_saved, t_a0A, t_a0B, a0A, a0B};
+#endif
                 // kick 0 is (0, 0) in every list (const.py:191-235): target = same cell of the new rotation
                 const uint32_t Vn = ((nrot & 2) ? VB : VA) >> (16 * (nrot & 1));
                 const uint32_t c0 = ne & Vn;
@@ -317,6 +354,9 @@ __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, i
                 }
             }
         }
+#ifdef TRL_T_TRACE
+        ++tround;
+#endif
         __syncwarp();
         // arrivals seed the next fill (a target is always a valid cell; T: low half = flag clear, high = set)
         {
@@ -343,6 +383,13 @@ __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, i
     // rows above the window would be needed: hand over to the exact form
     if (__any_sync(0xffffffffu, lane < 2 && (RA | RB))) return false;
     const uint32_t placedA = RA & ~dA, placedB = RB & ~dB;
+#ifdef TRL_T_TRACE
+    if (ttrace) {
+        ttrace[8 * 4 * 3 * 32 + 0 * 32 + lane] = placedA & 0xFFFFu; ttrace[8 * 4 * 3 * 32 + 1 * 32 + lane] = placedA >> 16;
+        ttrace[8 * 4 * 3 * 32 + 2 * 32 + lane] = placedB & 0xFFFFu; ttrace[8 * 4 * 3 * 32 + 3 * 32 + lane] = placedB >> 16;
+        ttrace[8 * 4 * 3 * 32 + 4 * 32 + lane] = (uint32_t)rows[lane] | (lane < TRL_ROWS - 32 ? (uint32_t)rows[lane + 32] << 16 : 0u);
+    }
+#endif
     if (is_T) {
         bool mixed = false;
 #pragma unroll 1
@@ -1185,6 +1232,20 @@ extern "C" int trl_debug_movegen_fast_stats(uint64_t* answered) {
     for (int k = 2; k < 8; ++k) answered[k] = h[k];   // instrumented builds: the caller passes 8 words
 #endif
     return rc;
+}
+
+// research build (-DTRL_T_TRACE): device buffer of `cap` records of kTTraceWords words; returns the record size
+extern "C" int trl_debug_movegen_t_trace(uint32_t* device_buffer, unsigned cap) {
+#ifdef TRL_T_TRACE
+    unsigned zero = 0;
+    int rc = trl_check(cudaMemcpyToSymbol(g_t_trace, &device_buffer, sizeof(device_buffer)));
+    if (!rc) rc = trl_check(cudaMemcpyToSymbol(g_t_trace_cap, &cap, sizeof(cap)));
+    if (!rc) rc = trl_check(cudaMemcpyToSymbol(g_t_trace_n, &zero, sizeof(zero)));
+    return rc ? rc : kTTraceWords;
+#else
+    (void)device_buffer; (void)cap;
+    return TRL_E_ARG;
+#endif
 }
 
 extern "C" int trl_debug_movegen_fifo_limit(int limit) {
