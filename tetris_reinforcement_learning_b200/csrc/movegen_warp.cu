@@ -46,7 +46,13 @@ constexpr int kVRows = TRL_MAP_H + 2;     // rows 44, 45 stay 0: "below the map"
 struct PieceState {
     uint32_t vv[4][kVRows];
     uint32_t fu[4][kVRows];
-    uint16_t fifo[kFifoCap];
+    union {
+        uint16_t fifo[kFifoCap];                 // exact FIFO form
+        struct {                                  // closure form, T only (see t_order_decide)
+            uint32_t tsnap[4][32];                // arrivals of the first two kick rounds per (rotation, lane): N | U << 16
+            uint32_t tp[4][2][36];                // class planes of up to four kick passes: [pass][N_hi | U << 16, N_lo][row + 2]
+        };
+    };
 };
 
 struct CallState {
@@ -200,6 +206,174 @@ __device__ __forceinline__ void kick_passes_wall(St& S, int lane, uint32_t ne, u
 
 // St: anything with uint32_t vv[4][>= kWinRows], fu[4][>= kWinRows] in shared memory.  The loops are kept
 // rolled on purpose: the kernels that call this are bound by instruction fetch, not by loop overhead.
+// ---------------------------------------------------------------------------------------
+// T: which flag did the LAST rotation-flagged emission of a cell carry, when it received both?
+//
+// Called (out of line, by the 3 % of the searches that need it) after the closure search found a stuck cell with
+// arrivals of both flag values.  It replays the first two kick rounds with the arrivals separated by source and
+// decides from the structure of the reference's queue (move_generation.py:337-488):
+//   * level 0 is the start fill F0 (rotation 0).  Its edge cells push their kick targets in (row, column,
+//     direction) order, so the queue of level 1 starts with the targets e1, e2, e3 of the FIRST edge cell s* for
+//     rotations 1, 2, 3 (condition C1: all three exist);
+//   * level 1 therefore starts with the three fills B1, B2, B3 grown from e1, e2, e3, in that order.  If they cover
+//     everything level 1 reaches (C2: the closure of ei equals the rotation's whole reach after the second fill),
+//     no other fill happens in level 1 and the rest of its queue only emits;
+//   * so, for a stuck cell c of rotation R that was reached by then (c in F0 or B_R; not one of e1..e3), in time order:
+//       (a) arrivals from B_s found while c is already visited (R = 0, or s > R) are emitted at once, s ascending;
+//       (b) the arrivals pushed by F0 are popped afterwards;
+//       (c) arrivals from B_s with s < R were pushed and are popped in level 2, s ascending — interleaved, in an order
+//           this function does not know, with whatever later rounds emit at c;
+//     inside one (source fill, direction) the emissions follow the source cells' (row, column) order, i.e. a fixed
+//     priority of the kick indices: the used-last-kick arrival is the last one unless an arrival through a kick
+//     whose source lies later in the scan ("hi") exists.
+// Decided: no later-round arrival -> the last non-empty group of (c), (b), (a) in its known order; later-round
+// arrivals of ONE flag value and no other value in group (c) -> that value.  Everything else (also a failed C1 / C2,
+// cells reached later, the cells e1..e3) stays undecided and goes to the exact FIFO form.  Every search of the
+// BASELINE sweep and of the adversarial test boards is compared with the oracle, decided or not.
+// ---------------------------------------------------------------------------------------
+template <class St>
+__device__ __noinline__ bool t_order_decide(St& S, int lane, uint32_t VA, uint32_t VB, int slane, int sbit_index,
+                                            uint32_t placedA, uint32_t placedB, uint32_t a0A, uint32_t a0B, bool snapped,
+                                            uint32_t& ulkA, uint32_t& ulkB) {
+    constexpr unsigned kAll = 0xffffffffu;
+    const uint32_t PA1 = lane >= 1 ? VA : 0u, PB1 = lane >= 1 ? VB : 0u;
+    const uint32_t PA2 = PA1 & __shfl_up_sync(kAll, PA1, 1), PB2 = PB1 & __shfl_up_sync(kAll, PB1, 1);
+    const uint32_t PA4 = PA2 & __shfl_up_sync(kAll, PA2, 2), PB4 = PB2 & __shfl_up_sync(kAll, PB2, 2);
+    const uint32_t PA8 = PA4 & __shfl_up_sync(kAll, PA4, 4), PB8 = PB4 & __shfl_up_sync(kAll, PB4, 4);
+    const uint32_t PA16 = PA8 & __shfl_up_sync(kAll, PA8, 8), PB16 = PB8 & __shfl_up_sync(kAll, PB8, 8);
+    const uint32_t rVA = __brev(VA), rVB = __brev(VB);
+    uint32_t dA = __shfl_down_sync(kAll, VA, 1), dB = __shfl_down_sync(kAll, VB, 1);
+    if (lane == 31) { dA = 0u; dB = 0u; }
+    const uint32_t innerA = dA & (VA << 1) & (VA >> 1), innerB = dB & (VB << 1) & (VB >> 1);
+    auto fill = [&](uint32_t& A, uint32_t& B) {
+        while (true) {
+            const uint32_t a = hflood_r(A, VA, rVA), b = hflood_r(B, VB, rVB);
+            A = fall_scan(a, PA1, PA2, PA4, PA8, PA16);
+            B = fall_scan(b, PB1, PB2, PB4, PB8, PB16);
+            if (!__any_sync(kAll, (A ^ a) | (B ^ b))) break;
+        }
+    };
+    // one (source rotation s, direction kd) pass over the edge cells `ne`; arrivals by class into p0 = [N_hi | U << 16],
+    // p1 = [N_lo] (rows indexed lane + 2); optionally the target of the single source cell (seed_lane, seed_bit)
+    auto pass = [&](int s, int kd, uint32_t ne, uint32_t* p0, uint32_t* p1, int seed_lane, uint32_t seed_bit, int& hit_lane, uint32_t& hit_bit) {
+        const int nrot = (s + kd + 1) & 3;
+        const TrlKicks& K = c_kicks[0][s][kd];
+        const int kn = K.n;
+        const int lkx = K.k[kn - 1][0], lky = K.k[kn - 1][1];
+        uint32_t rem = ne;
+#pragma unroll 1
+        for (int ki = 0; ki < kn; ++ki) {
+            const int kx = K.k[ki][0], ky = K.k[ki][1];
+            const uint32_t cand = rem & (S.vv[nrot][lane + 2 - ky] >> (kx + 2));
+            rem &= ~cand;
+            const bool is_u = kd != 1 && ki == kn - 1;
+            const bool hi = kd != 1 && !is_u && (ky > lky || (ky == lky && kx < lkx));   // source later in the scan than the last kick's
+            if (cand) {
+                const uint32_t arr = kx >= 0 ? (cand << kx) : (cand >> -kx);
+                if (is_u) atomicOr(&p0[lane + 2 - ky], arr << 16);
+                else if (hi) atomicOr(&p0[lane + 2 - ky], arr);
+                else atomicOr(&p1[lane + 2 - ky], arr);
+            }
+            if (seed_bit) {
+                const bool hit = lane == seed_lane && (cand & seed_bit);
+                if (__any_sync(kAll, hit)) { hit_lane = seed_lane - ky; hit_bit = kx >= 0 ? (seed_bit << kx) : (seed_bit >> -kx); }
+            }
+            if (!__any_sync(kAll, rem)) break;
+        }
+    };
+    auto zero_planes = [&]() {
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            S.tp[q][0][lane + 2] = 0u; S.tp[q][1][lane + 2] = 0u;
+            if (lane < 4) { const int pad = lane < 2 ? lane : lane + 32; S.tp[q][0][pad] = 0u; S.tp[q][1][pad] = 0u; }
+        }
+        __syncwarp();
+    };
+
+    // later-round arrivals (rounds >= 2) per rotation of this lane's row: N | U << 16
+    uint32_t late[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        late[r] = snapped ? (S.fu[r][lane + 2] | ((((r & 2) ? a0B : a0A) >> (16 * (r & 1))) & 0xFFFFu)) : 0u;
+
+    // ---- level 0: F0, its edge cells, the first of them ----
+    uint32_t A0 = (lane == slane) ? (1u << sbit_index) : 0u, B0 = 0u;
+    fill(A0, B0);
+    const uint32_t F0 = A0 & 0xFFFFu;
+    const uint32_t e0 = F0 & ~innerA;
+    const uint32_t rows_with_edges = __ballot_sync(kAll, e0 != 0u);
+    if (!rows_with_edges) return false;
+    const int lstar = __ffs(rows_with_edges) - 1;
+    const uint32_t e0star = __shfl_sync(kAll, e0, lstar);
+    const uint32_t bstar = e0star & (0u - e0star);
+    // ---- round 0: the kicks of F0 (target rotation kd + 1), classes kept for group (b), targets of s* ----
+    zero_planes();
+    int seed_lane[3] = {-1, -1, -1};
+    uint32_t seed_bit[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) pass(0, kd, e0, S.tp[kd + 1][0], S.tp[kd + 1][1], lstar, bstar, seed_lane[kd], seed_bit[kd]);
+    __syncwarp();
+    if (!seed_bit[0] || !seed_bit[1] || !seed_bit[2]) return false;                     // C1
+    uint32_t e0w0[4] = {0u, 0u, 0u, 0u}, e0w1[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int r = 1; r < 4; ++r) { e0w0[r] = S.tp[r][0][lane + 2]; e0w1[r] = S.tp[r][1][lane + 2]; }
+    auto total = [](uint32_t w0, uint32_t w1) { return (w0 | (w0 >> 16) | w1) & 0xFFFFu; };
+    // ---- level 1: the second fill, and the fills grown from e1, e2, e3 alone ----
+    uint32_t A1 = A0 | (total(e0w0[1], e0w1[1]) << 16), B1 = total(e0w0[2], e0w1[2]) | (total(e0w0[3], e0w1[3]) << 16);
+    fill(A1, B1);
+    uint32_t SA = (lane == seed_lane[0]) ? (seed_bit[0] << 16) : 0u;
+    uint32_t SB = ((lane == seed_lane[1]) ? seed_bit[1] : 0u) | ((lane == seed_lane[2]) ? (seed_bit[2] << 16) : 0u);
+    fill(SA, SB);
+    if (__any_sync(kAll, ((SA ^ A1) & 0xFFFF0000u) | (SB ^ B1))) return false;          // C2
+    const uint32_t n1A = (A1 & ~innerA) & 0xFFFF0000u, n1B = B1 & ~innerB;              // edge cells of B1 | B2, B3
+    // ---- per target rotation: the kicks of B1..B3 into it, by source, and the decision ----
+    bool undecided = false;
+    uint32_t ulk[4];
+#pragma unroll 1
+    for (int R = 0; R < 4; ++R) {
+        zero_planes();
+#pragma unroll 1
+        for (int s = 1; s < 4; ++s) {
+            if (s == R) continue;
+            const int kd = (R - s - 1) & 3;
+            const uint32_t ne = (((s & 2) ? n1B : n1A) >> (16 * (s & 1))) & 0xFFFFu;
+            int hl = 0; uint32_t hb = 0u;
+            if (__any_sync(kAll, ne)) pass(s, kd, ne, S.tp[s][0], S.tp[s][1], 0, 0u, hl, hb);
+        }
+        __syncwarp();
+        const uint32_t placed = (((R & 2) ? placedB : placedA) >> (16 * (R & 1))) & 0xFFFFu;
+        const uint32_t early = R == 0 ? F0 : ((((R & 2) ? SB : SA) >> (16 * (R & 1))) & 0xFFFFu);
+        const uint32_t seed_cell = (R >= 1 && lane == seed_lane[R - 1]) ? seed_bit[R - 1] : 0u;
+        uint32_t q_any = 0u, q_n = 0u, q_u = 0u, q_win = 0u;      // group (c): pushed by B_s, s < R
+        uint32_t i_any = 0u, i_win = 0u;                          // group (a): emitted at once, s > R (all s for R = 0)
+        uint32_t all_n = late[R] & 0xFFFFu, all_u = late[R] >> 16;
+#pragma unroll
+        for (int s = 1; s < 4; ++s) {
+            const uint32_t w0 = S.tp[s][0][lane + 2], w1 = S.tp[s][1][lane + 2];
+            const uint32_t nhi = w0 & 0xFFFFu, u = w0 >> 16, nlo = w1 & 0xFFFFu;
+            const uint32_t any = nhi | u | nlo, win_u = u & ~nhi;
+            all_n |= nhi | nlo; all_u |= u;
+            if (R != 0 && s < R) { q_any |= any; q_n |= nhi | nlo; q_u |= u; q_win = (q_win & ~any) | win_u; }
+            else { i_any |= any; i_win = (i_win & ~any) | win_u; }
+        }
+        const uint32_t b_nhi = e0w0[R] & 0xFFFFu, b_u = e0w0[R] >> 16, b_nlo = e0w1[R] & 0xFFFFu;   // group (b)
+        const uint32_t b_any = b_nhi | b_u | b_nlo, b_win = b_u & ~b_nhi;
+        all_n |= b_nhi | b_nlo; all_u |= b_u;
+        const uint32_t l_n = late[R] & 0xFFFFu, l_u = late[R] >> 16, has_late = l_n | l_u;
+        const uint32_t early_win = (q_any & q_win) | (~q_any & ((b_any & b_win) | (~b_any & i_win)));
+        const uint32_t dec_u = (has_late & l_u & ~l_n & ~q_n) | (~has_late & early_win);
+        const uint32_t decided = (has_late & ((l_u & ~l_n & ~q_n) | (l_n & ~l_u & ~q_u))) | ~has_late;
+        const uint32_t mixed = all_n & all_u & placed;
+        if (mixed & ~(decided & early & ~seed_cell)) undecided = true;
+        ulk[R] = ((all_u & ~mixed) | (dec_u & mixed)) & 0xFFFFu;
+    }
+    if (__any_sync(kAll, undecided)) return false;
+    ulkA = ulk[0] | (ulk[1] << 16);
+    ulkB = ulk[2] | (ulk[3] << 16);
+    return true;
+}
+
 // SPECIAL: kick passes of the non-I pieces with compile-time tables (the closure kernel; costs 11 KB of code).
 template <bool SPECIAL, class St>
 __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, int hi, int type, bool via_hold, uint32_t* mask) {
@@ -273,6 +447,8 @@ __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, i
     uint32_t RA = (lane == slane) ? (1u << (sx + 2)) : 0u, RB = 0u;
     uint32_t doneA = 0u, doneB = 0u;
     uint32_t a0A = 0u, a0B = 0u;   // arrivals by the in-place kick (0, 0): same lane, never the last kick
+    int kick_rounds = 0;           // T: the arrivals of the first two kick rounds are set aside (t_order_decide)
+    bool snapped = false;
 #ifdef TRL_MOVEGEN_STATS
     unsigned stat_2 = 0, stat_3 = 0, stat_4 = 0, stat_5 = 0, stat_6 = 0, stat_7 = 0;
 #endif
@@ -371,6 +547,14 @@ __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, i
 #endif
             RA |= a0A | ((f0 | (f0 >> 16)) & 0xFFFFu) | ((f1 | (f1 >> 16)) << 16);
             RB |= a0B | ((f2 | (f2 >> 16)) & 0xFFFFu) | ((f3 | (f3 >> 16)) << 16);
+            if (is_T && ++kick_rounds == 2) {   // later rounds accumulate from zero
+                S.tsnap[0][lane] = f0 | (a0A & 0xFFFFu); S.tsnap[1][lane] = f1 | (a0A >> 16);
+                S.tsnap[2][lane] = f2 | (a0B & 0xFFFFu); S.tsnap[3][lane] = f3 | (a0B >> 16);
+                S.fu[0][lane + 2] = 0u; S.fu[1][lane + 2] = 0u; S.fu[2][lane + 2] = 0u; S.fu[3][lane + 2] = 0u;
+                a0A = 0u; a0B = 0u;
+                snapped = true;
+                __syncwarp();
+            }
         }
     }
 #ifdef TRL_MOVEGEN_STATS
@@ -390,16 +574,21 @@ __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, i
         ttrace[8 * 4 * 3 * 32 + 4 * 32 + lane] = (uint32_t)rows[lane] | (lane < TRL_ROWS - 32 ? (uint32_t)rows[lane + 32] << 16 : 0u);
     }
 #endif
+    uint32_t flagA = 0u, flagB = 0u, ulkA = 0u, ulkB = 0u;   // T: some flagged emission / the last one used the last kick
     if (is_T) {
-        bool mixed = false;
-#pragma unroll 1
+        uint32_t nA = a0A, nB = a0B, uA = 0u, uB = 0u;
+#pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const uint32_t fw = S.fu[r][lane + 2];
-            const uint32_t sel = ((r & 2) ? placedB : placedA) >> (16 * (r & 1));
-            const uint32_t a0 = ((r & 2) ? a0B : a0A) >> (16 * (r & 1));
-            mixed = mixed || ((fw | a0) & (fw >> 16) & sel & 0xFFFFu);
+            const uint32_t fw = S.fu[r][lane + 2] | (snapped ? S.tsnap[r][lane] : 0u);
+            const uint32_t n = (fw & 0xFFFFu) << (16 * (r & 1)), u = (fw >> 16) << (16 * (r & 1));
+            if (r & 2) { nB |= n; uB |= u; } else { nA |= n; uA |= u; }
         }
-        if (__any_sync(0xffffffffu, mixed)) return false;   // the order of emissions decides: exact form
+        flagA = nA | uA; flagB = nB | uB;
+        ulkA = uA; ulkB = uB;
+        if (__any_sync(0xffffffffu, (nA & uA & placedA) | (nB & uB & placedB))) {
+            // cells with both flag values: the order of emissions decides (:671-677)
+            if (!t_order_decide(S, lane, VA, VB, slane, sx + 2, placedA, placedB, a0A, a0B, snapped, ulkA, ulkB)) return false;
+        }
     }
     // ---- _convert_placements_to_policy (move_generation.py:650-749): lane = row ----
     const int pbase = c_plane_base[type];
@@ -420,9 +609,8 @@ __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, i
             if (!is_T) {
                 or_chunk(mask, pbase + rot % nrot_planes, row, bits & 0x7FFu);
             } else {
-                const uint32_t fw = S.fu[rot][lane + 2];
-                const uint32_t a0 = (((rot & 2) ? a0B : a0A) >> (16 * (rot & 1))) & 0xFFFFu;
-                const uint32_t f = (fw | (fw >> 16) | a0) & placed, u = fw >> 16;
+                const uint32_t f = (((rot & 2) ? flagB : flagA) >> (16 * (rot & 1))) & placed;
+                const uint32_t u = (((rot & 2) ? ulkB : ulkA) >> (16 * (rot & 1))) & 0xFFFFu;
                 or_chunk(mask, pbase + rot, row, (placed & ~f) & 0x7FFu);
                 or_chunk(mask, pbase + 4 + rot, row, (f & ~u) & 0x7FFu);
                 or_chunk(mask, pbase + 8 + rot, row, (f & u) & 0x7FFu);
@@ -1030,6 +1218,8 @@ constexpr int kRowsWarps = TRL_ROWS_WARPS;
 struct RowsState {
     uint32_t vv[4][kWinRows];
     uint32_t fu[4][kWinRows];
+    uint32_t tsnap[4][32];
+    uint32_t tp[4][2][36];
 };
 
 struct RowsWarp {
