@@ -121,7 +121,7 @@ __device__ __forceinline__ void flag_cell(uint32_t* fu_row, uint32_t bit, bool u
 constexpr int kWin0 = 12;   // validity row of lane 0
 constexpr int kWinRows = 36;                      // lane + 2, two zero rows either side
 __constant__ int c_fast_path = 1;                 // trl_debug_movegen_fast_path(0) forces the FIFO form (tests run both)
-__device__ unsigned long long g_fast_stats[8];    // [0] searches answered by the closure form, [1] handed to the FIFO form;
+__device__ unsigned long long g_fast_stats[16];    // [0] searches answered by the closure form, [1] handed to the FIFO form;
                                                   // with -DTRL_MOVEGEN_STATS also [2] rounds, [3] fill iterations, [4] (rotation, direction) passes, [5] kick tests
 #ifdef TRL_T_TRACE
 // research build: per T search, the arrival planes of every (round, target rotation, direction) pass
@@ -132,8 +132,10 @@ constexpr int kTTraceWords = 8 * 4 * 3 * 32 + 4 * 32 + 32;   // ... then the boa
 #endif
 #ifdef TRL_MOVEGEN_STATS
 #define TRL_STAT(i) (++stat_##i)
+#define TRL_REASON(i) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_fast_stats[i], 1ull); } while (0)
 #else
 #define TRL_STAT(i) ((void)0)
+#define TRL_REASON(i) ((void)0)
 #endif
 
 // R closed under "move one row down while the target is valid": P1..P16 are the propagate masks of
@@ -218,7 +220,9 @@ __device__ __forceinline__ void kick_passes_wall(St& S, int lane, uint32_t ne, u
 //   * level 1 therefore starts with the three fills B1, B2, B3 grown from e1, e2, e3, in that order.  If they cover
 //     everything level 1 reaches (C2: the closure of ei equals the rotation's whole reach after the second fill),
 //     no other fill happens in level 1 and the rest of its queue only emits;
-//   * so, for a stuck cell c of rotation R that was reached by then (c in F0 or B_R; not one of e1..e3), in time order:
+//   * a stuck cell c of rotation R that is reached only later is unvisited during the whole of level 1: everything B1, B2,
+//     B3 send there is pushed and popped in level 2 in push order (s ascending), group (c) below;
+//   * for a stuck cell c of rotation R that was reached by then (c in F0 or B_R; not one of e1..e3), in time order:
 //       (a) arrivals from B_s found while c is already visited (R = 0, or s > R) are emitted at once, s ascending;
 //       (b) the arrivals pushed by F0 are popped afterwards;
 //       (c) arrivals from B_s with s < R were pushed and are popped in level 2, s ascending — interleaved, in an order
@@ -228,13 +232,13 @@ __device__ __forceinline__ void kick_passes_wall(St& S, int lane, uint32_t ne, u
 //     whose source lies later in the scan ("hi") exists.
 // Decided: no later-round arrival -> the last non-empty group of (c), (b), (a) in its known order; later-round
 // arrivals of ONE flag value and no other value in group (c) -> that value.  Everything else (also a failed C1 / C2,
-// cells reached later, the cells e1..e3) stays undecided and goes to the exact FIFO form.  Every search of the
+// the cells e1..e3) stays undecided and goes to the exact FIFO form.  Every search of the
 // BASELINE sweep and of the adversarial test boards is compared with the oracle, decided or not.
 // ---------------------------------------------------------------------------------------
 template <class St>
 __device__ __noinline__ bool t_order_decide(St& S, int lane, uint32_t VA, uint32_t VB, int slane, int sbit_index,
                                             uint32_t placedA, uint32_t placedB, uint32_t a0A, uint32_t a0B, bool snapped,
-                                            uint32_t& ulkA, uint32_t& ulkB) {
+                                            uint32_t mixed_rots, uint32_t& ulkA, uint32_t& ulkB) {
     constexpr unsigned kAll = 0xffffffffu;
     const uint32_t PA1 = lane >= 1 ? VA : 0u, PB1 = lane >= 1 ? VB : 0u;
     const uint32_t PA2 = PA1 & __shfl_up_sync(kAll, PA1, 1), PB2 = PB1 & __shfl_up_sync(kAll, PB1, 1);
@@ -303,7 +307,7 @@ __device__ __noinline__ bool t_order_decide(St& S, int lane, uint32_t VA, uint32
     const uint32_t F0 = A0 & 0xFFFFu;
     const uint32_t e0 = F0 & ~innerA;
     const uint32_t rows_with_edges = __ballot_sync(kAll, e0 != 0u);
-    if (!rows_with_edges) return false;
+    if (!rows_with_edges) { TRL_REASON(8); return false; }
     const int lstar = __ffs(rows_with_edges) - 1;
     const uint32_t e0star = __shfl_sync(kAll, e0, lstar);
     const uint32_t bstar = e0star & (0u - e0star);
@@ -314,7 +318,7 @@ __device__ __noinline__ bool t_order_decide(St& S, int lane, uint32_t VA, uint32
 #pragma unroll
     for (int kd = 0; kd < 3; ++kd) pass(0, kd, e0, S.tp[kd + 1][0], S.tp[kd + 1][1], lstar, bstar, seed_lane[kd], seed_bit[kd]);
     __syncwarp();
-    if (!seed_bit[0] || !seed_bit[1] || !seed_bit[2]) return false;                     // C1
+    if (!seed_bit[0] || !seed_bit[1] || !seed_bit[2]) { TRL_REASON(9); return false; }   // C1
     uint32_t e0w0[4] = {0u, 0u, 0u, 0u}, e0w1[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int r = 1; r < 4; ++r) { e0w0[r] = S.tp[r][0][lane + 2]; e0w1[r] = S.tp[r][1][lane + 2]; }
@@ -325,13 +329,17 @@ __device__ __noinline__ bool t_order_decide(St& S, int lane, uint32_t VA, uint32
     uint32_t SA = (lane == seed_lane[0]) ? (seed_bit[0] << 16) : 0u;
     uint32_t SB = ((lane == seed_lane[1]) ? seed_bit[1] : 0u) | ((lane == seed_lane[2]) ? (seed_bit[2] << 16) : 0u);
     fill(SA, SB);
-    if (__any_sync(kAll, ((SA ^ A1) & 0xFFFF0000u) | (SB ^ B1))) return false;          // C2
+    if (__any_sync(kAll, ((SA ^ A1) & 0xFFFF0000u) | (SB ^ B1))) { TRL_REASON(10); return false; }   // C2
     const uint32_t n1A = (A1 & ~innerA) & 0xFFFF0000u, n1B = B1 & ~innerB;              // edge cells of B1 | B2, B3
     // ---- per target rotation: the kicks of B1..B3 into it, by source, and the decision ----
     bool undecided = false;
     uint32_t ulk[4];
 #pragma unroll 1
     for (int R = 0; R < 4; ++R) {
+        if (!((mixed_rots >> R) & 1u)) {   // no cell of this rotation needs a decision: its flags are the union of the arrivals
+            ulk[R] = (((R & 2) ? ulkB : ulkA) >> (16 * (R & 1))) & 0xFFFFu;
+            continue;
+        }
         zero_planes();
 #pragma unroll 1
         for (int s = 1; s < 4; ++s) {
@@ -347,6 +355,7 @@ __device__ __noinline__ bool t_order_decide(St& S, int lane, uint32_t VA, uint32
         const uint32_t seed_cell = (R >= 1 && lane == seed_lane[R - 1]) ? seed_bit[R - 1] : 0u;
         uint32_t q_any = 0u, q_n = 0u, q_u = 0u, q_win = 0u;      // group (c): pushed by B_s, s < R
         uint32_t i_any = 0u, i_win = 0u;                          // group (a): emitted at once, s > R (all s for R = 0)
+        uint32_t a_n = 0u, a_u = 0u, a_win = 0u;                  // cells reached later: every B_s pushes, s ascending
         uint32_t all_n = late[R] & 0xFFFFu, all_u = late[R] >> 16;
 #pragma unroll
         for (int s = 1; s < 4; ++s) {
@@ -354,6 +363,7 @@ __device__ __noinline__ bool t_order_decide(St& S, int lane, uint32_t VA, uint32
             const uint32_t nhi = w0 & 0xFFFFu, u = w0 >> 16, nlo = w1 & 0xFFFFu;
             const uint32_t any = nhi | u | nlo, win_u = u & ~nhi;
             all_n |= nhi | nlo; all_u |= u;
+            a_n |= nhi | nlo; a_u |= u; a_win = (a_win & ~any) | win_u;
             if (R != 0 && s < R) { q_any |= any; q_n |= nhi | nlo; q_u |= u; q_win = (q_win & ~any) | win_u; }
             else { i_any |= any; i_win = (i_win & ~any) | win_u; }
         }
@@ -361,14 +371,25 @@ __device__ __noinline__ bool t_order_decide(St& S, int lane, uint32_t VA, uint32
         const uint32_t b_any = b_nhi | b_u | b_nlo, b_win = b_u & ~b_nhi;
         all_n |= b_nhi | b_nlo; all_u |= b_u;
         const uint32_t l_n = late[R] & 0xFFFFu, l_u = late[R] >> 16, has_late = l_n | l_u;
+        // a cell reached only after level 1 (not in F0 / B_R; it cannot have an arrival from F0 then) is unvisited during the
+        // whole of level 1: everything B1..B3 send there is pushed and popped in level 2 in push order
         const uint32_t early_win = (q_any & q_win) | (~q_any & ((b_any & b_win) | (~b_any & i_win)));
-        const uint32_t dec_u = (has_late & l_u & ~l_n & ~q_n) | (~has_late & early_win);
-        const uint32_t decided = (has_late & ((l_u & ~l_n & ~q_n) | (l_n & ~l_u & ~q_u))) | ~has_late;
+        const uint32_t win = (early & early_win) | (~early & a_win);
+        const uint32_t qn = (early & q_n) | (~early & a_n), qu = (early & q_u) | (~early & a_u);
+        const uint32_t dec_u = (has_late & l_u & ~l_n & ~qn) | (~has_late & win);
+        const uint32_t decided = (has_late & ((l_u & ~l_n & ~qn) | (l_n & ~l_u & ~qu))) | ~has_late;
         const uint32_t mixed = all_n & all_u & placed;
-        if (mixed & ~(decided & early & ~seed_cell)) undecided = true;
+        const uint32_t suspect = seed_cell | (b_any & ~early);
+        if (mixed & ~(decided & ~suspect)) undecided = true;
+#ifdef TRL_MOVEGEN_STATS
+        if (__any_sync(kAll, mixed & ~early)) TRL_REASON(11);
+        if (__any_sync(kAll, mixed & suspect)) TRL_REASON(12);
+        if (__any_sync(kAll, mixed & ~suspect & ~decided)) TRL_REASON(13);
+#endif
         ulk[R] = ((all_u & ~mixed) | (dec_u & mixed)) & 0xFFFFu;
     }
-    if (__any_sync(kAll, undecided)) return false;
+    if (__any_sync(kAll, undecided)) { TRL_REASON(14); return false; }
+    TRL_REASON(15);
     ulkA = ulk[0] | (ulk[1] << 16);
     ulkB = ulk[2] | (ulk[3] << 16);
     return true;
@@ -585,9 +606,12 @@ __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, i
         }
         flagA = nA | uA; flagB = nB | uB;
         ulkA = uA; ulkB = uB;
-        if (__any_sync(0xffffffffu, (nA & uA & placedA) | (nB & uB & placedB))) {
+        const uint32_t mxA = nA & uA & placedA, mxB = nB & uB & placedB;
+        const uint32_t mixed_rots = (__any_sync(0xffffffffu, mxA & 0xFFFFu) ? 1u : 0u) | (__any_sync(0xffffffffu, mxA >> 16) ? 2u : 0u) |
+                                    (__any_sync(0xffffffffu, mxB & 0xFFFFu) ? 4u : 0u) | (__any_sync(0xffffffffu, mxB >> 16) ? 8u : 0u);
+        if (mixed_rots) {
             // cells with both flag values: the order of emissions decides (:671-677)
-            if (!t_order_decide(S, lane, VA, VB, slane, sx + 2, placedA, placedB, a0A, a0B, snapped, ulkA, ulkB)) return false;
+            if (!t_order_decide(S, lane, VA, VB, slane, sx + 2, placedA, placedB, a0A, a0B, snapped, mixed_rots, ulkA, ulkB)) return false;
         }
     }
     // ---- _convert_placements_to_policy (move_generation.py:650-749): lane = row ----
@@ -1414,12 +1438,12 @@ extern "C" int trl_debug_movegen_fast_path(int on) {
 // form, since the last call (the counters are reset)
 extern "C" int trl_debug_movegen_fast_stats(uint64_t* answered) {
     if (!answered) return TRL_E_ARG;
-    unsigned long long h[8] = {0}, z[8] = {0};
+    unsigned long long h[16] = {0}, z[16] = {0};
     int rc = trl_check(cudaMemcpyFromSymbol(h, g_fast_stats, sizeof(h)));
     if (!rc) rc = trl_check(cudaMemcpyToSymbol(g_fast_stats, z, sizeof(z)));
     answered[0] = h[0]; answered[1] = h[1];
 #ifdef TRL_MOVEGEN_STATS
-    for (int k = 2; k < 8; ++k) answered[k] = h[k];   // instrumented builds: the caller passes 8 words
+    for (int k = 2; k < 16; ++k) answered[k] = h[k];   // instrumented builds: the caller passes 16 words
 #endif
     return rc;
 }
