@@ -30,6 +30,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "trl_common.cuh"
 #include "trl_tables.cuh"
 
@@ -1496,7 +1498,10 @@ extern "C" void trl_movegen_warp_form(int form) { g_form = form; }
 struct TwoPassScratch { cudaStream_t stream; uint32_t* buf; size_t cap; bool used; };
 static TwoPassScratch g_scratch[8];
 
+static std::mutex g_scratch_mutex;   // device entry points are re-entrant per stream: the table is shared
+
 static uint32_t* two_pass_scratch(cudaStream_t stream, int n) {
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
     TwoPassScratch* slot = nullptr;
     for (auto& e : g_scratch) if (e.used && e.stream == stream) { slot = &e; break; }
     if (!slot) for (auto& e : g_scratch) if (!e.used) { slot = &e; e.used = true; e.stream = stream; e.buf = nullptr; e.cap = 0; break; }

@@ -1,3 +1,4 @@
+"""Repro of a race found in round 2 (fixed in capi.cu: cudaMemset on the legacy stream vs. the first H2D copy on a non-blocking stream after the host workspace is re-allocated): host and compact entry points against the oracle, all launch forms."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.getcwd())
