@@ -13,7 +13,9 @@ enum TrlWorkspaceSlot { TRL_WS_MOVEGEN_MASK = 0, TRL_WS_HOST_STAGE = 1, TRL_WS_T
 void* trl_workspace(int slot, size_t bytes);
 
 // Streams (0 .. TRL_HOST_STREAMS - 1) used by the *_host entry points (created on first use, non-blocking).
+#ifndef TRL_HOST_STREAMS
 #define TRL_HOST_STREAMS 4
+#endif
 cudaStream_t trl_host_stream(int which = 0);
 
 // Programmatic dependent launch (PDL).  A kernel launched with the attribute may become resident and run

@@ -31,9 +31,10 @@ if what.startswith("movegen"):
     d_n = torch.zeros(nc, dtype=torch.int16, device=dev)
     d_st = torch.zeros(nc, dtype=torch.int32, device=dev)
     _native.lib().trl_movegen_select_kernel(0 if what == "movegen_thread" else 1)
-    _native.lib().trl_movegen_warp_form({"movegen_warp2": 0, "movegen_solo": 1, "movegen_rows": 2}.get(what, -1))
+    _native.lib().trl_movegen_warp_form({"movegen_warp2": 0, "movegen_solo": 1, "movegen_rows": 2, "movegen_rows_list": 2}.get(what, -1))
+    d_moves = torch.zeros((nc, 128), dtype=torch.int16, device=dev) if what.endswith("_list") else None
     for _ in range(3):
-        move_generation.movegen_device(d_boards, d_cur, d_alt, d_mask, None, d_n, d_st)
+        move_generation.movegen_device(d_boards, d_cur, d_alt, None if d_moves is not None else d_mask, d_moves, d_n, d_st)
     torch.cuda.synchronize()
     print(what, "calls", nc, "placements", int(d_n.to(torch.int64).sum()), "status", int((d_st != 0).sum()))
 elif what.startswith("wide"):
