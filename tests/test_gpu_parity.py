@@ -147,6 +147,40 @@ def test_movegen_kernels_agree_on_adversarial_boards():
     assert int(t_planes.sum()) > 1000
 
 
+def test_closure_search_answers_most_searches():
+    """Regression guard for the throughput form: on the BASELINE config-2 boards the row-parallel closure search must
+    answer all non-T searches and, with the emission-order analysis, at least 85 % of the T searches itself (the rest
+    goes to the exact FIFO form; measured 100 % / 90.5 %).  Outputs are compared with the oracle by the tests around
+    this one; here only the split is checked."""
+    import ctypes
+    import torch
+    from tetris_reinforcement_learning_b200 import _native, move_generation
+    L = _native.lib()
+    boards, _, _ = synth.movegen_workload(20000)
+    boards = np.ascontiguousarray(boards[::7])
+    dev = torch.device("cuda:0")
+    d_b = torch.from_numpy(boards.view(np.int16)).to(dev)
+    n = boards.shape[0]
+    d_n = torch.zeros(n, dtype=torch.int16, device=dev)
+    d_mask = torch.zeros((n, MASK_WORDS), dtype=torch.int32, device=dev)
+    st = (ctypes.c_uint64 * 16)()
+    try:
+        L.trl_movegen_select_kernel(1)
+        L.trl_movegen_warp_form(1)          # the one-kernel form counts both outcomes
+        for piece, floor in ((1, 1.0), (4, 1.0), (6, 0.85)):
+            d_c = torch.full((n,), piece, dtype=torch.uint8, device=dev)
+            assert L.trl_debug_movegen_fast_stats(st) == 0      # reset
+            move_generation.movegen_device(d_b, d_c, d_c, d_mask, None, d_n, None)
+            torch.cuda.synchronize()
+            assert L.trl_debug_movegen_fast_stats(st) == 0
+            closure, fifo = int(st[0]), int(st[1])
+            assert closure + fifo == n
+            assert closure >= floor * n, (piece, closure, fifo)
+    finally:
+        L.trl_movegen_select_kernel(-1)
+        L.trl_movegen_warp_form(-1)
+
+
 def test_movegen_edge_cases(mg, oracle):
     rows = np.zeros((6, 40), np.uint16)
     rows[1, :] = 0x3FF & ~1            # everything full except column 0: topped out
