@@ -122,6 +122,12 @@ __device__ __forceinline__ void flag_cell(uint32_t* fu_row, uint32_t bit, bool u
 // above the window are not represented).  Counted in g_fast_stats: 24 % of the T searches, 0 of the others,
 // on the BASELINE config-2 boards.
 // ---------------------------------------------------------------------------------------
+#ifndef TRL_ROWS_SPECIAL_I
+#define TRL_ROWS_SPECIAL_I 0   // closure kernel: compile-time kick tables for the I piece too: measured SLOWER (4.63 vs 4.12 ms per 700 k calls: the code outgrows the instruction cache)
+#endif
+#ifndef TRL_ROWS_SPECIAL_V
+#define TRL_ROWS_SPECIAL_V 1   // closure kernel: validity rows with compile-time cell offsets (A/B switch)
+#endif
 constexpr int kWin0 = 12;   // validity row of lane 0
 constexpr int kWinRows = 36;                      // lane + 2, two zero rows either side
 __constant__ int c_fast_path = 1;                 // trl_debug_movegen_fast_path(0) forces the FIFO form (tests run both)
@@ -178,11 +184,20 @@ constexpr KickList kWallKicks[4][3] = {
     {{5, {{0, 0}, {-1, 0}, {-1, -1}, {0, 2}, {-1, 2}, {0, 0}}}, {6, {{0, 0}, {-1, 0}, {-1, 2}, {-1, 1}, {0, 2}, {0, 1}}}, {5, {{0, 0}, {-1, 0}, {-1, -1}, {0, 2}, {-1, 2}, {0, 0}}}},
 };
 
-// One (source rotation R, direction KD) pass over the new edge cells `ne` of this lane's row, non-I pieces.
-template <int R, int KD, class St>
+// ... and of the I piece (c_kicks[1], const.py:214-235)
+constexpr KickList kIKicks[4][3] = {
+    {{5, {{0, 0}, {-2, 0}, {1, 0}, {-2, -1}, {1, 2}, {0, 0}}}, {2, {{0, 0}, {0, 1}, {0, 0}, {0, 0}, {0, 0}, {0, 0}}}, {5, {{0, 0}, {-1, 0}, {2, 0}, {-1, 2}, {2, -1}, {0, 0}}}},
+    {{5, {{0, 0}, {-1, 0}, {2, 0}, {-1, 2}, {2, -1}, {0, 0}}}, {2, {{0, 0}, {1, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}}}, {5, {{0, 0}, {2, 0}, {-1, 0}, {2, 1}, {-1, -2}, {0, 0}}}},
+    {{5, {{0, 0}, {2, 0}, {-1, 0}, {2, 1}, {-1, -2}, {0, 0}}}, {2, {{0, 0}, {0, -1}, {0, 0}, {0, 0}, {0, 0}, {0, 0}}}, {5, {{0, 0}, {1, 0}, {-2, 0}, {1, -2}, {-2, 1}, {0, 0}}}},
+    {{5, {{0, 0}, {1, 0}, {-2, 0}, {1, -2}, {-2, 1}, {0, 0}}}, {2, {{0, 0}, {-1, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}}}, {5, {{0, 0}, {-2, 0}, {1, 0}, {-2, -1}, {1, 2}, {0, 0}}}},
+};
+
+// One (source rotation R, direction KD) pass over the new edge cells `ne` of this lane's row; TAB 0 = the six pieces
+// with the common wall-kick table, 1 = the I piece.
+template <int TAB, int R, int KD, class St>
 __device__ __forceinline__ void kick_pass_wall(St& S, int lane, uint32_t ne, uint32_t VA, uint32_t VB, uint32_t& a0A, uint32_t& a0B, bool is_T) {
     constexpr int nrot = (R + KD + 1) & 3;
-    constexpr KickList K = kWallKicks[R][KD];
+    constexpr KickList K = TAB ? kIKicks[R][KD] : kWallKicks[R][KD];
     // kick 0 is (0, 0) in every list (const.py:191-235): target = same cell of the new rotation
     const uint32_t Vn = ((nrot & 2) ? VB : VA) >> (16 * (nrot & 1));
     const uint32_t c0 = ne & Vn;
@@ -203,11 +218,11 @@ __device__ __forceinline__ void kick_pass_wall(St& S, int lane, uint32_t ne, uin
     }
 }
 
-template <int R, class St>
+template <int TAB, int R, class St>
 __device__ __forceinline__ void kick_passes_wall(St& S, int lane, uint32_t ne, uint32_t VA, uint32_t VB, uint32_t& a0A, uint32_t& a0B, bool is_T) {
-    kick_pass_wall<R, 0>(S, lane, ne, VA, VB, a0A, a0B, is_T);
-    kick_pass_wall<R, 1>(S, lane, ne, VA, VB, a0A, a0B, is_T);
-    kick_pass_wall<R, 2>(S, lane, ne, VA, VB, a0A, a0B, is_T);
+    kick_pass_wall<TAB, R, 0>(S, lane, ne, VA, VB, a0A, a0B, is_T);
+    kick_pass_wall<TAB, R, 1>(S, lane, ne, VA, VB, a0A, a0B, is_T);
+    kick_pass_wall<TAB, R, 2>(S, lane, ne, VA, VB, a0A, a0B, is_T);
 }
 
 // St: anything with uint32_t vv[4][>= kWinRows], fu[4][>= kWinRows] in shared memory.  The loops are kept
@@ -399,6 +414,34 @@ __device__ __noinline__ bool t_order_decide(St& S, int lane, uint32_t VA, uint32
     return true;
 }
 
+// Compile-time copy of c_minos (const.py:238-281) for the specialised validity rows: with the cell offsets as
+// immediates a validity row is 4 x (SHF + LOP3) instead of 50 instructions of nibble extraction and selects.
+constexpr uint32_t kMinos[7][4] = {
+    {TRL_PK(0, 0, 1, 0, 1, 1, 2, 1), TRL_PK(1, 1, 1, 2, 2, 0, 2, 1), TRL_PK(0, 1, 1, 1, 1, 2, 2, 2), TRL_PK(0, 1, 0, 2, 1, 0, 1, 1)},
+    {TRL_PK(0, 1, 1, 1, 2, 0, 2, 1), TRL_PK(1, 0, 1, 1, 1, 2, 2, 2), TRL_PK(0, 1, 0, 2, 1, 1, 2, 1), TRL_PK(0, 0, 1, 0, 1, 1, 1, 2)},
+    {TRL_PK(0, 0, 0, 1, 1, 0, 1, 1), TRL_PK(0, 0, 0, 1, 1, 0, 1, 1), TRL_PK(0, 0, 0, 1, 1, 0, 1, 1), TRL_PK(0, 0, 0, 1, 1, 0, 1, 1)},
+    {TRL_PK(0, 1, 1, 0, 1, 1, 2, 0), TRL_PK(1, 0, 1, 1, 2, 1, 2, 2), TRL_PK(0, 2, 1, 1, 1, 2, 2, 1), TRL_PK(0, 0, 0, 1, 1, 1, 1, 2)},
+    {TRL_PK(0, 1, 1, 1, 2, 1, 3, 1), TRL_PK(2, 0, 2, 1, 2, 2, 2, 3), TRL_PK(0, 2, 1, 2, 2, 2, 3, 2), TRL_PK(1, 0, 1, 1, 1, 2, 1, 3)},
+    {TRL_PK(0, 0, 0, 1, 1, 1, 2, 1), TRL_PK(1, 0, 1, 1, 1, 2, 2, 0), TRL_PK(0, 1, 1, 1, 2, 1, 2, 2), TRL_PK(0, 2, 1, 0, 1, 1, 1, 2)},
+    {TRL_PK(0, 1, 1, 0, 1, 1, 2, 1), TRL_PK(1, 0, 1, 1, 1, 2, 2, 1), TRL_PK(0, 1, 1, 1, 1, 2, 2, 1), TRL_PK(0, 1, 1, 0, 1, 1, 1, 2)},
+};
+
+template <int TYPE, int R>
+__device__ __forceinline__ uint32_t validity_row(const uint32_t (&e)[4]) {
+    constexpr uint32_t mm = kMinos[TYPE][R];
+    constexpr int c0 = mm & 15, r0 = (mm >> 4) & 15, c1 = (mm >> 8) & 15, r1 = (mm >> 12) & 15;
+    constexpr int c2 = (mm >> 16) & 15, r2 = (mm >> 20) & 15, c3 = (mm >> 24) & 15, r3 = (mm >> 28) & 15;
+    return 0x3FFFu & (e[r0] >> c0) & (e[r1] >> c1) & (e[r2] >> c2) & (e[r3] >> c3);
+}
+
+template <int TYPE>
+__device__ __forceinline__ void validity_rows(const uint32_t (&e)[4], uint32_t (&v)[4]) {
+    v[0] = validity_row<TYPE, 0>(e);
+    v[1] = validity_row<TYPE, 1>(e);
+    v[2] = validity_row<TYPE, 2>(e);
+    v[3] = validity_row<TYPE, 3>(e);
+}
+
 // SPECIAL: kick passes of the non-I pieces with compile-time tables (the closure kernel; costs 11 KB of code).
 template <bool SPECIAL, class St>
 __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, int hi, int type, bool via_hold, uint32_t* mask) {
@@ -411,6 +454,27 @@ __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, i
 #pragma unroll
     for (int k = 0; k < 4; ++k) e[k] = trl_empty_row(rows, my - 2 + k) << 2;
     uint32_t VA = 0u, VB = 0u;
+    if (SPECIAL && TRL_ROWS_SPECIAL_V) {
+        uint32_t v[4];
+        switch (type) {
+            case 0: validity_rows<0>(e, v); break;
+            case 1: validity_rows<1>(e, v); break;
+            case 2: validity_rows<2>(e, v); break;
+            case 3: validity_rows<3>(e, v); break;
+            case 4: validity_rows<4>(e, v); break;
+            case 5: validity_rows<5>(e, v); break;
+            default: validity_rows<6>(e, v); break;
+        }
+        const int pad = lane < 2 ? lane : lane + 32;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            S.vv[r][lane + 2] = v[r] << 2;
+            S.fu[r][lane + 2] = 0u;
+            if (lane < 4) { S.vv[r][pad] = 0u; S.fu[r][pad] = 0u; }
+        }
+        VA = v[0] | (v[1] << 16);
+        VB = v[2] | (v[3] << 16);
+    } else {
 #pragma unroll 1
     for (int r = 0; r < 4; ++r) {
         const uint32_t m4 = c_minos[type][r];
@@ -432,6 +496,7 @@ __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, i
         }
         const uint32_t sh = acc << (16 * (r & 1));
         if (r & 2) VB |= sh; else VA |= sh;
+    }
     }
     // Player.hold_piece -> create_piece spawn test (player.py:37-44, move_generation.py:112-121): the spawn
     // cell (sx, 17) is validity row 19 = lane 7 of rotation 0
@@ -501,10 +566,19 @@ __device__ __forceinline__ bool search_piece_rows(St& S, const uint16_t* rows, i
             if (!__any_sync(0xffffffffu, ne)) continue;
             if (SPECIAL && tab == 0) {
                 switch (r) {
-                    case 0: kick_passes_wall<0>(S, lane, ne, VA, VB, a0A, a0B, is_T); break;
-                    case 1: kick_passes_wall<1>(S, lane, ne, VA, VB, a0A, a0B, is_T); break;
-                    case 2: kick_passes_wall<2>(S, lane, ne, VA, VB, a0A, a0B, is_T); break;
-                    default: kick_passes_wall<3>(S, lane, ne, VA, VB, a0A, a0B, is_T); break;
+                    case 0: kick_passes_wall<0, 0>(S, lane, ne, VA, VB, a0A, a0B, is_T); break;
+                    case 1: kick_passes_wall<0, 1>(S, lane, ne, VA, VB, a0A, a0B, is_T); break;
+                    case 2: kick_passes_wall<0, 2>(S, lane, ne, VA, VB, a0A, a0B, is_T); break;
+                    default: kick_passes_wall<0, 3>(S, lane, ne, VA, VB, a0A, a0B, is_T); break;
+                }
+                continue;
+            }
+            if (SPECIAL && TRL_ROWS_SPECIAL_I) {
+                switch (r) {
+                    case 0: kick_passes_wall<1, 0>(S, lane, ne, VA, VB, a0A, a0B, false); break;
+                    case 1: kick_passes_wall<1, 1>(S, lane, ne, VA, VB, a0A, a0B, false); break;
+                    case 2: kick_passes_wall<1, 2>(S, lane, ne, VA, VB, a0A, a0B, false); break;
+                    default: kick_passes_wall<1, 3>(S, lane, ne, VA, VB, a0A, a0B, false); break;
                 }
                 continue;
             }
