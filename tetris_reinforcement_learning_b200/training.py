@@ -244,6 +244,21 @@ def _check_threshold(wins, games, threshold, threshold_type):
     return None
 
 
+def tally_battle_results(results):
+    """Win counts of a gating battle from (winner, side) pairs — winner: 0 / 1 = the player that won, -1 = draw; side = the
+    player network 1 controlled (game i plays side i % 2, reference ai.py:2087-2091).  Tally as ai.py:2103-2113: a draw
+    is half a win for both, otherwise the win goes to the network that controlled the winning player."""
+    wins = np.zeros(2, dtype=float)
+    for w, s in results:
+        if w == -1:
+            wins += 0.5
+        elif s == 0:
+            wins[w] += 1
+        else:
+            wins[1 - w] += 1
+    return wins
+
+
 class DualCachedEvaluator:
     """Engine evaluator of a gating battle: two networks, each with its cached-trunk evaluator (trunk.CachedTrunkEvaluator /
     trunk_wide.CachedWideEvaluator).  Every leaf goes through ONE network, the one that owns the running search of its
@@ -377,14 +392,5 @@ def battle_networks(NN_1, config_1, NN_2, config_2, threshold, threshold_type, g
         eng.step(chunk)
         ends.extend(eng.drain()[1])
         eng.check_status(ignore=0x20)        # sample records are not read here: a full sample ring is harmless
-    wins = np.zeros(2, dtype=float)
-    for e in ends:
-        s = int(e["game_id"]) % 2
-        w = int(e["winner"])
-        if w == -1:
-            wins += 0.5
-        elif s == 0:
-            wins[w] += 1
-        else:
-            wins[1 - w] += 1
+    wins = tally_battle_results((int(e["winner"]), int(e["game_id"]) % 2) for e in ends)
     return wins, _check_threshold(wins, games, threshold, threshold_type)
