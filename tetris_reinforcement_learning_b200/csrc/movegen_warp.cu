@@ -1076,6 +1076,7 @@ __device__ __noinline__ void write_move_list(const CallState& C, int lane, uint1
 
 // Outputs of one call, written by ONE warp from the call's shared-memory mask: the coalesced bit-packed
 // mask, the ascending move list, the count and the status word.
+template <int MODE = 0>   // 0: decided at run time; 1: no move list (code of the list writer dropped); 2: move list wanted
 __device__ __forceinline__ void write_call_outputs(CallState& C, int i, int lane, uint32_t* __restrict__ mask_bits,
                                                    uint16_t* __restrict__ moves, int moves_cap,
                                                    uint16_t* __restrict__ n_moves, uint32_t* __restrict__ status,
@@ -1092,7 +1093,7 @@ __device__ __forceinline__ void write_call_outputs(CallState& C, int i, int lane
     }
     // lane owns 12 consecutive words (the last lanes fewer): counts -> prefix -> ordered writes
     const int w0 = lane * 12;
-    const bool want_list = compact != nullptr || moves != nullptr;
+    const bool want_list = MODE == 0 ? (compact != nullptr || moves != nullptr) : (MODE == 2);
     int cnt = 0;
     uint32_t* gm = mask_bits ? mask_bits + (size_t)i * TRL_MASK_WORDS : nullptr;
 #pragma unroll 1
@@ -1117,7 +1118,7 @@ __device__ __forceinline__ void write_call_outputs(CallState& C, int i, int lane
         C.lbase[lane] = (uint16_t)(incl - cnt);
         __syncwarp();
     }
-    if (compact) {
+    if (want_list && compact) {
         unsigned long long off = 0;
         if (lane == 0) off = atomicAdd(compact_total, (unsigned long long)total);
         off = __shfl_sync(0xffffffffu, off, 0);
@@ -1125,7 +1126,7 @@ __device__ __forceinline__ void write_call_outputs(CallState& C, int i, int lane
         else write_move_list(C, lane, compact + off, 0x7fffffff);
         if (lane == 0) offsets[i] = off;
     }
-    if (moves) {
+    if (want_list && moves) {
         write_move_list(C, lane, moves + (size_t)i * moves_cap, moves_cap);
         if (total > moves_cap) st |= TRL_ST_MOVES_TRUNC;
     }
@@ -1345,6 +1346,7 @@ struct RowsWarp {
     CallState C;
 };
 
+template <bool WANT_LIST>   // two instantiations: every instruction less in this kernel is instruction-cache room
 __global__ void __launch_bounds__(kRowsWarps * 32, TRL_ROWS_MIN_BLOCKS)
 movegen_rows_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restrict__ cur,
                     const uint8_t* __restrict__ alt, const TrlGame* __restrict__ games,
@@ -1379,7 +1381,7 @@ movegen_rows_kernel(const uint16_t* __restrict__ boards, const uint8_t* __restri
             return;
         }
     }
-    write_call_outputs(C, i, lane, mask_bits, moves, moves_cap, n_moves, status, compact, compact_cap, compact_total, offsets);
+    write_call_outputs<WANT_LIST ? 2 : 1>(C, i, lane, mask_bits, moves, moves_cap, n_moves, status, compact, compact_cap, compact_total, offsets);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1627,8 +1629,10 @@ int trl_launch_movegen_warp(const uint16_t* boards, const uint8_t* cur, const ui
         if (!rc) rc = trl_check(cudaFuncSetAttribute(movegen_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_warp));
         if (!rc) rc = trl_check(cudaFuncSetAttribute(movegen_solo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solo));
         if (!rc) rc = trl_check(cudaFuncSetAttribute(movegen_solo_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        if (!rc) rc = trl_check(cudaFuncSetAttribute(movegen_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
-        if (!rc) rc = trl_check(cudaFuncSetAttribute(movegen_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        if (!rc) rc = trl_check(cudaFuncSetAttribute(movegen_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+        if (!rc) rc = trl_check(cudaFuncSetAttribute(movegen_rows_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        if (!rc) rc = trl_check(cudaFuncSetAttribute(movegen_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+        if (!rc) rc = trl_check(cudaFuncSetAttribute(movegen_rows_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         if (rc) return rc;
         configured = true;
     }
@@ -1642,9 +1646,14 @@ int trl_launch_movegen_warp(const uint16_t* boards, const uint8_t* cur, const ui
     if (form == 2) {
         int rc = trl_check(cudaMemsetAsync(scratch, 0, sizeof(uint32_t), stream));
         if (rc) return rc;
-        movegen_rows_kernel<<<(n + kRowsWarps - 1) / kRowsWarps, kRowsWarps * 32, smem_rows, stream>>>(
-            boards, cur, alt, games, index, n, mask_bits, moves, moves_cap, n_moves, status, compact, compact_cap,
-            compact_total, offsets, (int32_t*)(scratch + 16), scratch);
+        if (moves || compact)
+            movegen_rows_kernel<true><<<(n + kRowsWarps - 1) / kRowsWarps, kRowsWarps * 32, smem_rows, stream>>>(
+                boards, cur, alt, games, index, n, mask_bits, moves, moves_cap, n_moves, status, compact, compact_cap,
+                compact_total, offsets, (int32_t*)(scratch + 16), scratch);
+        else
+            movegen_rows_kernel<false><<<(n + kRowsWarps - 1) / kRowsWarps, kRowsWarps * 32, smem_rows, stream>>>(
+                boards, cur, alt, games, index, n, mask_bits, moves, moves_cap, n_moves, status, compact, compact_cap,
+                compact_total, offsets, (int32_t*)(scratch + 16), scratch);
         rc = trl_check(cudaGetLastError());
         if (rc) return rc;
         const int blocks = min(8 * n_sm, (n + kSoloWarps - 1) / kSoloWarps);
