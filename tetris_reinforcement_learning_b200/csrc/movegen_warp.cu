@@ -1,32 +1,41 @@
-// movegen_warp.cu — warp-cooperative legal-placement enumeration (one WARP per piece search).
+// movegen_warp.cu — warp-cooperative legal-placement enumeration.
 //
 // Same operator and the same bit-exact contract as movegen.cu (reference
 // move_generation.get_move_matrix(player, 'convolutional'), move_generation.py:77-149, 325-528,
 // 650-749, including the FIFO-order dependent choice between the two T-spin plane groups, SURVEY
-// 0.6 / A.2), re-organised so that a search runs in a few thousand warp instructions instead of
-// ~10^5 dependent thread instructions:
+// 0.6 / A.2).  Two search forms and three ways to launch them:
 //
-//   * a call (board, current piece, hold-or-next piece) is two warps, one per piece type; a block
-//     of 8 warps owns 4 calls.  All search state lives in shared memory:
+//   search_piece_rows   the row-parallel CLOSURE search (the common case): what the reference's queue
+//                       computes is a closure that does not depend on the queue order, so it is run as a
+//                       fix point on register-resident bit planes, lane = validity row, all four rotations
+//                       at once; t_order_decide settles the one order-dependent output (the used-last-kick
+//                       flag of T cells that received both flag values) from the structure of the queue where
+//                       it can, and says "undecided" where it cannot;
+//   search_piece_fifo   the exact FIFO search (round 1's kernel body, the specification of the T flags):
 //       vv[rot][row]  low 16 bits = validity row, high 16 bits = visited row     (4 x 46 words)
 //       fu[rot][row]  T: low 16 bits = flagged, high 16 bits = used-last-kick; other pieces: low 16
 //                     bits = "already queued" (de-duplicates queue entries; order is irrelevant for them)
 //       fifo[768]     the exploration queue (ring), entries (mx, my, rot, roc, ulk) as in movegen.cu
-//   * the queue is consumed 32 entries at a time: every lane tests one entry (stuck? visited?),
-//     a ballot finds the first entry that starts a flood fill, the entries before it only
-//     produce their "arrived by a kick and stuck" emission (move_generation.py:384-394);
-//   * the flood fill of one rotation is a serial scan over rows whose horizontal expansion is an
-//     O(1) carry-propagation trick (open + seed), not a fix-point loop;
-//   * kicks are evaluated for ALL edge cells of ALL rows of the fill at once: lane = row, bit =
-//     column, one AND/shift per (kick direction, kick index) against the target rotation's
-//     validity row ("first valid kick wins" = a running `remaining` mask, :443-481);
-//   * new queue entries are appended in the reference's order (row, column LSB->MSB, direction)
-//     with a warp prefix sum over per-row counts, so FIFO order — and with it the T-spin plane —
-//     is reproduced exactly.  "Last flagged emission wins" (:671-677) is order dependent only when
-//     emissions with different used-last-kick flags hit the same cell: the common case (all equal)
-//     is applied with shared-memory atomics, the mixed case serially in reference order;
-//   * the answer placed = visited & ~valid[row+1] is OR-ed into a per-call bit mask in shared
-//     memory, written out coalesced, and scanned into the ascending move list (= np.argwhere order).
+//     * the queue is consumed 32 entries at a time: every lane tests one entry (stuck? visited?),
+//       a ballot finds the first entry that starts a flood fill, the entries before it only
+//       produce their "arrived by a kick and stuck" emission (move_generation.py:384-394);
+//     * the flood fill of one rotation is a serial scan over rows whose horizontal expansion is an
+//       O(1) carry-propagation trick (open + seed), not a fix-point loop;
+//     * kicks are evaluated for ALL edge cells of ALL rows of the fill at once: lane = row, bit =
+//       column, one AND/shift per (kick direction, kick index) against the target rotation's
+//       validity row ("first valid kick wins" = a running `remaining` mask, :443-481);
+//     * new queue entries are appended in the reference's order (row, column LSB->MSB, direction)
+//       with a warp prefix sum over per-row counts, so FIFO order — and with it the T-spin plane —
+//       is reproduced exactly.  "Last flagged emission wins" (:671-677) is order dependent only when
+//       emissions with different used-last-kick flags hit the same cell: the common case (all equal)
+//       is applied with shared-memory atomics, the mixed case serially in reference order.
+//
+//   movegen_warp_kernel   two warps per call, one per piece type (latency form: self-play batches);
+//   movegen_solo_kernel   one warp per call; also the clean-up pass of the two-pass form;
+//   movegen_rows_kernel   the closure search alone, undecided calls appended to a list (throughput form: the
+//                         multi-million-call sweep); movegen_list_kernel is the enumeration inside a self-play step.
+// In every form the answer placed = visited & ~valid[row+1] is OR-ed into a per-call bit mask in shared
+// memory, written out coalesced, and turned into the ascending move list (= np.argwhere order).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
